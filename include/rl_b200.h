@@ -1,0 +1,341 @@
+/*
+ * rl_b200.h -- C ABI of the B200-native trace/plot/gather/tonemap engine.
+ *
+ * This is the drop-in boundary for the hot path of ruuda/robigo-luculenta:
+ * the four pipeline "units" that app.rs / task_scheduler.rs drive.  The
+ * reference has no FFI of its own (one binary crate of private modules), so
+ * each entry point below names the Rust inherent method it replaces; thin
+ * Rust shims with the same type names, methods and pub fields call these
+ * (see INTEGRATION.md for the shim source a maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *   - every function returns int: RL_OK (0) or a negative rl_status; the
+ *     message for the last failure on the calling thread is rl_last_error().
+ *     The reference panics on failure (app.rs:107,163; gather_unit.rs:69-70),
+ *     the Rust shim turns non-zero into `expect`;
+ *   - a handle is bound to the CUDA device current at creation time and owns
+ *     one stream; distinct handles may be driven from distinct host threads
+ *     concurrently (the scheduler's contract, app.rs:104-109), one handle is
+ *     never used from two threads at once;
+ *   - host-facing byte layouts equal the reference's: MappedPhoton is
+ *     4 x f32 (trace_unit.rs:23-37), a tristimulus buffer is packed
+ *     3 x f32 per pixel, row-major (vector3.rs:20-25, plot_unit.rs:80-83),
+ *     an image is packed RGB8 (tonemap_unit.rs:30,95-97);
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with RL_ERR_CUDA.
+ */
+#ifndef RL_B200_H
+#define RL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RL_ABI_VERSION 1
+
+/* trace_unit.rs:67 -- photons per TraceUnit batch (1024 under cfg(test), :70) */
+#define RL_BATCH_PHOTONS (1024u * 512u)
+#define RL_TEST_BATCH_PHOTONS 1024u
+
+typedef enum rl_status {
+    RL_OK = 0,
+    RL_ERR_INVALID = -1,     /* bad argument / malformed descriptor          */
+    RL_ERR_UNSUPPORTED = -2, /* descriptor uses a shape the engine lacks     */
+    RL_ERR_CUDA = -3,        /* CUDA runtime failure, or no device           */
+    RL_ERR_IO = -4,          /* buffer.raw could not be read / written       */
+    RL_ERR_NOMEM = -5
+} rl_status;
+
+/* ------------------------------------------------------------------ PODs */
+
+typedef struct rl_vec3 { float x, y, z; } rl_vec3;        /* vector3.rs:20-25   */
+typedef struct rl_quat { float x, y, z, w; } rl_quat;     /* quaternion.rs:19-25 */
+
+/* trace_unit.rs:23-37 (add #[repr(C)] in the shim) */
+typedef struct rl_mapped_photon {
+    float x;            /* screen x in [-1, 1]                       */
+    float y;            /* screen y in [-1/aspect, 1/aspect]         */
+    float probability;  /* path contribution                         */
+    float wavelength;   /* nm, [380, 780]                            */
+} rl_mapped_photon;
+
+/*
+ * A surface node is the state of one reference geometry struct after its
+ * constructor ran (geometry.rs); compound nodes reference two children by
+ * index into the same node array (geometry.rs:361-407).  Leaves of a compound
+ * must be half-spaces (the only Surface + Volume type the built-in scene
+ * combines, geometry.rs:409-416).
+ */
+typedef enum rl_surface_kind {
+    RL_SURFACE_PLANE = 1,      /* geometry.rs:35-87    a = normal, b = offset                    */
+    RL_SURFACE_HALFSPACE = 2,  /* geometry.rs:90-128   a = normal (points outside), b = offset   */
+    RL_SURFACE_CIRCLE = 3,     /* geometry.rs:130-184  a = normal, b = position, s = radius^2    */
+    RL_SURFACE_SPHERE = 4,     /* geometry.rs:186-267  a = position, s = radius^2                */
+    RL_SURFACE_PARABOLOID = 5, /* geometry.rs:269-358  a = offset, b = normal, c = focal_point   */
+    RL_SURFACE_COMPOUND = 6    /* geometry.rs:361-407  child[0] = surface1, child[1] = surface2  */
+} rl_surface_kind;
+
+typedef struct rl_surface {
+    uint32_t kind;
+    rl_vec3 a;
+    rl_vec3 b;
+    rl_vec3 c;
+    float s;
+    uint32_t child[2];
+} rl_surface;
+
+typedef enum rl_material_kind {
+    RL_MATERIAL_BLACKBODY = 1,        /* emissive, material.rs:77-105   p0 = temperature, p1 = normalisation_factor */
+    RL_MATERIAL_DIFFUSE_GREY = 2,     /* material.rs:109-130            p0 = reflectance                            */
+    RL_MATERIAL_DIFFUSE_COLOURED = 3, /* material.rs:134-168            p0 = reflectance, p1 = wavelength, p2 = deviation */
+    RL_MATERIAL_GLOSSY_MIRROR = 4,    /* material.rs:171-196            p0 = glossiness                             */
+    RL_MATERIAL_SF10_GLASS = 5,       /* material.rs:199-261                                                         */
+    RL_MATERIAL_SOAP_BUBBLE = 6       /* material.rs:265-306                                                         */
+} rl_material_kind;
+
+typedef struct rl_material {
+    uint32_t kind;
+    float p0, p1, p2;
+} rl_material;
+
+/* object.rs:20-31; list order is significant (scene.rs:51: first wins ties) */
+typedef struct rl_object {
+    uint32_t surface;  /* index of the object's root node in surfaces[] */
+    rl_material material;
+} rl_object;
+
+/* camera.rs:21-44 */
+typedef struct rl_camera {
+    rl_vec3 position;
+    float field_of_view;
+    float focal_distance;
+    float depth_of_field;
+    float chromatic_abberation;
+    rl_quat orientation;
+} rl_camera;
+
+/*
+ * scene.rs:34 holds `fn(f32) -> Camera`, which cannot cross an FFI.  The two
+ * camera models the engine evaluates per photon on the device:
+ *   STATIC : `fixed` for every t.
+ *   ORBIT  : the closed form of make_camera (app.rs:327-357):
+ *              phi      = PI * (phi_base   + phi_rate   * t)
+ *              alpha    = PI * (alpha_base + alpha_rate * t)
+ *              distance = distance_base + distance_rate * t
+ *              position = (cos a * sin p, cos a * cos p, sin a) * distance
+ *              orientation = rot(0,0,-1, phi + PI) * rot(1,0,0, -alpha)
+ *              focal_distance = distance * focal_factor
+ *            field_of_view / depth_of_field / chromatic_abberation from `fixed`.
+ */
+typedef enum rl_camera_kind { RL_CAMERA_STATIC = 1, RL_CAMERA_ORBIT = 2 } rl_camera_kind;
+
+typedef struct rl_camera_model {
+    uint32_t kind;
+    rl_camera fixed;
+    float phi_base, phi_rate;
+    float alpha_base, alpha_rate;
+    float distance_base, distance_rate;
+    float focal_factor;
+} rl_camera_model;
+
+/* scene.rs:23-36 flattened: what a `describe()` pass over Scene emits */
+typedef struct rl_scene_desc {
+    const rl_surface *surfaces;
+    uint32_t n_surfaces;
+    const rl_object *objects;
+    uint32_t n_objects;
+    rl_camera_model camera;
+} rl_scene_desc;
+
+/* --------------------------------------------------------------- handles */
+
+typedef struct rl_scene rl_scene;
+typedef struct rl_trace_unit rl_trace_unit;
+typedef struct rl_plot_unit rl_plot_unit;
+typedef struct rl_gather_unit rl_gather_unit;
+typedef struct rl_tonemap_unit rl_tonemap_unit;
+
+/* ------------------------------------------------------------- library   */
+
+int rl_abi_version(void);
+/* Message of the last failure on this thread ("" if none). */
+const char *rl_last_error(void);
+/* Number of visible CUDA devices (0 when there is none); never fails. */
+int rl_device_count(void);
+/* Kernels launched by this library since load / since the last reset. */
+uint64_t rl_kernel_launch_count(void);
+void rl_kernel_launch_count_reset(void);
+
+/* ---------------------------------------------------------------- scene  */
+
+/* Replaces Arc<Scene> (app.rs:63): validates the descriptor, uploads the
+ * primitive / material tables and the camera model to the current device. */
+int rl_scene_create(const rl_scene_desc *desc, rl_scene **out);
+int rl_scene_destroy(rl_scene *scene);
+
+/* ----------------------------------------------------------- TraceUnit   */
+
+/* TraceUnit::new (trace_unit.rs:64-78).  `seed` keys the counter-based RNG
+ * that stands in for rand::random (monte_carlo.rs:22-28 is unseeded). */
+int rl_trace_unit_create(uint64_t id, uint32_t width, uint32_t height, uint64_t seed,
+                         rl_trace_unit **out);
+int rl_trace_unit_destroy(rl_trace_unit *unit);
+/* Photons per render() call; default RL_BATCH_PHOTONS (trace_unit.rs:67). */
+int rl_trace_unit_set_batch_size(rl_trace_unit *unit, uint64_t n_photons);
+/* Bind the unit to a caller-owned cudaStream_t (NULL = its own stream). */
+int rl_trace_unit_set_stream(rl_trace_unit *unit, void *cuda_stream);
+/* TraceUnit::render (trace_unit.rs:151-168).  Photon ids of the batch are
+ * taken from a process-wide batch counter, so the union of photons over any
+ * schedule of B render() calls is ids [0, B * batch).  If `out` is non-NULL
+ * it receives batch_size records (the shim's `mapped_photons` Vec) and the
+ * call blocks; with NULL the records stay on the device for plot_device. */
+int rl_trace_unit_render(rl_trace_unit *unit, const rl_scene *scene, rl_mapped_photon *out);
+/* Same, for an explicit photon-id range [first_photon, first_photon + n). */
+int rl_trace_unit_render_range(rl_trace_unit *unit, const rl_scene *scene,
+                               uint64_t first_photon, uint64_t n_photons,
+                               rl_mapped_photon *out);
+/* Fused path: trace [first, first+n) and splat straight into `plot`'s device
+ * accumulator; no MappedPhoton record round-trip (trace_unit.rs:151-168 +
+ * plot_unit.rs:87-95 in one kernel).  Asynchronous on the trace unit's stream;
+ * the plot unit observes it through an event. */
+int rl_trace_unit_render_fused(rl_trace_unit *unit, const rl_scene *scene, rl_plot_unit *plot,
+                               uint64_t first_photon, uint64_t n_photons);
+/* Rays traced (= Scene::intersect calls, scene.rs:39) by this unit so far. */
+int rl_trace_unit_ray_count(rl_trace_unit *unit, uint64_t *out_rays);
+int rl_trace_unit_sync(rl_trace_unit *unit);
+/* Reset the process-wide batch counter used by rl_trace_unit_render. */
+void rl_trace_batch_counter_reset(uint64_t next_batch);
+
+/* ------------------------------------------------------------ PlotUnit   */
+
+/* PlotUnit::new (plot_unit.rs:43-53) */
+int rl_plot_unit_create(uint64_t id, uint32_t width, uint32_t height, rl_plot_unit **out);
+int rl_plot_unit_destroy(rl_plot_unit *unit);
+int rl_plot_unit_set_stream(rl_plot_unit *unit, void *cuda_stream);
+/* PlotUnit::plot (plot_unit.rs:87-95) on a host slice of photons. */
+int rl_plot_unit_plot(rl_plot_unit *unit, const rl_mapped_photon *photons, uint64_t n);
+/* PlotUnit::plot on the records a trace unit left on the device. */
+int rl_plot_unit_plot_device(rl_plot_unit *unit, rl_trace_unit *trace);
+/* PlotUnit::clear (plot_unit.rs:98-102) */
+int rl_plot_unit_clear(rl_plot_unit *unit);
+/* Copy out `tristimulus_buffer` (plot_unit.rs:34): width*height*3 floats. */
+int rl_plot_unit_download(rl_plot_unit *unit, float *xyz);
+/* Device address of the accumulator: width*height pixels of 4 floats
+ * (X, Y, Z, 0), for zero-copy views (NCCL reduce, peer access). */
+int rl_plot_unit_device_buffer(rl_plot_unit *unit, void **out_ptr, size_t *out_bytes);
+int rl_plot_unit_sync(rl_plot_unit *unit);
+
+/* ---------------------------------------------------------- GatherUnit   */
+
+/* GatherUnit::new (gather_unit.rs:35-46).  `resume_path` NULL = start from
+ * zero; otherwise the file is read like gather_unit.rs:81-92 if it exists
+ * (the reference's fixed name is "buffer.raw"). */
+int rl_gather_unit_create(uint32_t width, uint32_t height, const char *resume_path,
+                          rl_gather_unit **out);
+int rl_gather_unit_destroy(rl_gather_unit *unit);
+int rl_gather_unit_set_stream(rl_gather_unit *unit, void *cuda_stream);
+/* GatherUnit::accumulate (gather_unit.rs:49-64) from a host tristimulus
+ * slice of width*height*3 floats. */
+int rl_gather_unit_accumulate(rl_gather_unit *unit, const float *xyz);
+/* accumulate(&plot.tristimulus_buffer) followed by plot.clear()
+ * (app.rs:145-148), fused in one pass over the plot unit's device buffer. */
+int rl_gather_unit_accumulate_plot(rl_gather_unit *unit, rl_plot_unit *plot, int clear_plot);
+/* Same Kahan step from `n_buffers` device accumulators in PlotUnit layout
+ * (4 floats per pixel); pointers may be peer-device memory mapped into this
+ * process -- the cross-GPU reduce fused into the gather. */
+int rl_gather_unit_accumulate_device(rl_gather_unit *unit, const void *const *xyzw_buffers,
+                                     uint32_t n_buffers);
+/* GatherUnit::save (gather_unit.rs:68-78): accumulator then compensation,
+ * 12 raw bytes per pixel each, no header -> 24*w*h bytes. */
+int rl_gather_unit_save(rl_gather_unit *unit, const char *path);
+/* GatherUnit::read (gather_unit.rs:81-92); a short file is not an error
+ * (read.rs:20-32), a missing file is RL_ERR_IO here. */
+int rl_gather_unit_load(rl_gather_unit *unit, const char *path);
+/* Copy out `tristimulus_buffer` (gather_unit.rs:26); compensation optional. */
+int rl_gather_unit_download(rl_gather_unit *unit, float *xyz, float *compensation_or_null);
+int rl_gather_unit_sync(rl_gather_unit *unit);
+
+/* --------------------------------------------------------- TonemapUnit   */
+
+/* TonemapUnit::new (tonemap_unit.rs:43-51) */
+int rl_tonemap_unit_create(uint32_t width, uint32_t height, rl_tonemap_unit **out);
+int rl_tonemap_unit_destroy(rl_tonemap_unit *unit);
+int rl_tonemap_unit_set_stream(rl_tonemap_unit *unit, void *cuda_stream);
+/* TonemapUnit::tonemap (tonemap_unit.rs:73-100) on a host slice; writes
+ * width*height*3 bytes to `rgb` (the shim's `rgb_buffer`). */
+int rl_tonemap_unit_tonemap(rl_tonemap_unit *unit, const float *xyz, uint8_t *rgb);
+/* tonemap(&gather.tristimulus_buffer) (app.rs:157) without the host trip. */
+int rl_tonemap_unit_tonemap_gather(rl_tonemap_unit *unit, rl_gather_unit *gather, uint8_t *rgb);
+/* The exposure (`max_intensity`, tonemap_unit.rs:55-69) of the last call. */
+int rl_tonemap_unit_last_exposure(rl_tonemap_unit *unit, float *out);
+
+/* ------------------------------------------------- host scene builders   */
+/*
+ * Host-side mirrors of the reference's constructors and of
+ * App::set_up_scene (app.rs:166-363) that emit descriptors.  They are input
+ * generators for tests and benchmarks, not part of the device path.
+ */
+typedef struct rl_scene_builder rl_scene_builder;
+
+typedef enum rl_builtin_scene {
+    RL_SCENE_C1_SPHERE_PLANE = 1,  /* 1 diffuse sphere + emissive plane, static camera     */
+    RL_SCENE_C2_BUILTIN = 2,       /* app.rs:166-363, 339 objects, orbit camera            */
+    RL_SCENE_C3_PRISM = 3,         /* SF10 prism + emissive circle + grey floor            */
+    RL_SCENE_C4_SPHERES = 4        /* 4096 random spheres (param = sphere count, 0 = 4096) */
+} rl_builtin_scene;
+
+int rl_scene_builder_create(rl_scene_builder **out);
+int rl_scene_builder_destroy(rl_scene_builder *b);
+int rl_scene_builder_builtin(rl_scene_builder *b, int which, uint32_t param);
+/* Primitive constructors; each returns the new surface node index (>= 0). */
+int rl_scene_builder_plane(rl_scene_builder *b, rl_vec3 normal, rl_vec3 offset);
+int rl_scene_builder_circle(rl_scene_builder *b, rl_vec3 normal, rl_vec3 position, float radius);
+int rl_scene_builder_sphere(rl_scene_builder *b, rl_vec3 position, float radius);
+int rl_scene_builder_paraboloid(rl_scene_builder *b, rl_vec3 normal, rl_vec3 offset,
+                                float focal_distance);
+int rl_scene_builder_prism(rl_scene_builder *b, rl_vec3 axis, rl_vec3 offset, float edge_length,
+                           float angle, float height);
+int rl_scene_builder_hexagonal_prism(rl_scene_builder *b, rl_vec3 axis, rl_vec3 offset,
+                                     float edge_length, float bevel_size, float angle,
+                                     float height);
+/* BlackBodyMaterial::new (material.rs:92-97) -> material record. */
+int rl_material_blackbody(float kelvins, float intensity, rl_material *out);
+/* Object::new (object.rs:35-42); returns the object index. */
+int rl_scene_builder_object(rl_scene_builder *b, uint32_t surface, rl_material material);
+int rl_scene_builder_camera(rl_scene_builder *b, const rl_camera_model *camera);
+/* Borrow the descriptor; valid until the builder changes or is destroyed. */
+int rl_scene_builder_desc(rl_scene_builder *b, rl_scene_desc *out);
+
+/* ------------------------------------------------------------- debugging */
+/*
+ * Probes that run single device functions of the path over arrays, so the
+ * parity tests can compare them with the oracle one function at a time.
+ */
+typedef struct rl_ray { rl_vec3 origin; rl_vec3 direction; float wavelength; float probability; } rl_ray; /* ray.rs:19-33 */
+typedef struct rl_hit {                 /* intersection.rs:19-32 + object index */
+    int32_t object;                     /* -1 = miss */
+    float distance;
+    rl_vec3 position, normal, tangent;
+} rl_hit;
+/* Scene::intersect (scene.rs:39-60) for n host rays. */
+int rl_debug_intersect(const rl_scene *scene, const rl_ray *rays, uint64_t n, rl_hit *out);
+/* Device math of the path: fn = 0 sin, 1 cos, 2 exp, 3 acos (f32);
+ * 4 = Planck `boltzmann` (material.rs:61-74) with in2 = temperature,
+ * 5 = SF10 index of refraction (material.rs:203-213). */
+int rl_debug_math(int fn, const float *in, const float *in2_or_null, uint64_t n, float *out);
+/* cie1931::get_tristimulus (cie1931.rs:20-48): out = 3 floats per input. */
+int rl_debug_tristimulus(const float *wavelengths, uint64_t n, float *out_xyz);
+/* Camera ray of photon ids [first, first+n): TraceUnit::render's draws +
+ * render_camera_ray up to camera.get_ray (trace_unit.rs:136-158). */
+int rl_debug_camera_rays(const rl_scene *scene, uint64_t seed, uint32_t width, uint32_t height,
+                         uint64_t first_photon, uint64_t n, rl_ray *out_rays,
+                         rl_mapped_photon *out_xy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RL_B200_H */

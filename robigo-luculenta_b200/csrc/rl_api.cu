@@ -1,0 +1,848 @@
+// rl_api.cu -- the extern "C" boundary (include/rl_b200.h): handles, scene
+// flattening, stream ordering between units.  No compute happens on the host;
+// without a CUDA device every compute entry point returns RL_ERR_CUDA.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rl_b200.h"
+#include "rl_kernels.h"
+
+using namespace rl;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string &msg) {
+    g_error = msg;
+    return code;
+}
+
+#define RL_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(RL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+
+std::atomic<uint64_t> g_next_batch{0};
+
+struct Device {
+    int index = 0;
+    int sm_count = 148;
+    size_t max_smem = 0;
+};
+
+int current_device(Device &d) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(RL_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    }
+    RL_CUDA(cudaGetDevice(&d.index));
+    RL_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.index));
+    int smem = 0;
+    RL_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.index));
+    d.max_smem = (size_t)smem;
+    return RL_OK;
+}
+
+// A stream owned by the handle unless the caller bound its own.
+struct StreamSlot {
+    cudaStream_t stream = nullptr;
+    bool owned = false;
+    cudaEvent_t event = nullptr;  // ordering point for other units
+
+    int create() {
+        RL_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        owned = true;
+        RL_CUDA(cudaEventCreateWithFlags(&event, cudaEventDisableTiming));
+        return RL_OK;
+    }
+    void bind(void *external) {
+        if (owned && stream) cudaStreamDestroy(stream);
+        if (external) { stream = (cudaStream_t)external; owned = false; }
+        else { cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking); owned = true; }
+    }
+    void destroy() {
+        if (owned && stream) cudaStreamDestroy(stream);
+        if (event) cudaEventDestroy(event);
+        stream = nullptr; event = nullptr;
+    }
+};
+
+// Make `later` wait for everything queued so far on `earlier`.
+int order_after(StreamSlot &earlier, StreamSlot &later) {
+    if (earlier.stream == later.stream) return RL_OK;
+    RL_CUDA(cudaEventRecord(earlier.event, earlier.stream));
+    RL_CUDA(cudaStreamWaitEvent(later.stream, earlier.event, 0));
+    return RL_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ handles
+struct rl_scene {
+    Device dev;
+    DevScene ds;
+    void *d_blob = nullptr;
+    void *d_materials = nullptr;
+    size_t smem = 0;
+};
+
+struct rl_trace_unit {
+    uint64_t id = 0;
+    uint32_t width = 0, height = 0;
+    uint64_t seed = 0;
+    uint64_t batch = RL_BATCH_PHOTONS;
+    Device dev;
+    StreamSlot ss;
+    rl_mapped_photon *d_records = nullptr;
+    uint64_t capacity = 0;
+    uint64_t n_valid = 0;  // records left on the device by the last render
+    unsigned long long *d_rays = nullptr;
+};
+
+struct rl_plot_unit {
+    uint64_t id = 0;
+    uint32_t width = 0, height = 0;
+    Device dev;
+    StreamSlot ss;
+    float4 *d_accum = nullptr;
+    float *d_packed = nullptr;
+    rl_mapped_photon *d_staging = nullptr;
+    uint64_t staging_capacity = 0;
+};
+
+struct rl_gather_unit {
+    uint32_t width = 0, height = 0;
+    Device dev;
+    StreamSlot ss;
+    float *d_acc = nullptr;
+    float *d_comp = nullptr;
+    float *d_staging = nullptr;
+};
+
+struct rl_tonemap_unit {
+    uint32_t width = 0, height = 0;
+    Device dev;
+    StreamSlot ss;
+    float *d_xyz = nullptr;
+    uint8_t *d_rgb = nullptr;
+    double *d_moments = nullptr;
+    float *d_exposure = nullptr;
+    float last_exposure = 0.0f;
+};
+
+// ------------------------------------------------------------ scene flatten
+namespace {
+
+struct Flat {
+    std::vector<float4> spheres, planes, paraboloids, leaves, compounds;
+    std::vector<uint32_t> ops, sphere_obj, plane_obj, paraboloid_obj, compound_obj;
+};
+
+float4 f4(rl_vec3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+float as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+// Emits the post-order program of a compound tree; returns false on a
+// malformed or unsupported tree.  [lo, hi) = leaf range of the subtree.
+bool emit_compound(const rl_scene_desc *d, uint32_t node, Flat &fl, uint32_t first_leaf, int depth,
+                   uint32_t &lo, uint32_t &hi) {
+    if (node >= d->n_surfaces || depth > 16) return false;
+    const rl_surface &s = d->surfaces[node];
+    if (s.kind == RL_SURFACE_HALFSPACE) {
+        uint32_t rel = (uint32_t)(fl.leaves.size() / 2) - first_leaf;
+        if (rel > 254) return false;
+        fl.leaves.push_back(f4(s.a, 0.f));
+        fl.leaves.push_back(f4(s.b, 0.f));
+        fl.ops.push_back(0u | (rel << 8));
+        lo = rel; hi = rel + 1;
+        return true;
+    }
+    if (s.kind != RL_SURFACE_COMPOUND) return false;
+    uint32_t lo1, hi1, lo2, hi2;
+    if (!emit_compound(d, s.child[0], fl, first_leaf, depth + 1, lo1, hi1)) return false;
+    if (!emit_compound(d, s.child[1], fl, first_leaf, depth + 1, lo2, hi2)) return false;
+    fl.ops.push_back(1u | (lo1 << 8) | (hi1 << 16) | (hi2 << 24));
+    lo = lo1; hi = hi2;
+    return true;
+}
+
+int max_stack(const std::vector<uint32_t> &ops, size_t first, size_t n) {
+    int sp = 0, mx = 0;
+    for (size_t i = 0; i < n; i++) {
+        if ((ops[first + i] & 3u) == 0u) sp++; else sp--;
+        if (sp > mx) mx = sp;
+    }
+    return mx;
+}
+
+template <class T>
+uint32_t append(std::vector<float4> &blob, const std::vector<T> &v) {
+    uint32_t off = (uint32_t)blob.size();
+    size_t bytes = v.size() * sizeof(T);
+    size_t vec4 = (bytes + 15) / 16;
+    blob.resize(blob.size() + vec4, make_float4(0.f, 0.f, 0.f, 0.f));
+    if (bytes) memcpy(blob.data() + off, v.data(), bytes);
+    return off;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rl_abi_version(void) { return RL_ABI_VERSION; }
+const char *rl_last_error(void) { return g_error.c_str(); }
+
+int rl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+uint64_t rl_kernel_launch_count(void) { return kernel_launches(); }
+void rl_kernel_launch_count_reset(void) { kernel_launches_reset(); }
+
+// -------------------------------------------------------------------- scene
+int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
+    if (!desc || !out) return fail(RL_ERR_INVALID, "rl_scene_create: null argument");
+    if ((!desc->surfaces && desc->n_surfaces) || (!desc->objects && desc->n_objects))
+        return fail(RL_ERR_INVALID, "rl_scene_create: null table");
+    if (desc->camera.kind != RL_CAMERA_STATIC && desc->camera.kind != RL_CAMERA_ORBIT)
+        return fail(RL_ERR_INVALID, "rl_scene_create: unknown camera kind");
+
+    Flat fl;
+    std::vector<float4> materials;
+    for (uint32_t i = 0; i < desc->n_objects; i++) {
+        const rl_object &o = desc->objects[i];
+        if (o.surface >= desc->n_surfaces) return fail(RL_ERR_INVALID, "object surface index out of range");
+        if (o.material.kind < RL_MATERIAL_BLACKBODY || o.material.kind > RL_MATERIAL_SOAP_BUBBLE)
+            return fail(RL_ERR_INVALID, "unknown material kind");
+        materials.push_back(make_float4(as_float(o.material.kind), o.material.p0, o.material.p1,
+                                        o.material.p2));
+        const rl_surface &s = desc->surfaces[o.surface];
+        switch (s.kind) {
+        case RL_SURFACE_SPHERE:
+            fl.spheres.push_back(f4(s.a, s.s));
+            fl.sphere_obj.push_back(i);
+            break;
+        case RL_SURFACE_PLANE:
+        case RL_SURFACE_HALFSPACE:
+        case RL_SURFACE_CIRCLE:
+            fl.planes.push_back(f4(s.a, as_float(s.kind)));
+            fl.planes.push_back(f4(s.b, s.s));
+            fl.plane_obj.push_back(i);
+            break;
+        case RL_SURFACE_PARABOLOID:
+            fl.paraboloids.push_back(f4(s.a, 0.f));
+            fl.paraboloids.push_back(f4(s.b, 0.f));
+            fl.paraboloids.push_back(f4(s.c, 0.f));
+            fl.paraboloid_obj.push_back(i);
+            break;
+        case RL_SURFACE_COMPOUND: {
+            uint32_t first_leaf = (uint32_t)(fl.leaves.size() / 2);
+            uint32_t first_op = (uint32_t)fl.ops.size();
+            uint32_t lo, hi;
+            if (!emit_compound(desc, o.surface, fl, first_leaf, 0, lo, hi))
+                return fail(RL_ERR_UNSUPPORTED,
+                            "compound surfaces must be trees of half-spaces (<= 255 leaves)");
+            uint32_t n_ops = (uint32_t)fl.ops.size() - first_op;
+            if (max_stack(fl.ops, first_op, n_ops) > RL_MAX_COMPOUND_STACK)
+                return fail(RL_ERR_UNSUPPORTED, "compound tree too deep");
+            fl.compounds.push_back(make_float4(as_float(first_leaf), as_float(hi - lo),
+                                               as_float(first_op), as_float(n_ops)));
+            fl.compounds.push_back(make_float4(0.f, 0.f, 0.f, -1.0f));  // no bound
+            fl.compound_obj.push_back(i);
+            break;
+        }
+        default:
+            return fail(RL_ERR_INVALID, "unknown surface kind");
+        }
+    }
+
+    rl_scene *sc = new (std::nothrow) rl_scene();
+    if (!sc) return fail(RL_ERR_NOMEM, "out of memory");
+    int rc = current_device(sc->dev);
+    if (rc != RL_OK) { delete sc; return rc; }
+
+    std::vector<float4> blob;
+    DevScene &ds = sc->ds;
+    memset(&ds, 0, sizeof(ds));
+    ds.off_spheres = append(blob, fl.spheres);          ds.n_spheres = (uint32_t)fl.spheres.size();
+    ds.off_planes = append(blob, fl.planes);            ds.n_planes = (uint32_t)fl.planes.size() / 2;
+    ds.off_paraboloids = append(blob, fl.paraboloids);  ds.n_paraboloids = (uint32_t)fl.paraboloids.size() / 3;
+    ds.off_leaves = append(blob, fl.leaves);            ds.n_leaves = (uint32_t)fl.leaves.size() / 2;
+    ds.off_compounds = append(blob, fl.compounds);      ds.n_compounds = (uint32_t)fl.compounds.size() / 2;
+    ds.off_ops = append(blob, fl.ops);                  ds.n_ops = (uint32_t)fl.ops.size();
+    ds.off_sphere_obj = append(blob, fl.sphere_obj);
+    ds.off_plane_obj = append(blob, fl.plane_obj);
+    ds.off_paraboloid_obj = append(blob, fl.paraboloid_obj);
+    ds.off_compound_obj = append(blob, fl.compound_obj);
+    if (blob.empty()) blob.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
+    ds.blob_vec4 = (uint32_t)blob.size();
+    ds.n_objects = desc->n_objects;
+    sc->smem = blob.size() * sizeof(float4);
+    if (sc->smem > sc->dev.max_smem) {
+        delete sc;
+        return fail(RL_ERR_UNSUPPORTED, "scene primitive tables exceed shared memory per CTA");
+    }
+
+    const rl_camera_model &cm = desc->camera;
+    DevCamera &c = ds.camera;
+    c.kind = cm.kind;
+    c.px = cm.fixed.position.x; c.py = cm.fixed.position.y; c.pz = cm.fixed.position.z;
+    c.field_of_view = cm.fixed.field_of_view;
+    c.focal_distance = cm.fixed.focal_distance;
+    c.depth_of_field = cm.fixed.depth_of_field;
+    c.chromatic_abberation = cm.fixed.chromatic_abberation;
+    c.qx = cm.fixed.orientation.x; c.qy = cm.fixed.orientation.y;
+    c.qz = cm.fixed.orientation.z; c.qw = cm.fixed.orientation.w;
+    c.phi_base = cm.phi_base; c.phi_rate = cm.phi_rate;
+    c.alpha_base = cm.alpha_base; c.alpha_rate = cm.alpha_rate;
+    c.distance_base = cm.distance_base; c.distance_rate = cm.distance_rate;
+    c.focal_factor = cm.focal_factor;
+
+    if (materials.empty()) materials.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
+    cudaError_t e = cudaMalloc(&sc->d_blob, blob.size() * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&sc->d_materials, materials.size() * sizeof(float4));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(sc->d_blob, blob.data(), blob.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(sc->d_materials, materials.data(), materials.size() * sizeof(float4),
+                       cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(sc->d_blob); cudaFree(sc->d_materials);
+        delete sc;
+        return fail(RL_ERR_CUDA, std::string("rl_scene_create: ") + cudaGetErrorString(e));
+    }
+    ds.blob = (const float4 *)sc->d_blob;
+    ds.materials = (const float4 *)sc->d_materials;
+    *out = sc;
+    return RL_OK;
+}
+
+int rl_scene_destroy(rl_scene *scene) {
+    if (!scene) return RL_OK;
+    cudaSetDevice(scene->dev.index);
+    cudaFree(scene->d_blob);
+    cudaFree(scene->d_materials);
+    delete scene;
+    return RL_OK;
+}
+
+// --------------------------------------------------------------- TraceUnit
+int rl_trace_unit_create(uint64_t id, uint32_t width, uint32_t height, uint64_t seed,
+                         rl_trace_unit **out) {
+    if (!out || width == 0 || height == 0) return fail(RL_ERR_INVALID, "rl_trace_unit_create: bad argument");
+    rl_trace_unit *u = new (std::nothrow) rl_trace_unit();
+    if (!u) return fail(RL_ERR_NOMEM, "out of memory");
+    u->id = id; u->width = width; u->height = height; u->seed = seed;
+    int rc = current_device(u->dev);
+    if (rc == RL_OK) rc = u->ss.create();
+    if (rc != RL_OK) { delete u; return rc; }
+    cudaError_t e = cudaMalloc(&u->d_rays, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(u->d_rays, 0, sizeof(unsigned long long));
+    if (e != cudaSuccess) { u->ss.destroy(); delete u; return fail(RL_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = u;
+    return RL_OK;
+}
+
+int rl_trace_unit_destroy(rl_trace_unit *u) {
+    if (!u) return RL_OK;
+    cudaSetDevice(u->dev.index);
+    if (u->ss.stream) cudaStreamSynchronize(u->ss.stream);
+    cudaFree(u->d_records);
+    cudaFree(u->d_rays);
+    u->ss.destroy();
+    delete u;
+    return RL_OK;
+}
+
+int rl_trace_unit_set_batch_size(rl_trace_unit *u, uint64_t n) {
+    if (!u || n == 0) return fail(RL_ERR_INVALID, "rl_trace_unit_set_batch_size: bad argument");
+    u->batch = n;
+    return RL_OK;
+}
+
+int rl_trace_unit_set_stream(rl_trace_unit *u, void *s) {
+    if (!u) return fail(RL_ERR_INVALID, "null unit");
+    cudaSetDevice(u->dev.index);
+    u->ss.bind(s);
+    return RL_OK;
+}
+
+static int ensure_records(rl_trace_unit *u, uint64_t n) {
+    if (u->capacity >= n) return RL_OK;
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    cudaFree(u->d_records);
+    u->d_records = nullptr; u->capacity = 0;
+    RL_CUDA(cudaMalloc(&u->d_records, n * sizeof(rl_mapped_photon)));
+    u->capacity = n;
+    return RL_OK;
+}
+
+int rl_trace_unit_render_range(rl_trace_unit *u, const rl_scene *scene, uint64_t first_photon,
+                               uint64_t n_photons, rl_mapped_photon *out) {
+    if (!u || !scene) return fail(RL_ERR_INVALID, "rl_trace_unit_render: null argument");
+    if (scene->dev.index != u->dev.index) return fail(RL_ERR_INVALID, "scene and unit on different devices");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    int rc = ensure_records(u, n_photons);
+    if (rc != RL_OK) return rc;
+    TraceLaunch p;
+    p.seed = u->seed; p.first_photon = first_photon; p.n_photons = n_photons;
+    p.width = u->width; p.height = u->height;
+    p.records = u->d_records; p.accum = nullptr; p.ray_counter = u->d_rays;
+    RL_CUDA(launch_trace(scene->ds, p, u->dev.sm_count, u->ss.stream));
+    u->n_valid = n_photons;
+    if (out) {
+        RL_CUDA(cudaMemcpyAsync(out, u->d_records, n_photons * sizeof(rl_mapped_photon),
+                                cudaMemcpyDeviceToHost, u->ss.stream));
+        RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    }
+    return RL_OK;
+}
+
+int rl_trace_unit_render(rl_trace_unit *u, const rl_scene *scene, rl_mapped_photon *out) {
+    if (!u) return fail(RL_ERR_INVALID, "null unit");
+    const uint64_t b = g_next_batch.fetch_add(1);
+    return rl_trace_unit_render_range(u, scene, b * u->batch, u->batch, out);
+}
+
+int rl_trace_unit_render_fused(rl_trace_unit *u, const rl_scene *scene, rl_plot_unit *plot,
+                               uint64_t first_photon, uint64_t n_photons) {
+    if (!u || !scene || !plot) return fail(RL_ERR_INVALID, "rl_trace_unit_render_fused: null argument");
+    if (scene->dev.index != u->dev.index || plot->dev.index != u->dev.index)
+        return fail(RL_ERR_INVALID, "scene, trace unit and plot unit must share a device");
+    if (plot->width != u->width || plot->height != u->height)
+        return fail(RL_ERR_INVALID, "trace and plot unit canvas sizes differ");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    int rc = order_after(plot->ss, u->ss);
+    if (rc != RL_OK) return rc;
+    TraceLaunch p;
+    p.seed = u->seed; p.first_photon = first_photon; p.n_photons = n_photons;
+    p.width = u->width; p.height = u->height;
+    p.records = nullptr; p.accum = plot->d_accum; p.ray_counter = u->d_rays;
+    RL_CUDA(launch_trace(scene->ds, p, u->dev.sm_count, u->ss.stream));
+    u->n_valid = 0;
+    return order_after(u->ss, plot->ss);
+}
+
+int rl_trace_unit_ray_count(rl_trace_unit *u, uint64_t *out_rays) {
+    if (!u || !out_rays) return fail(RL_ERR_INVALID, "null argument");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    unsigned long long v = 0;
+    RL_CUDA(cudaMemcpyAsync(&v, u->d_rays, sizeof(v), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    *out_rays = v;
+    return RL_OK;
+}
+
+int rl_trace_unit_sync(rl_trace_unit *u) {
+    if (!u) return fail(RL_ERR_INVALID, "null unit");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    return RL_OK;
+}
+
+void rl_trace_batch_counter_reset(uint64_t next_batch) { g_next_batch.store(next_batch); }
+
+// ---------------------------------------------------------------- PlotUnit
+int rl_plot_unit_create(uint64_t id, uint32_t width, uint32_t height, rl_plot_unit **out) {
+    if (!out || width == 0 || height == 0) return fail(RL_ERR_INVALID, "rl_plot_unit_create: bad argument");
+    rl_plot_unit *u = new (std::nothrow) rl_plot_unit();
+    if (!u) return fail(RL_ERR_NOMEM, "out of memory");
+    u->id = id; u->width = width; u->height = height;
+    int rc = current_device(u->dev);
+    if (rc == RL_OK) rc = u->ss.create();
+    if (rc != RL_OK) { delete u; return rc; }
+    const size_t n = (size_t)width * height;
+    cudaError_t e = cudaMalloc(&u->d_accum, n * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&u->d_packed, n * 3 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(u->d_accum, 0, n * sizeof(float4));
+    if (e != cudaSuccess) {
+        cudaFree(u->d_accum); cudaFree(u->d_packed); u->ss.destroy(); delete u;
+        return fail(RL_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = u;
+    return RL_OK;
+}
+
+int rl_plot_unit_destroy(rl_plot_unit *u) {
+    if (!u) return RL_OK;
+    cudaSetDevice(u->dev.index);
+    if (u->ss.stream) cudaStreamSynchronize(u->ss.stream);
+    cudaFree(u->d_accum); cudaFree(u->d_packed); cudaFree(u->d_staging);
+    u->ss.destroy();
+    delete u;
+    return RL_OK;
+}
+
+int rl_plot_unit_set_stream(rl_plot_unit *u, void *s) {
+    if (!u) return fail(RL_ERR_INVALID, "null unit");
+    cudaSetDevice(u->dev.index);
+    u->ss.bind(s);
+    return RL_OK;
+}
+
+int rl_plot_unit_plot(rl_plot_unit *u, const rl_mapped_photon *photons, uint64_t n) {
+    if (!u || (!photons && n)) return fail(RL_ERR_INVALID, "rl_plot_unit_plot: null argument");
+    if (n == 0) return RL_OK;
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    if (u->staging_capacity < n) {
+        RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+        cudaFree(u->d_staging);
+        u->d_staging = nullptr; u->staging_capacity = 0;
+        RL_CUDA(cudaMalloc(&u->d_staging, n * sizeof(rl_mapped_photon)));
+        u->staging_capacity = n;
+    }
+    RL_CUDA(cudaMemcpyAsync(u->d_staging, photons, n * sizeof(rl_mapped_photon),
+                            cudaMemcpyHostToDevice, u->ss.stream));
+    RL_CUDA(launch_splat(u->d_staging, n, u->d_accum, u->width, u->height, u->dev.sm_count,
+                         u->ss.stream));
+    // the caller may reuse `photons` as soon as we return
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    return RL_OK;
+}
+
+int rl_plot_unit_plot_device(rl_plot_unit *u, rl_trace_unit *trace) {
+    if (!u || !trace) return fail(RL_ERR_INVALID, "rl_plot_unit_plot_device: null argument");
+    if (u->dev.index != trace->dev.index) return fail(RL_ERR_INVALID, "units on different devices");
+    if (trace->n_valid == 0) return RL_OK;
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    int rc = order_after(trace->ss, u->ss);
+    if (rc != RL_OK) return rc;
+    RL_CUDA(launch_splat(trace->d_records, trace->n_valid, u->d_accum, u->width, u->height,
+                         u->dev.sm_count, u->ss.stream));
+    return order_after(u->ss, trace->ss);
+}
+
+int rl_plot_unit_clear(rl_plot_unit *u) {
+    if (!u) return fail(RL_ERR_INVALID, "null unit");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    RL_CUDA(cudaMemsetAsync(u->d_accum, 0, (size_t)u->width * u->height * sizeof(float4), u->ss.stream));
+    return RL_OK;
+}
+
+int rl_plot_unit_download(rl_plot_unit *u, float *xyz) {
+    if (!u || !xyz) return fail(RL_ERR_INVALID, "rl_plot_unit_download: null argument");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    const uint64_t n = (uint64_t)u->width * u->height;
+    RL_CUDA(launch_pack_xyz(u->d_accum, u->d_packed, n, u->ss.stream));
+    RL_CUDA(cudaMemcpyAsync(xyz, u->d_packed, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    return RL_OK;
+}
+
+int rl_plot_unit_device_buffer(rl_plot_unit *u, void **out_ptr, size_t *out_bytes) {
+    if (!u || !out_ptr) return fail(RL_ERR_INVALID, "null argument");
+    *out_ptr = u->d_accum;
+    if (out_bytes) *out_bytes = (size_t)u->width * u->height * sizeof(float4);
+    return RL_OK;
+}
+
+int rl_plot_unit_sync(rl_plot_unit *u) {
+    if (!u) return fail(RL_ERR_INVALID, "null unit");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    return RL_OK;
+}
+
+// -------------------------------------------------------------- GatherUnit
+int rl_gather_unit_create(uint32_t width, uint32_t height, const char *resume_path,
+                          rl_gather_unit **out) {
+    if (!out || width == 0 || height == 0) return fail(RL_ERR_INVALID, "rl_gather_unit_create: bad argument");
+    rl_gather_unit *u = new (std::nothrow) rl_gather_unit();
+    if (!u) return fail(RL_ERR_NOMEM, "out of memory");
+    u->width = width; u->height = height;
+    int rc = current_device(u->dev);
+    if (rc == RL_OK) rc = u->ss.create();
+    if (rc != RL_OK) { delete u; return rc; }
+    const size_t bytes = (size_t)width * height * 3 * sizeof(float);
+    cudaError_t e = cudaMalloc(&u->d_acc, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&u->d_comp, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&u->d_staging, bytes);
+    if (e == cudaSuccess) e = cudaMemset(u->d_acc, 0, bytes);
+    if (e == cudaSuccess) e = cudaMemset(u->d_comp, 0, bytes);
+    if (e != cudaSuccess) {
+        cudaFree(u->d_acc); cudaFree(u->d_comp); cudaFree(u->d_staging); u->ss.destroy(); delete u;
+        return fail(RL_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (resume_path) {
+        // gather_unit.rs:43,82: resume silently iff the file exists
+        FILE *f = fopen(resume_path, "rb");
+        if (f) {
+            fclose(f);
+            rc = rl_gather_unit_load(u, resume_path);
+            if (rc != RL_OK) { rl_gather_unit_destroy(u); return rc; }
+        }
+    }
+    *out = u;
+    return RL_OK;
+}
+
+int rl_gather_unit_destroy(rl_gather_unit *u) {
+    if (!u) return RL_OK;
+    cudaSetDevice(u->dev.index);
+    if (u->ss.stream) cudaStreamSynchronize(u->ss.stream);
+    cudaFree(u->d_acc); cudaFree(u->d_comp); cudaFree(u->d_staging);
+    u->ss.destroy();
+    delete u;
+    return RL_OK;
+}
+
+int rl_gather_unit_set_stream(rl_gather_unit *u, void *s) {
+    if (!u) return fail(RL_ERR_INVALID, "null unit");
+    cudaSetDevice(u->dev.index);
+    u->ss.bind(s);
+    return RL_OK;
+}
+
+int rl_gather_unit_accumulate(rl_gather_unit *u, const float *xyz) {
+    if (!u || !xyz) return fail(RL_ERR_INVALID, "rl_gather_unit_accumulate: null argument");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    const uint64_t n = (uint64_t)u->width * u->height;
+    RL_CUDA(cudaMemcpyAsync(u->d_staging, xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, u->ss.stream));
+    RL_CUDA(launch_gather(u->d_acc, u->d_comp, nullptr, 0, u->d_staging, nullptr, n, u->dev.sm_count,
+                          u->ss.stream));
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    return RL_OK;
+}
+
+int rl_gather_unit_accumulate_plot(rl_gather_unit *u, rl_plot_unit *plot, int clear_plot) {
+    if (!u || !plot) return fail(RL_ERR_INVALID, "rl_gather_unit_accumulate_plot: null argument");
+    if (u->dev.index != plot->dev.index) return fail(RL_ERR_INVALID, "units on different devices");
+    if (u->width != plot->width || u->height != plot->height)
+        return fail(RL_ERR_INVALID, "gather and plot unit canvas sizes differ");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    int rc = order_after(plot->ss, u->ss);
+    if (rc != RL_OK) return rc;
+    const float4 *src = plot->d_accum;
+    RL_CUDA(launch_gather(u->d_acc, u->d_comp, &src, 1, nullptr, clear_plot ? plot->d_accum : nullptr,
+                          (uint64_t)u->width * u->height, u->dev.sm_count, u->ss.stream));
+    return order_after(u->ss, plot->ss);
+}
+
+int rl_gather_unit_accumulate_device(rl_gather_unit *u, const void *const *bufs, uint32_t n_buffers) {
+    if (!u || (!bufs && n_buffers)) return fail(RL_ERR_INVALID, "rl_gather_unit_accumulate_device: null argument");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    const uint64_t n = (uint64_t)u->width * u->height;
+    for (uint32_t i = 0; i < n_buffers; i += 8) {
+        const float4 *srcs[8];
+        uint32_t k = n_buffers - i < 8 ? n_buffers - i : 8;
+        for (uint32_t j = 0; j < k; j++) srcs[j] = (const float4 *)bufs[i + j];
+        RL_CUDA(launch_gather(u->d_acc, u->d_comp, srcs, k, nullptr, nullptr, n, u->dev.sm_count,
+                              u->ss.stream));
+    }
+    return RL_OK;
+}
+
+int rl_gather_unit_save(rl_gather_unit *u, const char *path) {
+    if (!u || !path) return fail(RL_ERR_INVALID, "rl_gather_unit_save: null argument");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    const size_t n = (size_t)u->width * u->height * 3;
+    std::vector<float> host(2 * n);
+    RL_CUDA(cudaMemcpyAsync(host.data(), u->d_acc, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(cudaMemcpyAsync(host.data() + n, u->d_comp, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(RL_ERR_IO, std::string("failed to open file ") + path);
+    size_t w = fwrite(host.data(), sizeof(float), 2 * n, f);
+    int c = fclose(f);
+    if (w != 2 * n || c != 0) return fail(RL_ERR_IO, "failed to write raw buffer");
+    return RL_OK;
+}
+
+int rl_gather_unit_load(rl_gather_unit *u, const char *path) {
+    if (!u || !path) return fail(RL_ERR_INVALID, "rl_gather_unit_load: null argument");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    const size_t n = (size_t)u->width * u->height * 3;
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(RL_ERR_IO, std::string("failed to open file ") + path);
+    // read.rs:20-32: a short file is not an error; what was not read keeps
+    // its current value.
+    std::vector<float> host(2 * n);
+    RL_CUDA(cudaMemcpyAsync(host.data(), u->d_acc, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(cudaMemcpyAsync(host.data() + n, u->d_comp, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    size_t got = fread(host.data(), 1, 2 * n * sizeof(float), f);
+    (void)got;
+    fclose(f);
+    RL_CUDA(cudaMemcpyAsync(u->d_acc, host.data(), n * sizeof(float), cudaMemcpyHostToDevice, u->ss.stream));
+    RL_CUDA(cudaMemcpyAsync(u->d_comp, host.data() + n, n * sizeof(float), cudaMemcpyHostToDevice, u->ss.stream));
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    return RL_OK;
+}
+
+int rl_gather_unit_download(rl_gather_unit *u, float *xyz, float *comp) {
+    if (!u || !xyz) return fail(RL_ERR_INVALID, "rl_gather_unit_download: null argument");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    const size_t bytes = (size_t)u->width * u->height * 3 * sizeof(float);
+    RL_CUDA(cudaMemcpyAsync(xyz, u->d_acc, bytes, cudaMemcpyDeviceToHost, u->ss.stream));
+    if (comp) RL_CUDA(cudaMemcpyAsync(comp, u->d_comp, bytes, cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    return RL_OK;
+}
+
+int rl_gather_unit_sync(rl_gather_unit *u) {
+    if (!u) return fail(RL_ERR_INVALID, "null unit");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    return RL_OK;
+}
+
+// ------------------------------------------------------------- TonemapUnit
+int rl_tonemap_unit_create(uint32_t width, uint32_t height, rl_tonemap_unit **out) {
+    if (!out || width == 0 || height == 0) return fail(RL_ERR_INVALID, "rl_tonemap_unit_create: bad argument");
+    rl_tonemap_unit *u = new (std::nothrow) rl_tonemap_unit();
+    if (!u) return fail(RL_ERR_NOMEM, "out of memory");
+    u->width = width; u->height = height;
+    int rc = current_device(u->dev);
+    if (rc == RL_OK) rc = u->ss.create();
+    if (rc != RL_OK) { delete u; return rc; }
+    const size_t n = (size_t)width * height;
+    cudaError_t e = cudaMalloc(&u->d_xyz, n * 3 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&u->d_rgb, n * 3);
+    if (e == cudaSuccess) e = cudaMalloc(&u->d_moments, 2 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&u->d_exposure, sizeof(float));
+    if (e != cudaSuccess) {
+        cudaFree(u->d_xyz); cudaFree(u->d_rgb); cudaFree(u->d_moments); cudaFree(u->d_exposure);
+        u->ss.destroy(); delete u;
+        return fail(RL_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = u;
+    return RL_OK;
+}
+
+int rl_tonemap_unit_destroy(rl_tonemap_unit *u) {
+    if (!u) return RL_OK;
+    cudaSetDevice(u->dev.index);
+    if (u->ss.stream) cudaStreamSynchronize(u->ss.stream);
+    cudaFree(u->d_xyz); cudaFree(u->d_rgb); cudaFree(u->d_moments); cudaFree(u->d_exposure);
+    u->ss.destroy();
+    delete u;
+    return RL_OK;
+}
+
+int rl_tonemap_unit_set_stream(rl_tonemap_unit *u, void *s) {
+    if (!u) return fail(RL_ERR_INVALID, "null unit");
+    cudaSetDevice(u->dev.index);
+    u->ss.bind(s);
+    return RL_OK;
+}
+
+static int tonemap_device(rl_tonemap_unit *u, const float *d_xyz, uint8_t *rgb) {
+    RL_CUDA(launch_tonemap(d_xyz, u->width, u->height, u->d_moments, u->d_exposure, u->d_rgb,
+                           u->dev.sm_count, u->ss.stream));
+    RL_CUDA(cudaMemcpyAsync(&u->last_exposure, u->d_exposure, sizeof(float), cudaMemcpyDeviceToHost,
+                            u->ss.stream));
+    if (rgb)
+        RL_CUDA(cudaMemcpyAsync(rgb, u->d_rgb, (size_t)u->width * u->height * 3, cudaMemcpyDeviceToHost,
+                                u->ss.stream));
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    return RL_OK;
+}
+
+int rl_tonemap_unit_tonemap(rl_tonemap_unit *u, const float *xyz, uint8_t *rgb) {
+    if (!u || !xyz || !rgb) return fail(RL_ERR_INVALID, "rl_tonemap_unit_tonemap: null argument");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    RL_CUDA(cudaMemcpyAsync(u->d_xyz, xyz, (size_t)u->width * u->height * 3 * sizeof(float),
+                            cudaMemcpyHostToDevice, u->ss.stream));
+    return tonemap_device(u, u->d_xyz, rgb);
+}
+
+int rl_tonemap_unit_tonemap_gather(rl_tonemap_unit *u, rl_gather_unit *g, uint8_t *rgb) {
+    if (!u || !g) return fail(RL_ERR_INVALID, "rl_tonemap_unit_tonemap_gather: null argument");
+    if (u->dev.index != g->dev.index) return fail(RL_ERR_INVALID, "units on different devices");
+    if (u->width != g->width || u->height != g->height)
+        return fail(RL_ERR_INVALID, "tonemap and gather unit canvas sizes differ");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    int rc = order_after(g->ss, u->ss);
+    if (rc != RL_OK) return rc;
+    rc = tonemap_device(u, g->d_acc, rgb);
+    if (rc != RL_OK) return rc;
+    return order_after(u->ss, g->ss);
+}
+
+int rl_tonemap_unit_last_exposure(rl_tonemap_unit *u, float *out) {
+    if (!u || !out) return fail(RL_ERR_INVALID, "null argument");
+    *out = u->last_exposure;
+    return RL_OK;
+}
+
+// ------------------------------------------------------------------ probes
+int rl_debug_intersect(const rl_scene *scene, const rl_ray *rays, uint64_t n, rl_hit *out) {
+    if (!scene || (!rays && n) || (!out && n)) return fail(RL_ERR_INVALID, "null argument");
+    if (n == 0) return RL_OK;
+    RL_CUDA(cudaSetDevice(scene->dev.index));
+    rl_ray *d_rays = nullptr; rl_hit *d_out = nullptr;
+    RL_CUDA(cudaMalloc(&d_rays, n * sizeof(rl_ray)));
+    cudaError_t e = cudaMalloc(&d_out, n * sizeof(rl_hit));
+    if (e == cudaSuccess) e = cudaMemcpy(d_rays, rays, n * sizeof(rl_ray), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_debug_intersect(scene->ds, d_rays, n, d_out, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n * sizeof(rl_hit), cudaMemcpyDeviceToHost);
+    cudaFree(d_rays); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(RL_ERR_CUDA, cudaGetErrorString(e));
+    return RL_OK;
+}
+
+int rl_debug_math(int fn, const float *in, const float *in2, uint64_t n, float *out) {
+    if ((!in || !out) && n) return fail(RL_ERR_INVALID, "null argument");
+    if (fn < 0 || fn > 8) return fail(RL_ERR_INVALID, "unknown function");
+    if ((fn == 4 || fn == 7) && !in2) return fail(RL_ERR_INVALID, "second operand required");
+    if (n == 0) return RL_OK;
+    Device dev;
+    int rc = current_device(dev);
+    if (rc != RL_OK) return rc;
+    float *d_in = nullptr, *d_in2 = nullptr, *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_in, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, n * sizeof(float));
+    if (e == cudaSuccess && in2) e = cudaMalloc(&d_in2, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, in, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && in2) e = cudaMemcpy(d_in2, in2, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_debug_math(fn, d_in, d_in2, n, d_out, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_in2); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(RL_ERR_CUDA, cudaGetErrorString(e));
+    return RL_OK;
+}
+
+int rl_debug_tristimulus(const float *wl, uint64_t n, float *out_xyz) {
+    if ((!wl || !out_xyz) && n) return fail(RL_ERR_INVALID, "null argument");
+    if (n == 0) return RL_OK;
+    Device dev;
+    int rc = current_device(dev);
+    if (rc != RL_OK) return rc;
+    float *d_in = nullptr, *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_in, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, 3 * n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, wl, n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_debug_tristimulus(d_in, n, d_out, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out_xyz, d_out, 3 * n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(RL_ERR_CUDA, cudaGetErrorString(e));
+    return RL_OK;
+}
+
+int rl_debug_camera_rays(const rl_scene *scene, uint64_t seed, uint32_t width, uint32_t height,
+                         uint64_t first_photon, uint64_t n, rl_ray *out_rays, rl_mapped_photon *out_xy) {
+    if (!scene || (!out_rays && n) || width == 0 || height == 0) return fail(RL_ERR_INVALID, "bad argument");
+    if (n == 0) return RL_OK;
+    RL_CUDA(cudaSetDevice(scene->dev.index));
+    rl_ray *d_rays = nullptr; rl_mapped_photon *d_xy = nullptr;
+    cudaError_t e = cudaMalloc(&d_rays, n * sizeof(rl_ray));
+    if (e == cudaSuccess && out_xy) e = cudaMalloc(&d_xy, n * sizeof(rl_mapped_photon));
+    if (e == cudaSuccess) e = launch_debug_camera(scene->ds, seed, width, height, first_photon, n, d_rays, d_xy, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out_rays, d_rays, n * sizeof(rl_ray), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_xy) e = cudaMemcpy(out_xy, d_xy, n * sizeof(rl_mapped_photon), cudaMemcpyDeviceToHost);
+    cudaFree(d_rays); cudaFree(d_xy);
+    if (e != cudaSuccess) return fail(RL_ERR_CUDA, cudaGetErrorString(e));
+    return RL_OK;
+}
+
+}  // extern "C"

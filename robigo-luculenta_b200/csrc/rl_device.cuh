@@ -1,0 +1,500 @@
+// rl_device.cuh -- device-side scene layout and the per-ray functions of the
+// path: RNG draws, camera ray, Scene::intersect, materials, splat.
+//
+// Layout in HBM / shared memory.  rl_scene_create flattens the descriptor into
+// one "primitive blob" of 16-byte records, grouped by primitive type so that a
+// warp walks each list with uniform (broadcast) shared-memory loads:
+//
+//   spheres      n_spheres     x float4 {cx, cy, cz, r^2}
+//   planes       n_planes      x 2 float4 {n.xyz, kind} {offset.xyz, r^2}
+//   paraboloids  n_paraboloids x 3 float4 {offset,0} {normal,0} {focal_point,0}
+//   leaves       n_leaves      x 2 float4 {n.xyz, 0} {offset.xyz, 0}   half-spaces of compounds
+//   compounds    n_compounds   x 2 float4 {first_leaf, n_leaves, first_op, n_ops} {bound c.xyz, bound r^2}
+//   ops          n_ops         x uint32   post-order program of the compound trees
+//   *_obj                      x uint32   object index of each sphere/plane/paraboloid/compound
+//
+// The kernel copies the blob into shared memory once per CTA.  Per-object
+// material records {kind, p0, p1, p2} stay in global memory (one read per
+// bounce, L1-resident).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rl_b200.h"
+#include "rl_math.cuh"
+
+namespace rl {
+
+struct DevCamera {
+    uint32_t kind;
+    float px, py, pz;
+    float field_of_view, focal_distance, depth_of_field, chromatic_abberation;
+    float qx, qy, qz, qw;
+    float phi_base, phi_rate, alpha_base, alpha_rate, distance_base, distance_rate, focal_factor;
+};
+
+struct DevScene {
+    const float4 *blob;       // global copy of the primitive blob
+    uint32_t blob_vec4;       // its size in float4 units
+    // offsets into the blob, in float4 units
+    uint32_t off_spheres, n_spheres;
+    uint32_t off_planes, n_planes;
+    uint32_t off_paraboloids, n_paraboloids;
+    uint32_t off_leaves, n_leaves;
+    uint32_t off_compounds, n_compounds;
+    uint32_t off_ops, n_ops;
+    uint32_t off_sphere_obj, off_plane_obj, off_paraboloid_obj, off_compound_obj;
+    const float4 *materials;  // per object
+    uint32_t n_objects;
+    DevCamera camera;
+};
+
+// Views into the blob once it sits in shared memory.
+struct PrimTables {
+    const float4 *spheres;
+    const float4 *planes;
+    const float4 *paraboloids;
+    const float4 *leaves;
+    const float4 *compounds;
+    const uint32_t *ops;
+    const uint32_t *sphere_obj, *plane_obj, *paraboloid_obj, *compound_obj;
+    uint32_t n_spheres, n_planes, n_paraboloids, n_compounds;
+};
+
+__device__ __forceinline__ PrimTables make_tables(const DevScene &sc, const float4 *base) {
+    PrimTables t;
+    t.spheres = base + sc.off_spheres;
+    t.planes = base + sc.off_planes;
+    t.paraboloids = base + sc.off_paraboloids;
+    t.leaves = base + sc.off_leaves;
+    t.compounds = base + sc.off_compounds;
+    t.ops = reinterpret_cast<const uint32_t *>(base + sc.off_ops);
+    t.sphere_obj = reinterpret_cast<const uint32_t *>(base + sc.off_sphere_obj);
+    t.plane_obj = reinterpret_cast<const uint32_t *>(base + sc.off_plane_obj);
+    t.paraboloid_obj = reinterpret_cast<const uint32_t *>(base + sc.off_paraboloid_obj);
+    t.compound_obj = reinterpret_cast<const uint32_t *>(base + sc.off_compound_obj);
+    t.n_spheres = sc.n_spheres;
+    t.n_planes = sc.n_planes;
+    t.n_paraboloids = sc.n_paraboloids;
+    t.n_compounds = sc.n_compounds;
+    return t;
+}
+
+// ---------------------------------------------------------------------- RNG
+// Philox4x32-10, counter (photon_lo, photon_hi, block, 0), key (seed_lo,
+// seed_hi).  Stands in for rand::random (monte_carlo.rs:22-28).
+struct Rng {
+    uint32_t k0, k1, c0, c1, block;
+    uint32_t b0, b1, b2, b3;
+    uint32_t left;
+
+    RL_HD void init(uint64_t seed, uint64_t photon) {
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+        c0 = (uint32_t)photon; c1 = (uint32_t)(photon >> 32);
+        block = 0; left = 0; b0 = b1 = b2 = b3 = 0;
+    }
+    RL_HD void refill() {
+        uint32_t x0 = c0, x1 = c1, x2 = block, x3 = 0u, ka = k0, kb = k1;
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+#if defined(__CUDA_ARCH__)
+            const uint32_t h0 = __umulhi(0xD2511F53u, x0), l0 = 0xD2511F53u * x0;
+            const uint32_t h1 = __umulhi(0xCD9E8D57u, x2), l1 = 0xCD9E8D57u * x2;
+#else
+            const uint64_t p0 = (uint64_t)0xD2511F53u * x0, p1 = (uint64_t)0xCD9E8D57u * x2;
+            const uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0;
+            const uint32_t h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+#endif
+            const uint32_t y0 = h1 ^ x1 ^ ka, y2 = h0 ^ x3 ^ kb;
+            x0 = y0; x1 = l1; x2 = y2; x3 = l0;
+            ka += 0x9E3779B9u; kb += 0xBB67AE85u;
+        }
+        b0 = x0; b1 = x1; b2 = x2; b3 = x3;
+        block++;
+        left = 4;
+    }
+    RL_HD uint32_t next_u32() {
+        if (left == 0) refill();
+        const uint32_t v = b0;
+        b0 = b1; b1 = b2; b2 = b3;
+        left--;
+        return v;
+    }
+    // Closed01<f32> of rand 0.3.11 (monte_carlo.rs:25-28): in [0, 1]
+    RL_HD float unit() { return (float)(next_u32() >> 8) / 16777215.0f; }
+    // rand::random::<f32>() (monte_carlo.rs:37): in [0, 1)
+    RL_HD float half_open() { return (float)(next_u32() >> 8) * 5.9604644775390625e-8f; }
+    RL_HD float bi_unit() { return unit() * 2.0f - 1.0f; }             // monte_carlo.rs:31-33
+    RL_HD float longitude() { return half_open() * RL_PI * 2.0f; }     // monte_carlo.rs:36-38
+    RL_HD float wavelength() { return unit() * 400.0f + 380.0f; }      // monte_carlo.rs:41-43
+};
+
+struct Ray { V3 origin, direction; float wavelength; };
+
+// ------------------------------------------------------------------- camera
+// app.rs:327-357 (make_camera) in closed form, camera.rs:94-108 + :47-90.
+RL_HD Ray camera_ray(const DevCamera &cm, float x, float y, float wavelength, float t, Rng &rng) {
+    V3 position;
+    Quat orientation;
+    float focal_distance;
+    if (cm.kind == RL_CAMERA_STATIC) {
+        position = mk(cm.px, cm.py, cm.pz);
+        orientation = mkq(cm.qx, cm.qy, cm.qz, cm.qw);
+        focal_distance = cm.focal_distance;
+    } else {
+        const float phi = RL_PI * (cm.phi_base + cm.phi_rate * t);
+        const float alpha = RL_PI * (cm.alpha_base + cm.alpha_rate * t);
+        const float distance = cm.distance_base + cm.distance_rate * t;
+        float sa, ca, sp, cp;
+        spec_sincos(alpha, sa, ca);
+        spec_sincos(phi, sp, cp);
+        position = mk(ca * sp * distance, ca * cp * distance, sa * distance);
+        orientation = rotation(0.0f, 0.0f, -1.0f, phi + RL_PI) * rotation(1.0f, 0.0f, 0.0f, -alpha);
+        focal_distance = distance * cm.focal_factor;
+    }
+    const float dof_angle = rng.longitude();
+    const float dof_radius = rng.unit() / cm.depth_of_field;
+    const float d = (wavelength - 580.0f) / 200.0f;
+    const float chromatic_zoom = 1.0f + d * cm.chromatic_abberation;
+    const float screen_distance = 1.0f / spec_tan(cm.field_of_view * 0.5f);
+    const float xs = x * chromatic_zoom;
+    const float ys = y * chromatic_zoom;
+    const V3 direction = normalise(mk(xs, screen_distance, -ys));
+    const V3 focus_point = direction * (focal_distance / direction.y);
+    float sd, cd;
+    spec_sincos(dof_angle, sd, cd);
+    const V3 lens_point = mk(cd * dof_radius, 0.0f, sd * dof_radius);
+    Ray r;
+    r.origin = position + rotate(lens_point, orientation);
+    r.direction = normalise(rotate(focus_point - lens_point, orientation));
+    r.wavelength = wavelength;
+    return r;
+}
+
+// ------------------------------------------------------------- intersection
+#define RL_HIT_NONE 0u
+#define RL_HIT_SPHERE 1u
+#define RL_HIT_PLANE 2u
+#define RL_HIT_PARABOLOID 3u
+#define RL_HIT_LEAF 4u
+
+struct Hit {
+    float t;
+    int obj;        // object index, -1 = miss
+    uint32_t code;  // (type << 28) | index of the primitive (sphere / plane / paraboloid / leaf)
+};
+
+// scene.rs:51 keeps the first object of the list on equal distance; the typed
+// lists are walked out of list order, so ties resolve on the object index.
+__device__ __forceinline__ void consider(Hit &best, float t, int obj, uint32_t code) {
+    if (t < best.t || (t == best.t && obj < best.obj)) {
+        best.t = t; best.obj = obj; best.code = code;
+    }
+}
+
+// geometry.rs:55-71; returns t (> 0) or a negative number for "no hit"
+__device__ __forceinline__ float plane_t(V3 n, V3 off, const Ray &ray, float &d) {
+    const V3 origin = ray.origin - off;
+    d = dot(n, ray.direction);
+    if (d == 0.0f) return -1.0f;
+    const float t = -dot(n, origin) / d;
+    return t <= 0.0f ? -1.0f : t;
+}
+
+// geometry.rs:204-240: the distance of Sphere::intersect, or negative.
+__device__ __forceinline__ float sphere_t(float4 s, const Ray &ray) {
+    const V3 co = mk(s.x, s.y, s.z) - ray.origin;
+    const float b = 2.0f * dot(ray.direction, co);
+    const float c = magnitude_squared(co) - s.w;
+    const float disc = b * b - 4.0f * c;
+    if (disc < 0.0f) return -1.0f;
+    const float d = sqrtf(disc);
+    const float t1 = -0.5f * (-b + d);
+    const float t2 = -0.5f * (-b - d);
+    // `t2 > 0 && t2 < t1` (geometry.rs:238) cannot hold since d >= 0
+    return (t1 > 0.0f && t1 < t2) ? t1 : -1.0f;
+}
+
+// geometry.rs:299-341
+__device__ __forceinline__ float paraboloid_t(const float4 *p, const Ray &ray) {
+    const V3 offset = mk(p[0].x, p[0].y, p[0].z);
+    const V3 normal = mk(p[1].x, p[1].y, p[1].z);
+    const V3 focal_point = mk(p[2].x, p[2].y, p[2].z);
+    const V3 origin = ray.origin - offset;
+    const V3 focal_offset = origin - focal_point;
+    const float n_dot_d = dot(normal, ray.direction);
+    const float n_dot_o = dot(normal, origin);
+    const float d_dot_f = dot(ray.direction, focal_offset);
+    const float a = n_dot_d * n_dot_d - 1.0f;
+    const float b = 2.0f * n_dot_d * n_dot_o - 2.0f * d_dot_f;
+    const float c = n_dot_o * n_dot_o - magnitude_squared(focal_offset);
+    if (a == 0.0f) {
+        const float t1 = -c / b;
+        return t1 < 0.0f ? -1.0f : t1;   // NaN (b == 0, c == 0) passes `t1 < 0` like the reference
+    }
+    const float d = b * b - 4.0f * a * c;
+    if (d < 0.0f) return -1.0f;
+    const float sqrt_d = sqrtf(d);
+    const float p1 = 0.5f * (-b + sqrt_d) / a;
+    const float q1 = 0.5f * (-b - sqrt_d) / a;
+    if (p1 > 0.0f && (p1 < q1 || q1 < 0.0f)) return p1;
+    if (q1 > 0.0f) return q1;
+    return -1.0f;
+}
+
+// geometry.rs:380-407 for trees whose leaves are half-spaces: the post-order
+// program replays the reference's recursion with an explicit stack.
+// op word: bits 0-1 kind (0 = leaf, 1 = compound); leaf: bits 8.. = leaf index
+// relative to the compound's first leaf; compound: lo = bits 8-15, mid = bits
+// 16-23, hi = bits 24-31 (children own leaves [lo, mid) and [mid, hi)).
+#define RL_MAX_COMPOUND_STACK 8
+__device__ __forceinline__ float compound_t(const PrimTables &tb, uint32_t first_leaf,
+                                            uint32_t first_op, uint32_t n_ops, const Ray &ray,
+                                            uint32_t &leaf_out) {
+    float st_t[RL_MAX_COMPOUND_STACK];
+    uint32_t st_leaf[RL_MAX_COMPOUND_STACK];
+    int sp = 0;
+    for (uint32_t i = 0; i < n_ops; i++) {
+        const uint32_t op = tb.ops[first_op + i];
+        if ((op & 3u) == 0u) {
+            const uint32_t leaf = first_leaf + (op >> 8);
+            const float4 n4 = tb.leaves[2 * leaf], o4 = tb.leaves[2 * leaf + 1];
+            float d;
+            st_t[sp] = plane_t(mk(n4.x, n4.y, n4.z), mk(o4.x, o4.y, o4.z), ray, d);
+            st_leaf[sp] = leaf;
+            sp++;
+        } else {
+            const uint32_t lo = first_leaf + ((op >> 8) & 0xffu);
+            const uint32_t mid = first_leaf + ((op >> 16) & 0xffu);
+            const uint32_t hi = first_leaf + ((op >> 24) & 0xffu);
+            float t2 = st_t[sp - 1]; const uint32_t l2 = st_leaf[sp - 1];
+            float t1 = st_t[sp - 2]; const uint32_t l1 = st_leaf[sp - 2];
+            sp -= 2;
+            if (t1 > 0.0f) {  // surface2.lies_inside(i1.position)
+                const V3 pos = ray.origin + ray.direction * t1;
+                for (uint32_t k = mid; k < hi; k++) {
+                    const float4 n4 = tb.leaves[2 * k], o4 = tb.leaves[2 * k + 1];
+                    if (!(dot(pos - mk(o4.x, o4.y, o4.z), mk(n4.x, n4.y, n4.z)) < 0.0f)) { t1 = -1.0f; break; }
+                }
+            }
+            if (t2 > 0.0f) {  // surface1.lies_inside(i2.position)
+                const V3 pos = ray.origin + ray.direction * t2;
+                for (uint32_t k = lo; k < mid; k++) {
+                    const float4 n4 = tb.leaves[2 * k], o4 = tb.leaves[2 * k + 1];
+                    if (!(dot(pos - mk(o4.x, o4.y, o4.z), mk(n4.x, n4.y, n4.z)) < 0.0f)) { t2 = -1.0f; break; }
+                }
+            }
+            float t; uint32_t l;
+            if (t1 > 0.0f && t2 > 0.0f) {
+                if (t1 < t2) { t = t1; l = l1; } else { t = t2; l = l2; }
+            } else if (t1 > 0.0f) { t = t1; l = l1; }
+            else { t = t2; l = l2; }
+            st_t[sp] = t; st_leaf[sp] = l;
+            sp++;
+        }
+    }
+    leaf_out = st_leaf[0];
+    return st_t[0];
+}
+
+// Scene::intersect (scene.rs:39-60): closest hit over all objects.
+__device__ __forceinline__ Hit intersect_scene(const PrimTables &tb, const Ray &ray) {
+    Hit best;
+    best.t = 1.0e12f; best.obj = -1; best.code = RL_HIT_NONE;
+    for (uint32_t i = 0; i < tb.n_spheres; i++) {
+        const float t = sphere_t(tb.spheres[i], ray);
+        if (t > 0.0f) consider(best, t, (int)tb.sphere_obj[i], (RL_HIT_SPHERE << 28) | i);
+    }
+    for (uint32_t i = 0; i < tb.n_planes; i++) {
+        const float4 n4 = tb.planes[2 * i], o4 = tb.planes[2 * i + 1];
+        float d;
+        const float t = plane_t(mk(n4.x, n4.y, n4.z), mk(o4.x, o4.y, o4.z), ray, d);
+        if (t > 0.0f) {
+            bool ok = true;
+            if (__float_as_uint(n4.w) == RL_SURFACE_CIRCLE) {  // geometry.rs:169-172
+                const V3 pos = ray.origin + ray.direction * t;
+                ok = magnitude_squared(pos - mk(o4.x, o4.y, o4.z)) <= o4.w;
+            }
+            if (ok) consider(best, t, (int)tb.plane_obj[i], (RL_HIT_PLANE << 28) | i);
+        }
+    }
+    for (uint32_t i = 0; i < tb.n_paraboloids; i++) {
+        const float t = paraboloid_t(tb.paraboloids + 3 * i, ray);
+        // the a == 0 branch admits t == 0 (geometry.rs:319: only t1 < 0 is rejected)
+        if (t >= 0.0f) consider(best, t, (int)tb.paraboloid_obj[i], (RL_HIT_PARABOLOID << 28) | i);
+    }
+    for (uint32_t i = 0; i < tb.n_compounds; i++) {
+        const float4 c4 = tb.compounds[2 * i];
+        uint32_t leaf;
+        const float t = compound_t(tb, __float_as_uint(c4.x), __float_as_uint(c4.z),
+                                   __float_as_uint(c4.w), ray, leaf);
+        if (t > 0.0f) consider(best, t, (int)tb.compound_obj[i], (RL_HIT_LEAF << 28) | leaf);
+    }
+    return best;
+}
+
+struct Surf { V3 position, normal, tangent; };
+
+// The Intersection record of the winning primitive (intersection.rs:19-32);
+// the reference builds it for every candidate, the result only needs the winner.
+__device__ __forceinline__ Surf surface_at(const PrimTables &tb, const Ray &ray, const Hit &hit) {
+    Surf s;
+    s.position = ray.origin + ray.direction * hit.t;
+    s.tangent = mk(0.0f, 0.0f, 0.0f);
+    const uint32_t type = hit.code >> 28, idx = hit.code & 0x0fffffffu;
+    if (type == RL_HIT_SPHERE) {                                       // geometry.rs:243-251
+        const float4 sp = tb.spheres[idx];
+        s.normal = normalise(s.position - mk(sp.x, sp.y, sp.z));
+        s.tangent = normalise(cross(mk(0.0f, 1.0f, 0.0f), s.normal));
+    } else if (type == RL_HIT_PLANE) {
+        const float4 n4 = tb.planes[2 * idx];
+        const V3 n = mk(n4.x, n4.y, n4.z);
+        if (__float_as_uint(n4.w) == RL_SURFACE_HALFSPACE) {
+            s.normal = n;                                              // geometry.rs:115
+        } else {
+            const float d = dot(n, ray.direction);
+            s.normal = d < 0.0f ? n : -n;                              // geometry.rs:80, :178
+        }
+    } else if (type == RL_HIT_PARABOLOID) {                            // geometry.rs:343-347
+        const float4 *p = tb.paraboloids + 3 * idx;
+        const V3 offset = mk(p[0].x, p[0].y, p[0].z);
+        const V3 normal = mk(p[1].x, p[1].y, p[1].z);
+        const V3 focal_point = mk(p[2].x, p[2].y, p[2].z);
+        const V3 local_pos = s.position - offset;
+        const V3 plane_pr = local_pos - normal * dot(local_pos, normal);
+        s.normal = normalise(focal_point - plane_pr);
+    } else {                                                           // geometry.rs:115
+        const float4 n4 = tb.leaves[2 * idx];
+        s.normal = mk(n4.x, n4.y, n4.z);
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------- materials
+// material.rs:38-58 with monte_carlo.rs:47-58
+__device__ __forceinline__ V3 diffuse_direction(const Ray &in, const Surf &s, Rng &rng) {
+    const float phi = rng.longitude();
+    const float rq = rng.unit();
+    const float r = sqrtf(rq);
+    float sn, cs;
+    spec_sincos(phi, sn, cs);
+    const V3 hemi = mk(cs * r, sn * r, sqrtf(1.0f - rq));
+    const V3 normal = dot(in.direction, s.normal) < 0.0f ? s.normal : -s.normal;
+    return rotate_towards(hemi, normal);
+}
+
+__device__ __forceinline__ float soap_clamp(float x) {                 // material.rs:290-294
+    return x < -0.999f ? -0.999f : (x > 0.999f ? 0.999f : x);
+}
+
+// Material::get_new_ray for the five reflective materials; returns the new
+// direction and the ray's probability (origin = intersection position).
+__device__ __forceinline__ V3 material_bounce(float4 m, const Ray &in, const Surf &s, Rng &rng,
+                                              float &probability) {
+    const uint32_t kind = __float_as_uint(m.x);
+    switch (kind) {
+    case RL_MATERIAL_DIFFUSE_GREY:                                     // material.rs:122-130
+        probability = m.y;
+        return diffuse_direction(in, s, rng);
+    case RL_MATERIAL_DIFFUSE_COLOURED: {                               // material.rs:155-168
+        const float p = (m.z - in.wavelength) / m.w;
+        const float q = spec_exp(-0.5f * p * p);
+        probability = m.y * q;
+        return diffuse_direction(in, s, rng);
+    }
+    case RL_MATERIAL_GLOSSY_MIRROR: {                                  // material.rs:185-196
+        const V3 diffuse = diffuse_direction(in, s, rng);
+        const V3 reflection = reflect(in.direction, s.normal);
+        probability = 1.0f;
+        return normalise(diffuse * m.y + reflection * (1.0f - m.y));
+    }
+    case RL_MATERIAL_SF10_GLASS: {                                     // material.rs:216-261
+        float cos_i = -dot(in.direction, s.normal);
+        float ior = sf10_index_of_refraction(in.wavelength);
+        V3 normal = s.normal;
+        if (cos_i > 0.0f) {
+            ior = 1.0f / ior;
+        } else {
+            normal = -normal;
+            cos_i = -cos_i;
+        }
+        const float sin_t_sqr = ior * ior * (1.0f - cos_i * cos_i);
+        probability = 1.0f;
+        if (sin_t_sqr > 1.0f) return reflect(in.direction, normal);
+        const float cos_t = sqrtf(1.0f - sin_t_sqr);
+        return in.direction * ior + normal * (ior * cos_i - cos_t);
+    }
+    default: {  // RL_MATERIAL_SOAP_BUBBLE                                material.rs:267-306
+        const float cos_alpha = dot(in.direction, s.normal);
+        const V3 direction = (rng.unit() - 0.3f > fabsf(cos_alpha))
+                                 ? reflect(in.direction, s.normal)
+                                 : in.direction;
+        const float phase_shift = (in.wavelength - 380.0f) / 200.0f * RL_PI;
+        const float cos_phi = soap_clamp(dot(direction, s.normal));
+        const float cos_theta = soap_clamp(dot(direction, s.tangent));
+        float sn, cs;
+        spec_sincos(phase_shift - spec_acos(cos_phi) * 3.0f - spec_acos(cos_theta) * 2.0f
+                        + RL_PI * 0.5f, sn, cs);
+        probability = cs * 0.1f + 0.9f;
+        return direction;
+    }
+    }
+}
+
+// material.rs:101-105
+__device__ __forceinline__ float blackbody_intensity(float4 m, float wavelength) {
+    return (float)boltzmann((double)wavelength, (double)m.y) * m.z;
+}
+
+// --------------------------------------------------------------------- plot
+__constant__ float c_cie[81][3] = {
+#include "rl_cie1931_data.inc"
+};
+
+// cie1931.rs:20-48
+__device__ __forceinline__ V3 tristimulus(float wavelength) {
+    const float indexf = (wavelength - 380.0f) / 5.0f;
+    const int index = (int)floorf(indexf);
+    const float remainder = indexf - (float)index;
+    if (index < -1 || index > 80) return mk(0.0f, 0.0f, 0.0f);
+    if (index == -1) return mk(c_cie[0][0] * remainder, c_cie[0][1] * remainder, c_cie[0][2] * remainder);
+    if (index == 80) {
+        const float w = 1.0f - remainder;
+        return mk(c_cie[80][0] * w, c_cie[80][1] * w, c_cie[80][2] * w);
+    }
+    const float w = 1.0f - remainder;
+    return mk(c_cie[index][0] * w + c_cie[index + 1][0] * remainder,
+              c_cie[index][1] * w + c_cie[index + 1][1] * remainder,
+              c_cie[index][2] * w + c_cie[index + 1][2] * remainder);
+}
+
+__device__ __forceinline__ void red_add_v4(float4 *addr, float x, float y, float z) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(addr), "f"(x), "f"(y), "f"(z), "f"(0.0f) : "memory");
+}
+
+// PlotUnit::plot for one photon (plot_unit.rs:56-95) into the padded
+// accumulator (one float4 {X, Y, Z, 0} per pixel): four vector reductions.
+__device__ __forceinline__ void splat_photon(float4 *accum, int w, int h, float aspect, float x,
+                                             float y, float wavelength, float probability) {
+    const V3 cie = tristimulus(wavelength) * probability;
+    const float px = (x * 0.5f + 0.5f) * ((float)w - 1.0f);
+    const float py = (y * aspect * 0.5f + 0.5f) * ((float)h - 1.0f);
+    const int px1 = max(0, min(w - 1, (int)floorf(px)));
+    const int px2 = max(0, min(w - 1, (int)ceilf(px)));
+    const int py1 = max(0, min(h - 1, (int)floorf(py)));
+    const int py2 = max(0, min(h - 1, (int)ceilf(py)));
+    const float cx = px - (float)px1;
+    const float cy = py - (float)py1;
+    const float c11 = (1.0f - cx) * (1.0f - cy);
+    const float c12 = (1.0f - cx) * cy;
+    const float c21 = cx * (1.0f - cy);
+    const float c22 = cx * cy;
+    red_add_v4(accum + ((size_t)py1 * w + px1), cie.x * c11, cie.y * c11, cie.z * c11);
+    red_add_v4(accum + ((size_t)py1 * w + px2), cie.x * c21, cie.y * c21, cie.z * c21);
+    red_add_v4(accum + ((size_t)py2 * w + px1), cie.x * c12, cie.y * c12, cie.z * c12);
+    red_add_v4(accum + ((size_t)py2 * w + px2), cie.x * c22, cie.y * c22, cie.z * c22);
+}
+
+}  // namespace rl

@@ -1,0 +1,493 @@
+// rl_kernels.cu -- the sm_100a kernels of the path.
+//
+//   K1 trace_kernel    TraceUnit::render (trace_unit.rs:81-168), optionally
+//                      fused with PlotUnit::plot (plot_unit.rs:56-95)
+//   K2 splat_kernel    PlotUnit::plot over MappedPhoton records
+//   K3 gather_kernel   GatherUnit::accumulate (gather_unit.rs:49-64) + PlotUnit::clear
+//   K4 tonemap_*       TonemapUnit::tonemap (tonemap_unit.rs:55-100, srgb.rs:20-41)
+//
+// Compile with -fmad=false: see rl_math.cuh.
+#include <atomic>
+
+#include "rl_kernels.h"
+
+namespace rl {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t kernel_launches() { return g_launches.load(); }
+void kernel_launches_reset() { g_launches.store(0); }
+
+#define RL_TRACE_THREADS 256
+
+// ------------------------------------------------------------------ K1 trace
+struct TraceArgs {
+    uint64_t seed;
+    uint64_t first_photon;
+    uint64_t n_photons;
+    int width, height;
+    float aspect;
+    rl_mapped_photon *records;
+    float4 *accum;
+    unsigned long long *ray_counter;
+};
+
+// Persistent threads with path regeneration: every lane owns the photons
+// tid, tid + T, tid + 2T, ... of the launch and starts its next photon as soon
+// as its current path ends, so a warp never idles on its longest path.  The
+// primitive tables live in shared memory; each loop iteration is one
+// Scene::intersect plus one material interaction for every live lane.
+__global__ void __launch_bounds__(RL_TRACE_THREADS)
+trace_kernel(const DevScene sc, const TraceArgs a) {
+    extern __shared__ float4 smem[];
+    for (uint32_t i = threadIdx.x; i < sc.blob_vec4; i += blockDim.x) smem[i] = sc.blob[i];
+    __syncthreads();
+    const PrimTables tb = make_tables(sc, smem);
+
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t next = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+
+    bool alive = false;
+    uint64_t cur = 0;
+    Ray ray;
+    ray.origin = mk(0.f, 0.f, 0.f); ray.direction = mk(0.f, 0.f, 0.f); ray.wavelength = 0.f;
+    float sx = 0.f, sy = 0.f;
+    float intensity = 1.0f, continue_chance = 1.0f;
+    Rng rng;
+    rng.init(a.seed, 0);
+    uint32_t rays = 0;
+
+    for (;;) {
+        if (!alive && next < a.n_photons) {
+            // trace_unit.rs:151-158 and :136-145
+            cur = next;
+            next += stride;
+            rng.init(a.seed, a.first_photon + cur);
+            const float wavelength = rng.wavelength();
+            sx = rng.bi_unit();
+            sy = rng.bi_unit() / a.aspect;
+            const float t = rng.unit();
+            ray = camera_ray(sc.camera, sx, sy, wavelength, t, rng);
+            intensity = 1.0f;
+            continue_chance = 1.0f;
+            alive = true;
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+        if (alive) {
+            // trace_unit.rs:91-131
+            rays++;
+            const Hit hit = intersect_scene(tb, ray);
+            bool done = false;
+            float result = 0.0f;
+            if (hit.obj < 0) {
+                done = true;                                            // trace_unit.rs:94
+            } else {
+                const float4 m = __ldg(sc.materials + hit.obj);
+                if (__float_as_uint(m.x) == RL_MATERIAL_BLACKBODY) {
+                    result = intensity * blackbody_intensity(m, ray.wavelength);  // :99-101
+                    done = true;
+                } else {
+                    const Surf s = surface_at(tb, ray, hit);
+                    float probability;
+                    const V3 dir = material_bounce(m, ray, s, rng, probability);  // :104-107
+                    intensity = intensity * probability;
+                    ray.direction = dir;
+                    ray.origin = s.position + dir * 0.00001f;                      // :114
+                    continue_chance = continue_chance * 0.96f;                    // :117
+                    if (rng.unit() * 0.85f
+                        > continue_chance * (1.0f - spec_exp(intensity * -20.0f)))  // :122-125
+                        done = true;
+                }
+            }
+            if (done) {
+                if (a.records) {
+                    rl_mapped_photon ph;
+                    ph.x = sx; ph.y = sy; ph.probability = result; ph.wavelength = ray.wavelength;
+                    *reinterpret_cast<float4 *>(a.records + cur) =
+                        make_float4(ph.x, ph.y, ph.probability, ph.wavelength);
+                }
+                // adding cie * 0 leaves the accumulator unchanged (plot_unit.rs:80-83)
+                if (a.accum && result != 0.0f)
+                    splat_photon(a.accum, a.width, a.height, a.aspect, sx, sy, ray.wavelength, result);
+                alive = false;
+            }
+        }
+    }
+
+    // rays traced = Scene::intersect calls (scene.rs:39)
+    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
+    if ((threadIdx.x & 31) == 0 && a.ray_counter) atomicAdd(a.ray_counter, (unsigned long long)rays);
+}
+
+size_t trace_smem_bytes(const DevScene &sc) { return (size_t)sc.blob_vec4 * sizeof(float4); }
+
+cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count, cudaStream_t st) {
+    if (p.n_photons == 0) return cudaSuccess;
+    const size_t smem = trace_smem_bytes(sc);
+    cudaError_t err = cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem);
+    if (err != cudaSuccess) return err;
+    int per_sm = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel, RL_TRACE_THREADS, smem);
+    if (err != cudaSuccess) return err;
+    if (per_sm < 1) per_sm = 1;
+    uint64_t want = (p.n_photons + RL_TRACE_THREADS - 1) / RL_TRACE_THREADS;
+    uint64_t full = (uint64_t)sm_count * per_sm;
+    unsigned grid = (unsigned)(want < full ? want : full);
+    TraceArgs a;
+    a.seed = p.seed;
+    a.first_photon = p.first_photon;
+    a.n_photons = p.n_photons;
+    a.width = (int)p.width;
+    a.height = (int)p.height;
+    a.aspect = (float)p.width / (float)p.height;  // trace_unit.rs:73, plot_unit.rs:49
+    a.records = p.records;
+    a.accum = p.accum;
+    a.ray_counter = p.ray_counter;
+    trace_kernel<<<grid, RL_TRACE_THREADS, smem, st>>>(sc, a);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ K2 splat
+__global__ void __launch_bounds__(256)
+splat_kernel(const float4 *__restrict__ records, uint64_t n, float4 *accum, int width, int height,
+             float aspect) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 ph = __ldg(records + i);  // {x, y, probability, wavelength}
+        if (ph.z != 0.0f) splat_photon(accum, width, height, aspect, ph.x, ph.y, ph.w, ph.z);
+    }
+}
+
+cudaError_t launch_splat(const rl_mapped_photon *records, uint64_t n, float4 *accum, uint32_t width,
+                         uint32_t height, int sm_count, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    uint64_t want = (n + 255) / 256;
+    uint64_t full = (uint64_t)sm_count * 8;
+    unsigned grid = (unsigned)(want < full ? want : full);
+    splat_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(records), n, accum,
+                                       (int)width, (int)height, (float)width / (float)height);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+pack_xyz_kernel(const float4 *__restrict__ accum, float *__restrict__ xyz, uint64_t n_pixels) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += stride) {
+        const float4 v = accum[i];
+        xyz[3 * i + 0] = v.x; xyz[3 * i + 1] = v.y; xyz[3 * i + 2] = v.z;
+    }
+}
+
+cudaError_t launch_pack_xyz(const float4 *accum, float *xyz, uint64_t n_pixels, cudaStream_t st) {
+    if (n_pixels == 0) return cudaSuccess;
+    uint64_t want = (n_pixels + 255) / 256;
+    unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+    pack_xyz_kernel<<<grid, 256, 0, st>>>(accum, xyz, n_pixels);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------- K3 gather
+#define RL_GATHER_MAX_SRC 8
+struct GatherSrcs { const float4 *p[RL_GATHER_MAX_SRC]; };
+
+// gather_unit.rs:55-63, one component
+__device__ __forceinline__ void kahan(float &acc, float &comp, float px) {
+    const float extra = px - comp;
+    const float sum = acc + extra;
+    comp = (sum - acc) - extra;
+    acc = sum;
+}
+
+// One thread owns 4 consecutive pixels = 12 floats = three 16-byte vectors of
+// the packed accumulator / compensation arrays, so every access is 128-bit.
+__global__ void __launch_bounds__(256)
+gather_kernel(float *__restrict__ acc, float *__restrict__ comp, GatherSrcs srcs, uint32_t n_src,
+              const float *__restrict__ packed_src, float4 *clear, uint64_t n_pixels) {
+    const uint64_t n_quads = n_pixels / 4;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint64_t q = tid; q < n_quads; q += stride) {
+        float4 *acc4 = reinterpret_cast<float4 *>(acc) + 3 * q;
+        float4 *comp4 = reinterpret_cast<float4 *>(comp) + 3 * q;
+        float a[12], c[12];
+        *reinterpret_cast<float4 *>(a + 0) = acc4[0];
+        *reinterpret_cast<float4 *>(a + 4) = acc4[1];
+        *reinterpret_cast<float4 *>(a + 8) = acc4[2];
+        *reinterpret_cast<float4 *>(c + 0) = comp4[0];
+        *reinterpret_cast<float4 *>(c + 4) = comp4[1];
+        *reinterpret_cast<float4 *>(c + 8) = comp4[2];
+        if (packed_src) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(packed_src) + 3 * q;
+            float p[12];
+            *reinterpret_cast<float4 *>(p + 0) = s4[0];
+            *reinterpret_cast<float4 *>(p + 4) = s4[1];
+            *reinterpret_cast<float4 *>(p + 8) = s4[2];
+#pragma unroll
+            for (int k = 0; k < 12; k++) kahan(a[k], c[k], p[k]);
+        }
+        for (uint32_t s = 0; s < n_src; s++) {
+            const float4 *src = srcs.p[s] + 4 * q;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float4 v = src[k];
+                kahan(a[3 * k + 0], c[3 * k + 0], v.x);
+                kahan(a[3 * k + 1], c[3 * k + 1], v.y);
+                kahan(a[3 * k + 2], c[3 * k + 2], v.z);
+            }
+        }
+        acc4[0] = *reinterpret_cast<float4 *>(a + 0);
+        acc4[1] = *reinterpret_cast<float4 *>(a + 4);
+        acc4[2] = *reinterpret_cast<float4 *>(a + 8);
+        comp4[0] = *reinterpret_cast<float4 *>(c + 0);
+        comp4[1] = *reinterpret_cast<float4 *>(c + 4);
+        comp4[2] = *reinterpret_cast<float4 *>(c + 8);
+        if (clear) {  // PlotUnit::clear (plot_unit.rs:98-102)
+            float4 *cl = clear + 4 * q;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            cl[0] = z; cl[1] = z; cl[2] = z; cl[3] = z;
+        }
+    }
+    // up to 3 tail pixels
+    for (uint64_t px = n_quads * 4 + tid; px < n_pixels; px += stride) {
+        for (int k = 0; k < 3; k++) {
+            float av = acc[3 * px + k], cv = comp[3 * px + k];
+            if (packed_src) kahan(av, cv, packed_src[3 * px + k]);
+            for (uint32_t s = 0; s < n_src; s++) {
+                const float4 v = srcs.p[s][px];
+                kahan(av, cv, k == 0 ? v.x : (k == 1 ? v.y : v.z));
+            }
+            acc[3 * px + k] = av; comp[3 * px + k] = cv;
+        }
+        if (clear) clear[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+cudaError_t launch_gather(float *acc, float *comp, const float4 *const *srcs, uint32_t n_src,
+                          const float *packed_src, float4 *clear_or_null, uint64_t n_pixels,
+                          int sm_count, cudaStream_t st) {
+    if (n_pixels == 0) return cudaSuccess;
+    if (n_src > RL_GATHER_MAX_SRC) return cudaErrorInvalidValue;
+    GatherSrcs g;
+    for (uint32_t i = 0; i < RL_GATHER_MAX_SRC; i++) g.p[i] = i < n_src ? srcs[i] : nullptr;
+    uint64_t want = (n_pixels / 4 + 255) / 256 + 1;
+    uint64_t full = (uint64_t)sm_count * 8;
+    unsigned grid = (unsigned)(want < full ? want : full);
+    gather_kernel<<<grid, 256, 0, st>>>(acc, comp, g, n_src, packed_src, clear_or_null, n_pixels);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- K4 tonemap
+// tonemap_unit.rs:55-69.  The reference folds the two sums sequentially in
+// f32; here they are reduced in f64 (order-independent to ~1e-16), then the
+// reference's f32 formula is applied to the rounded means.
+__global__ void __launch_bounds__(256)
+tonemap_moments_kernel(const float *__restrict__ xyz, uint64_t n_pixels, double *moments) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double s1 = 0.0, s2 = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += stride) {
+        const float y = xyz[3 * i + 1];
+        s1 += (double)y;
+        s2 += (double)(y * y);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    __shared__ double w1[8], w2[8];
+    if ((threadIdx.x & 31) == 0) { w1[threadIdx.x >> 5] = s1; w2[threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int i = 0; i < 8; i++) { t1 += w1[i]; t2 += w2[i]; }
+        atomicAdd(moments + 0, t1);
+        atomicAdd(moments + 1, t2);
+    }
+}
+
+__global__ void tonemap_exposure_kernel(const double *moments, uint32_t width, uint32_t height,
+                                        float *exposure) {
+    const float n = (float)(width * height);               // tonemap_unit.rs:56
+    const float mean = (float)moments[0] / n;              // :61
+    const float sqr_mean = (float)moments[1] / n;          // :64
+    const float variance = sqr_mean - mean * mean;         // :65
+    *exposure = mean + sqrtf(variance);                    // :68
+}
+
+__device__ __forceinline__ float gamma_correct(float f) {  // srgb.rs:20-26
+    if (f <= 0.0031308f) return 12.92f * f;
+    return 1.055f * spec_pow(f, 1.0f / 2.4f) - 0.055f;
+}
+__device__ __forceinline__ float clamp01(float x) {        // tonemap_unit.rs:34-38
+    if (x < 0.0f) return 0.0f;
+    if (1.0f < x) return 1.0f;
+    return x;
+}
+__device__ __forceinline__ uint32_t to_u8(float v) {       // Rust `as u8`: saturating, NaN -> 0
+    if (!(v == v)) return 0u;
+    if (v <= 0.0f) return 0u;
+    if (v >= 255.0f) return 255u;
+    return (uint32_t)v;
+}
+
+// tonemap_unit.rs:73-100 + srgb.rs:29-41, one pixel per thread-iteration.
+__global__ void __launch_bounds__(256)
+tonemap_map_kernel(const float *__restrict__ xyz, uint64_t n_pixels, const float *exposure,
+                   uint8_t *__restrict__ rgb) {
+    const float max_intensity = *exposure;
+    const float ln_4 = spec_ln(4.0f);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += stride) {
+        const float cx = spec_ln(xyz[3 * i + 0] / max_intensity + 1.0f) / ln_4;
+        const float cy = spec_ln(xyz[3 * i + 1] / max_intensity + 1.0f) / ln_4;
+        const float cz = spec_ln(xyz[3 * i + 2] / max_intensity + 1.0f) / ln_4;
+        const float r = 3.2406f * cx - 1.5372f * cy - 0.4986f * cz;
+        const float g = -0.9689f * cx + 1.8758f * cy + 0.0415f * cz;
+        const float b = 0.0557f * cx - 0.2040f * cy + 1.0570f * cz;
+        rgb[3 * i + 0] = (uint8_t)to_u8(clamp01(gamma_correct(r)) * 255.0f);
+        rgb[3 * i + 1] = (uint8_t)to_u8(clamp01(gamma_correct(g)) * 255.0f);
+        rgb[3 * i + 2] = (uint8_t)to_u8(clamp01(gamma_correct(b)) * 255.0f);
+    }
+}
+
+cudaError_t launch_tonemap(const float *xyz, uint32_t width, uint32_t height, double *moments,
+                           float *exposure_out, uint8_t *rgb, int sm_count, cudaStream_t st) {
+    const uint64_t n_pixels = (uint64_t)width * height;
+    if (n_pixels == 0) return cudaSuccess;
+    cudaError_t err = cudaMemsetAsync(moments, 0, 2 * sizeof(double), st);
+    if (err != cudaSuccess) return err;
+    uint64_t want = (n_pixels + 255) / 256;
+    uint64_t full = (uint64_t)sm_count * 8;
+    unsigned grid = (unsigned)(want < full ? want : full);
+    tonemap_moments_kernel<<<grid, 256, 0, st>>>(xyz, n_pixels, moments);
+    tonemap_exposure_kernel<<<1, 1, 0, st>>>(moments, width, height, exposure_out);
+    tonemap_map_kernel<<<grid, 256, 0, st>>>(xyz, n_pixels, exposure_out, rgb);
+    g_launches += 3;
+    return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------- probes
+__global__ void debug_intersect_kernel(const DevScene sc, const rl_ray *rays, uint64_t n, rl_hit *out) {
+    extern __shared__ float4 smem[];
+    for (uint32_t i = threadIdx.x; i < sc.blob_vec4; i += blockDim.x) smem[i] = sc.blob[i];
+    __syncthreads();
+    const PrimTables tb = make_tables(sc, smem);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Ray r;
+        r.origin = mk(rays[i].origin.x, rays[i].origin.y, rays[i].origin.z);
+        r.direction = mk(rays[i].direction.x, rays[i].direction.y, rays[i].direction.z);
+        r.wavelength = rays[i].wavelength;
+        const Hit h = intersect_scene(tb, r);
+        rl_hit o;
+        o.object = h.obj;
+        o.distance = 0.f;
+        o.position = o.normal = o.tangent = rl_vec3{0.f, 0.f, 0.f};
+        if (h.obj >= 0) {
+            const Surf s = surface_at(tb, r, h);
+            o.distance = h.t;
+            o.position = rl_vec3{s.position.x, s.position.y, s.position.z};
+            o.normal = rl_vec3{s.normal.x, s.normal.y, s.normal.z};
+            o.tangent = rl_vec3{s.tangent.x, s.tangent.y, s.tangent.z};
+        }
+        out[i] = o;
+    }
+}
+
+cudaError_t launch_debug_intersect(const DevScene &sc, const rl_ray *rays, uint64_t n, rl_hit *out,
+                                   cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const size_t smem = trace_smem_bytes(sc);
+    cudaError_t err = cudaFuncSetAttribute(debug_intersect_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    uint64_t want = (n + 127) / 128;
+    unsigned grid = (unsigned)(want < 148 * 4 ? want : 148 * 4);
+    debug_intersect_kernel<<<grid, 128, smem, st>>>(sc, rays, n, out);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+__global__ void debug_math_kernel(int fn, const float *in, const float *in2, uint64_t n, float *out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float x = in[i];
+        float s, c, r = 0.f;
+        switch (fn) {
+        case 0: spec_sincos(x, s, c); r = s; break;
+        case 1: spec_sincos(x, s, c); r = c; break;
+        case 2: r = spec_exp(x); break;
+        case 3: r = spec_acos(x); break;
+        case 4: r = (float)boltzmann((double)x, (double)in2[i]); break;
+        case 5: r = sf10_index_of_refraction(x); break;
+        case 6: r = spec_ln(x); break;
+        case 7: r = spec_pow(x, in2[i]); break;
+        case 8: r = spec_tan(x); break;
+        }
+        out[i] = r;
+    }
+}
+
+cudaError_t launch_debug_math(int fn, const float *in, const float *in2, uint64_t n, float *out,
+                              cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    uint64_t want = (n + 255) / 256;
+    unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+    debug_math_kernel<<<grid, 256, 0, st>>>(fn, in, in2, n, out);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+__global__ void debug_tristimulus_kernel(const float *wl, uint64_t n, float *out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const V3 t = tristimulus(wl[i]);
+        out[3 * i] = t.x; out[3 * i + 1] = t.y; out[3 * i + 2] = t.z;
+    }
+}
+
+cudaError_t launch_debug_tristimulus(const float *wl, uint64_t n, float *out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    uint64_t want = (n + 255) / 256;
+    unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+    debug_tristimulus_kernel<<<grid, 256, 0, st>>>(wl, n, out);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+__global__ void debug_camera_kernel(const DevScene sc, uint64_t seed, float aspect, uint64_t first,
+                                    uint64_t n, rl_ray *rays, rl_mapped_photon *xy) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Rng rng;
+        rng.init(seed, first + i);
+        const float wavelength = rng.wavelength();
+        const float x = rng.bi_unit();
+        const float y = rng.bi_unit() / aspect;
+        const float t = rng.unit();
+        const Ray r = camera_ray(sc.camera, x, y, wavelength, t, rng);
+        rl_ray o;
+        o.origin = rl_vec3{r.origin.x, r.origin.y, r.origin.z};
+        o.direction = rl_vec3{r.direction.x, r.direction.y, r.direction.z};
+        o.wavelength = wavelength;
+        o.probability = 1.0f;
+        rays[i] = o;
+        if (xy) { xy[i].x = x; xy[i].y = y; xy[i].wavelength = wavelength; xy[i].probability = t; }
+    }
+}
+
+cudaError_t launch_debug_camera(const DevScene &sc, uint64_t seed, uint32_t width, uint32_t height,
+                                uint64_t first, uint64_t n, rl_ray *rays, rl_mapped_photon *xy,
+                                cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    uint64_t want = (n + 127) / 128;
+    unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+    debug_camera_kernel<<<grid, 128, 0, st>>>(sc, seed, (float)width / (float)height, first, n, rays, xy);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace rl
