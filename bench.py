@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s of the hot path on BASELINE.json configs[1]:
+the reference's built-in scene (app.rs:166-363), 1024x1024, 256 spp, 1xB200.
+
+A step is one full pass of the fused trace+splat path over the workload:
+2^28 photons (= 256 spp x 1024^2; 512 reference batches of 524 288,
+trace_unit.rs:67) traced and splatted into the XYZ accumulator.  A ray is one
+Scene::intersect call (scene.rs:39), counted on the device.
+
+  python bench.py --gpus N --steps K --warmup W          # this engine
+  python bench.py --impl reference ...                    # the reference's CPU path (oracle port)
+
+Under torchrun (N > 1) every rank traces its own 2^28-photon id range (weak
+scaling: the job renders N x 256 spp), the XYZ framebuffers are summed onto
+rank 0 with one NCCL reduce and gathered there (gather_unit.rs:49-64).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH = HEIGHT = 1024
+SPP = 256
+PHOTONS_PER_STEP = WIDTH * HEIGHT * SPP          # 2^28
+SEED = 0x5EED
+WORKLOAD = "built-in scene (app.rs:166-363, 339 objects), 1024x1024, 256 spp = 2^28 photons per step"
+
+# algorithmic bytes (DESIGN.md "Kernels")
+SPLAT_FUSED_BYTES_PER_PHOTON = 48      # 4 px x 3 ch x 4 B accumulator payload, no record round trip
+SPLAT_BYTES_PER_PHOTON = 64            # + 16 B MappedPhoton read
+GATHER_BYTES_PER_PIXEL = 72            # read px/acc/comp, write acc/comp, clear px (12 B each)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 9:
+                self.samples.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[1])); mx.append(float(s[2])); power.append(float(s[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, s[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class DeviceView:
+    """Zero-copy torch view of a unit's device buffer (for the NCCL reduce)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def cpu_reference_run(orc, desc, n_photons, threads, first=0):
+    """The reference's CPU pipeline shape on host threads (oracle port, glibc math)."""
+    # the bounded sample is cut into 8 batches per thread (the reference's 524 288-photon batch
+    # would leave most threads idle on a sample this small); throughput is batch-size invariant
+    batch = max(1024, n_photons // (threads * 8))
+    _, ct, secs = orc.render_mt(desc, SEED, WIDTH, HEIGHT, first, n_photons, threads,
+                                mode=orc.MATH_LIBM, batch=batch, want_image=False)
+    return ct["rays"], secs
+
+
+def cpu_sample_size(orc, desc, threads, target_seconds):
+    probe = max(threads * 4096, 16384)
+    rays, secs = cpu_reference_run(orc, desc, probe, threads, first=1 << 40)
+    rate = probe / max(secs, 1e-6)
+    n = int(rate * target_seconds)
+    return max(probe, (n // 4096) * 4096)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.
+    The reference is Rust and cannot be compiled here (no rustc/cargo in the
+    image), so this is the oracle port of it, all host threads, glibc math."""
+    if rank != 0:
+        return
+    import __graft_entry__ as entry
+    entry.build_oracle()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as orc
+    pkg = entry.load_package()
+    desc = pkg.SceneBuilder(pkg.SCENE_C2).desc()
+    threads = orc.hardware_threads()
+    n = cpu_sample_size(orc, desc, threads, 6.0)
+    for i in range(args.warmup):
+        cpu_reference_run(orc, desc, n, threads, first=i * n)
+    rays = 0
+    secs = 0.0
+    for i in range(args.steps):
+        r, s = cpu_reference_run(orc, desc, n, threads, first=(args.warmup + i) * n)
+        rays += r
+        secs += s
+    value = rays / secs / 1e6
+    sample = f"{n} photons per step (of the workload's 2^28), {threads} threads, 8 batches per thread"
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "photons_per_s": n * args.steps / secs,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--photons", type=int, default=PHOTONS_PER_STEP, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import __graft_entry__ as entry
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = entry.load_package()
+    if pkg.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
+
+    n = args.photons
+    builder = pkg.SceneBuilder(pkg.SCENE_C2)
+    desc = builder.desc()
+    scene = pkg.Scene(builder)
+    # a non-default torch stream: the units launch on it, so torch.cuda.Event records on the
+    # same stream the kernels run on (handle 0, the legacy default stream, means "own stream"
+    # to rl_*_set_stream)
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    stream = side.cuda_stream
+    assert stream != 0
+    trace = pkg.TraceUnit(rank, WIDTH, HEIGHT, seed=SEED, batch=n)
+    plot = pkg.PlotUnit(rank, WIDTH, HEIGHT)
+    gather = pkg.GatherUnit(WIDTH, HEIGHT)
+    for u in (trace, plot, gather):
+        u.set_stream(stream)
+    plot_ptr, plot_bytes = plot.device_buffer()
+    plot_view = torch.as_tensor(DeviceView(plot_ptr, (HEIGHT, WIDTH, 4)), device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    first = rank * n                                                     # this rank's photon ids
+
+    def step():
+        trace.render_fused(scene, plot, first, n)
+        if world > 1:
+            dist.reduce(plot_view, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            gather.accumulate(plot, clear=True)
+        elif world > 1:
+            plot.clear()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    rays0 = trace.ray_count()
+    pkg.reset_kernel_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b, c in ev:
+        flush.fill_(1)                       # L2 flush between timed steps, outside the timed events
+        a.record()
+        trace.render_fused(scene, plot, first, n)
+        b.record()                           # [a, b] = the trace+splat kernel alone
+        if world > 1:
+            dist.reduce(plot_view, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            gather.accumulate(plot, clear=True)
+        elif world > 1:
+            plot.clear()
+        c.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = pkg.kernel_launch_count()
+    step_ms = sum(a.elapsed_time(c) for a, _, c in ev)
+    kernel_ms = sum(a.elapsed_time(b) for a, b, _ in ev)
+    rays = trace.ray_count() - rays0
+    t = torch.tensor([step_ms, kernel_ms], dtype=torch.float64, device="cuda")
+    r = torch.tensor([rays], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    step_ms, kernel_ms = float(t[0]), float(t[1])
+    total_rays = int(r[0])
+    value = total_rays / (step_ms * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------
+    # every step: scene descriptor (host) -> rl_scene_create, fused trace+splat, gather, and the
+    # XYZ framebuffer copied back into pinned host memory
+    host_xyz = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float32).pin_memory().numpy()
+    h2d = desc.n_surfaces * 52 + desc.n_objects * 20 + 84
+    d2h = WIDTH * HEIGHT * 12
+    e2e_gather = pkg.GatherUnit(WIDTH, HEIGHT)
+    e2e_gather.set_stream(stream)
+
+    def e2e_step():
+        sc = pkg.Scene(desc)
+        trace.render_fused(sc, plot, first, n)
+        if world > 1:
+            dist.reduce(plot_view, dst=0, op=dist.ReduceOp.SUM)
+        e2e_gather.accumulate(plot, clear=True)
+        e2e_gather.download(out=host_xyz)
+        return sc
+
+    e2e_step()
+    barrier()
+    rays1 = trace.ray_count()
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_rays = trace.ray_count() - rays1
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    r = torch.tensor([e2e_rays], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    e2e_value = int(r[0]) / float(t[0]) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- secondary, bandwidth-shaped kernels (rank 0, N = 1 semantics) ----------------------
+    peak, peak_src = measured_peaks()
+
+    def time_ms(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        total = 0.0
+        for _ in range(reps):
+            flush.fill_(1)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            total += a.elapsed_time(b)
+        return total / reps
+
+    n_splat = 1 << 25                                   # 512 MiB of records > L2
+    tr2 = pkg.TraceUnit(100, WIDTH, HEIGHT, seed=SEED, batch=n_splat)
+    tr2.set_stream(stream)
+    tr2.render_range(scene, 0, n_splat, download=False)
+    splat_ms = time_ms(lambda: plot.plot(tr2), 5)
+    plot.clear()
+    gw = 4096                                           # 4096^2: 192 MiB acc + 256 MiB plot > L2
+    gp, gg = pkg.PlotUnit(101, gw, gw), pkg.GatherUnit(gw, gw)
+    gp.set_stream(stream); gg.set_stream(stream)
+    gather_ms = time_ms(lambda: gg.accumulate(gp, clear=True), 5)
+    del gp, gg, tr2
+
+    kernel_s = kernel_ms * 1e-3 / args.steps
+    photons_per_launch = n
+    achieved = photons_per_launch * SPLAT_FUSED_BYTES_PER_PHOTON / kernel_s / 1e9
+    roofline = {
+        "kernel": "trace_kernel (fused TraceUnit::render + PlotUnit::plot)",
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_photon": SPLAT_FUSED_BYTES_PER_PHOTON,
+        "note": ("the fused kernel is FP32-issue/divergence bound, not HBM bound: scene tables sit in shared "
+                 "memory and the 16.8 MB accumulator is L2-resident, so its HBM fraction is small by design; "
+                 "the bandwidth-shaped kernels are listed under `also`"),
+        "kernel_ms_per_launch": kernel_s * 1e3,
+        "also": [
+            {"kernel": "splat_kernel (PlotUnit::plot, 2^25 records)", "bound": "hbm",
+             "achieved": n_splat * SPLAT_BYTES_PER_PHOTON / (splat_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+             "frac": n_splat * SPLAT_BYTES_PER_PHOTON / (splat_ms * 1e-3) / 1e9 / peak, "ms": splat_ms},
+            {"kernel": "gather_kernel (GatherUnit::accumulate + clear, 4096^2)", "bound": "hbm",
+             "achieved": gw * gw * GATHER_BYTES_PER_PIXEL / (gather_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+             "frac": gw * gw * GATHER_BYTES_PER_PIXEL / (gather_ms * 1e-3) / 1e9 / peak, "ms": gather_ms},
+        ],
+    }
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        entry.build_oracle()
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as orc
+        threads = orc.hardware_threads()
+        n_cpu = cpu_sample_size(orc, desc, threads, 12.0)
+        c_rays, c_secs = cpu_reference_run(orc, desc, n_cpu, threads)
+        cpu_baseline = {"value": c_rays / c_secs / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                        "sample": f"{n_cpu} photons of the workload ({c_secs:.1f} s), 8 batches per thread, "
+                                  "C++ restatement of the reference CPU path (no Rust toolchain), glibc math"}
+
+    line = {
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "photons_per_step_per_gpu": n, "seed": SEED,
+                   "l2": "flushed (256 MiB write) between timed steps",
+                   "parallelism": f"photon-id partition x{world}, one NCCL reduce of the XYZ framebuffer per step"
+                   if world > 1 else "single GPU"},
+        "rays_per_photon": total_rays / (n * world * args.steps),
+        "mphotons_per_s": n * world * args.steps / (step_ms * 1e-3) / 1e6,
+        "batches_per_s": n * world * args.steps / (step_ms * 1e-3) / 524288,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
