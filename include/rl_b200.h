@@ -335,6 +335,15 @@ int rl_debug_camera_rays(const rl_scene *scene, uint64_t seed, uint32_t width, u
                          uint64_t first_photon, uint64_t n, rl_ray *out_rays,
                          rl_mapped_photon *out_xy);
 
+/* Self-check of the result-preserving culls: traces photon ids [first, first+n)
+ * with the brute-force Scene::intersect (every primitive, reference
+ * arithmetic) and evaluates the culled intersect beside it on every ray;
+ * reports the rays compared and how many differed in object, distance bits or
+ * primitive (must be 0). */
+int rl_debug_cull_check(const rl_scene *scene, uint64_t seed, uint32_t width, uint32_t height,
+                        uint64_t first_photon, uint64_t n, uint64_t *out_rays,
+                        uint64_t *out_mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -156,6 +156,7 @@ SYMBOLS = {
     "rl_debug_math": (_I, [_I, _P, _P, _U64, _P]),
     "rl_debug_tristimulus": (_I, [_P, _U64, _P]),
     "rl_debug_camera_rays": (_I, [_P, _U64, _U32, _U32, _U64, _U64, _P, _P]),
+    "rl_debug_cull_check": (_I, [_P, _U64, _U32, _U32, _U64, _U64, C.POINTER(_U64), C.POINTER(_U64)]),
 }
 
 _lib_handle = None
@@ -299,6 +300,12 @@ class Scene:
         out = np.zeros(rays.shape[0], dtype=HIT)
         _check(lib().rl_debug_intersect(self._h, _ptr(rays), rays.shape[0], _ptr(out)))
         return out
+
+    def cull_check(self, seed, width, height, first, n):
+        """(rays compared, rays where the culled intersect differed from brute force)."""
+        rays, bad = _U64(0), _U64(0)
+        _check(lib().rl_debug_cull_check(self._h, seed, width, height, first, n, C.byref(rays), C.byref(bad)))
+        return int(rays.value), int(bad.value)
 
     def camera_rays(self, seed, width, height, first, n):
         rays = np.zeros(n, dtype=RAY)

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -143,7 +144,8 @@ struct rl_tonemap_unit {
 namespace {
 
 struct Flat {
-    std::vector<float4> spheres, planes, paraboloids, leaves, compounds;
+    std::vector<float4> spheres, sphere_k, planes, paraboloids, leaves, compounds;
+    double cmax2 = 0.0;
     std::vector<uint32_t> ops, sphere_obj, plane_obj, paraboloid_obj, compound_obj;
 };
 
@@ -171,6 +173,71 @@ bool emit_compound(const rl_scene_desc *d, uint32_t node, Flat &fl, uint32_t fir
     if (!emit_compound(d, s.child[1], fl, first_leaf, depth + 1, lo2, hi2)) return false;
     fl.ops.push_back(1u | (lo1 << 8) | (hi1 << 16) | (hi2 << 24));
     lo = lo1; hi = hi2;
+    return true;
+}
+
+// Bounding sphere of the convex body cut out by half-spaces n_i.(x - p_i) < 0:
+// vertices = triple-plane intersections that satisfy every half-space, computed
+// in double; centre = their mean, radius = the largest distance, inflated by
+// 1 % + 0.05 so that any point the reference's f32 containment tests can accept
+// (geometry.rs:124-128 on positions rounded at magnitude ~1e2: slack ~1e-4)
+// lies strictly inside.  Returns false for unbounded or degenerate bodies.
+bool convex_bound(const std::vector<float4> &leaves, size_t first, size_t n, float4 &out) {
+    struct D3 { double x, y, z; };
+    auto dot3 = [](D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; };
+    auto cross3 = [](D3 a, D3 b) { return D3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; };
+    std::vector<D3> nrm(n), off(n);
+    for (size_t i = 0; i < n; i++) {
+        const float4 a = leaves[2 * (first + i)], b = leaves[2 * (first + i) + 1];
+        nrm[i] = D3{a.x, a.y, a.z};
+        off[i] = D3{b.x, b.y, b.z};
+    }
+    // unbounded iff the recession cone {u : n_i.u <= 0} is non-trivial; its extreme rays are
+    // cross products of normal pairs (a cone containing a line leaves no vertices at all)
+    for (size_t i = 0; i < n; i++)
+        for (size_t j = i + 1; j < n; j++) {
+            D3 u = cross3(nrm[i], nrm[j]);
+            double len = sqrt(dot3(u, u));
+            if (len < 1e-9) continue;
+            u = D3{u.x / len, u.y / len, u.z / len};
+            for (int sign = -1; sign <= 1; sign += 2) {
+                bool in_cone = true;
+                for (size_t m = 0; m < n && in_cone; m++)
+                    if (sign * dot3(nrm[m], u) > 1e-9) in_cone = false;
+                if (in_cone) return false;
+            }
+        }
+    std::vector<D3> verts;
+    for (size_t i = 0; i < n; i++)
+        for (size_t j = i + 1; j < n; j++)
+            for (size_t k = j + 1; k < n; k++) {
+                const D3 cjk = cross3(nrm[j], nrm[k]);
+                const double det = dot3(nrm[i], cjk);
+                if (fabs(det) < 1e-9) continue;
+                const double di = dot3(nrm[i], off[i]), dj = dot3(nrm[j], off[j]), dk = dot3(nrm[k], off[k]);
+                const D3 cki = cross3(nrm[k], nrm[i]), cij = cross3(nrm[i], nrm[j]);
+                const D3 x{(di * cjk.x + dj * cki.x + dk * cij.x) / det,
+                           (di * cjk.y + dj * cki.y + dk * cij.y) / det,
+                           (di * cjk.z + dj * cki.z + dk * cij.z) / det};
+                bool inside = true;
+                for (size_t m = 0; m < n && inside; m++) {
+                    const D3 r{x.x - off[m].x, x.y - off[m].y, x.z - off[m].z};
+                    if (dot3(r, nrm[m]) > 1e-6 * (1.0 + sqrt(dot3(x, x)))) inside = false;
+                }
+                if (inside) verts.push_back(x);
+            }
+    if (verts.size() < 4) return false;
+    D3 c{0, 0, 0};
+    for (const D3 &v : verts) { c.x += v.x; c.y += v.y; c.z += v.z; }
+    c = D3{c.x / verts.size(), c.y / verts.size(), c.z / verts.size()};
+    double r = 0.0;
+    for (const D3 &v : verts) {
+        const D3 e{v.x - c.x, v.y - c.y, v.z - c.z};
+        r = fmax(r, sqrt(dot3(e, e)));
+    }
+    if (!(r > 0.0) || !std::isfinite(r)) return false;
+    r = r * 1.01 + 0.05;
+    out = make_float4((float)c.x, (float)c.y, (float)c.z, (float)(r * r));
     return true;
 }
 
@@ -228,10 +295,14 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
                                         o.material.p2));
         const rl_surface &s = desc->surfaces[o.surface];
         switch (s.kind) {
-        case RL_SURFACE_SPHERE:
+        case RL_SURFACE_SPHERE: {
             fl.spheres.push_back(f4(s.a, s.s));
+            const double c2 = (double)s.a.x * s.a.x + (double)s.a.y * s.a.y + (double)s.a.z * s.a.z;
+            fl.sphere_k.push_back(f4(s.a, (float)(c2 - (double)s.s)));
+            if (c2 + (double)s.s > fl.cmax2) fl.cmax2 = c2 + (double)s.s;
             fl.sphere_obj.push_back(i);
             break;
+        }
         case RL_SURFACE_PLANE:
         case RL_SURFACE_HALFSPACE:
         case RL_SURFACE_CIRCLE:
@@ -257,7 +328,9 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
                 return fail(RL_ERR_UNSUPPORTED, "compound tree too deep");
             fl.compounds.push_back(make_float4(as_float(first_leaf), as_float(hi - lo),
                                                as_float(first_op), as_float(n_ops)));
-            fl.compounds.push_back(make_float4(0.f, 0.f, 0.f, -1.0f));  // no bound
+            float4 bound = make_float4(0.f, 0.f, 0.f, -1.0f);          // r^2 < 0: unbounded, never culled
+            convex_bound(fl.leaves, first_leaf, hi - lo, bound);
+            fl.compounds.push_back(bound);
             fl.compound_obj.push_back(i);
             break;
         }
@@ -280,6 +353,12 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     ds.off_leaves = append(blob, fl.leaves);            ds.n_leaves = (uint32_t)fl.leaves.size() / 2;
     ds.off_compounds = append(blob, fl.compounds);      ds.n_compounds = (uint32_t)fl.compounds.size() / 2;
     ds.off_ops = append(blob, fl.ops);                  ds.n_ops = (uint32_t)fl.ops.size();
+    ds.off_sphere_k = append(blob, fl.sphere_k);
+    if (fl.spheres.size() > 65535) {
+        delete sc;
+        return fail(RL_ERR_UNSUPPORTED, "more than 65535 spheres");
+    }
+    ds.sphere_cmax2 = (float)(fl.cmax2 * 1.0001);
     ds.off_sphere_obj = append(blob, fl.sphere_obj);
     ds.off_plane_obj = append(blob, fl.plane_obj);
     ds.off_paraboloid_obj = append(blob, fl.paraboloid_obj);
@@ -287,7 +366,7 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     if (blob.empty()) blob.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
     ds.blob_vec4 = (uint32_t)blob.size();
     ds.n_objects = desc->n_objects;
-    sc->smem = blob.size() * sizeof(float4);
+    sc->smem = trace_smem_bytes(ds, 256);
     if (sc->smem > sc->dev.max_smem) {
         delete sc;
         return fail(RL_ERR_UNSUPPORTED, "scene primitive tables exceed shared memory per CTA");
@@ -788,6 +867,23 @@ int rl_debug_intersect(const rl_scene *scene, const rl_ray *rays, uint64_t n, rl
     if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n * sizeof(rl_hit), cudaMemcpyDeviceToHost);
     cudaFree(d_rays); cudaFree(d_out);
     if (e != cudaSuccess) return fail(RL_ERR_CUDA, cudaGetErrorString(e));
+    return RL_OK;
+}
+
+int rl_debug_cull_check(const rl_scene *scene, uint64_t seed, uint32_t width, uint32_t height,
+                        uint64_t first_photon, uint64_t n, uint64_t *out_rays, uint64_t *out_mismatches) {
+    if (!scene || !out_rays || !out_mismatches || width == 0 || height == 0)
+        return fail(RL_ERR_INVALID, "bad argument");
+    RL_CUDA(cudaSetDevice(scene->dev.index));
+    unsigned long long *d = nullptr, h[2] = {0, 0};
+    RL_CUDA(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemset(d, 0, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = launch_debug_cull_check(scene->ds, seed, width, height, first_photon, n, d, d + 1, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(RL_ERR_CUDA, cudaGetErrorString(e));
+    *out_rays = h[0];
+    *out_mismatches = h[1];
     return RL_OK;
 }
 

@@ -9,8 +9,9 @@
 //   planes       n_planes      x 2 float4 {n.xyz, kind} {offset.xyz, r^2}
 //   paraboloids  n_paraboloids x 3 float4 {offset,0} {normal,0} {focal_point,0}
 //   leaves       n_leaves      x 2 float4 {n.xyz, 0} {offset.xyz, 0}   half-spaces of compounds
-//   compounds    n_compounds   x 2 float4 {first_leaf, n_leaves, first_op, n_ops} {bound c.xyz, bound r^2}
+//   compounds    n_compounds   x 2 float4 {first_leaf, n_leaves, first_op, n_ops} {bound c.xyz, bound r^2 (< 0: unbounded)}
 //   ops          n_ops         x uint32   post-order program of the compound trees
+//   sphere_k     n_spheres     x float4   {cx, cy, cz, |c|^2 - r^2}, record of the sphere pre-test
 //   *_obj                      x uint32   object index of each sphere/plane/paraboloid/compound
 //
 // The kernel copies the blob into shared memory once per CTA.  Per-object
@@ -44,15 +45,17 @@ struct DevScene {
     uint32_t off_leaves, n_leaves;
     uint32_t off_compounds, n_compounds;
     uint32_t off_ops, n_ops;
-    uint32_t off_sphere_obj, off_plane_obj, off_paraboloid_obj, off_compound_obj;
+    uint32_t off_sphere_obj, off_plane_obj, off_paraboloid_obj, off_compound_obj, off_sphere_k;
     const float4 *materials;  // per object
     uint32_t n_objects;
+    float sphere_cmax2;       // max (|centre|^2 + r^2) over the spheres (error bound of the pre-test)
     DevCamera camera;
 };
 
 // Views into the blob once it sits in shared memory.
 struct PrimTables {
     const float4 *spheres;
+    const float4 *sphere_k;   // {cx, cy, cz, |c|^2 - r^2} per sphere (pre-test record)
     const float4 *planes;
     const float4 *paraboloids;
     const float4 *leaves;
@@ -60,6 +63,8 @@ struct PrimTables {
     const uint32_t *ops;
     const uint32_t *sphere_obj, *plane_obj, *paraboloid_obj, *compound_obj;
     uint32_t n_spheres, n_planes, n_paraboloids, n_compounds;
+    float sphere_cmax2;
+    uint16_t *cand;           // per-thread candidate slots in shared memory: cand[slot * blockDim.x + tid]
 };
 
 __device__ __forceinline__ PrimTables make_tables(const DevScene &sc, const float4 *base) {
@@ -70,6 +75,7 @@ __device__ __forceinline__ PrimTables make_tables(const DevScene &sc, const floa
     t.leaves = base + sc.off_leaves;
     t.compounds = base + sc.off_compounds;
     t.ops = reinterpret_cast<const uint32_t *>(base + sc.off_ops);
+    t.sphere_k = base + sc.off_sphere_k;
     t.sphere_obj = reinterpret_cast<const uint32_t *>(base + sc.off_sphere_obj);
     t.plane_obj = reinterpret_cast<const uint32_t *>(base + sc.off_plane_obj);
     t.paraboloid_obj = reinterpret_cast<const uint32_t *>(base + sc.off_paraboloid_obj);
@@ -78,6 +84,8 @@ __device__ __forceinline__ PrimTables make_tables(const DevScene &sc, const floa
     t.n_planes = sc.n_planes;
     t.n_paraboloids = sc.n_paraboloids;
     t.n_compounds = sc.n_compounds;
+    t.sphere_cmax2 = sc.sphere_cmax2;
+    t.cand = reinterpret_cast<uint16_t *>(const_cast<float4 *>(base) + sc.blob_vec4);
     return t;
 }
 
@@ -298,8 +306,10 @@ __device__ __forceinline__ float compound_t(const PrimTables &tb, uint32_t first
     return st_t[0];
 }
 
-// Scene::intersect (scene.rs:39-60): closest hit over all objects.
-__device__ __forceinline__ Hit intersect_scene(const PrimTables &tb, const Ray &ray) {
+// Scene::intersect (scene.rs:39-60): closest hit over all objects, every
+// primitive evaluated with the reference's arithmetic.  Kept as the in-kernel
+// reference the culled version below is checked against (rl_debug_cull_check).
+__device__ __forceinline__ Hit intersect_scene_brute(const PrimTables &tb, const Ray &ray) {
     Hit best;
     best.t = 1.0e12f; best.obj = -1; best.code = RL_HIT_NONE;
     for (uint32_t i = 0; i < tb.n_spheres; i++) {
@@ -326,6 +336,105 @@ __device__ __forceinline__ Hit intersect_scene(const PrimTables &tb, const Ray &
     }
     for (uint32_t i = 0; i < tb.n_compounds; i++) {
         const float4 c4 = tb.compounds[2 * i];
+        uint32_t leaf;
+        const float t = compound_t(tb, __float_as_uint(c4.x), __float_as_uint(c4.z),
+                                   __float_as_uint(c4.w), ray, leaf);
+        if (t > 0.0f) consider(best, t, (int)tb.compound_obj[i], (RL_HIT_LEAF << 28) | leaf);
+    }
+    return best;
+}
+
+#define RL_CAND_SLOTS 8
+
+// Exact Sphere::intersect for the candidates a lane queued.
+__device__ __forceinline__ void flush_candidates(const PrimTables &tb, const Ray &ray, Hit &best,
+                                                 uint32_t &cnt) {
+    for (uint32_t k = 0; k < cnt; k++) {
+        const uint32_t i = tb.cand[k * blockDim.x + threadIdx.x];
+        const float t = sphere_t(tb.spheres[i], ray);
+        if (t > 0.0f) consider(best, t, (int)tb.sphere_obj[i], (RL_HIT_SPHERE << 28) | i);
+    }
+    cnt = 0;
+}
+
+// Scene::intersect with result-preserving culls.
+//
+// Spheres.  The reference accepts a sphere only if fl(b^2 - 4c) >= 0 and
+// t1 = (b - sqrt(disc)) / 2 > 0, which needs b > 0 (geometry.rs:204-240).
+// With B = d.(c - o) and C = |c - o|^2 - r^2 (so disc / 4 = B^2 - C), the
+// pre-test evaluates B and C from per-ray constants in 6 + 2 fused operations,
+//     B' = d.c - d.o,     C' = (|c|^2 - r^2) - 2 o.c + |o|^2,
+// and keeps the sphere iff B'^2 - C' >= -e1 and B' >= -e2, where e1, e2 bound
+// the rounding error of BOTH evaluations (reference and pre-test):
+//     |B'^2 - C' - disc_ref/4| <= 44 eps (cmax2 + |o|^2) max(1,|d|^2)   <  e1 = 2^-17 (cmax2 + |o|^2) max(1,|d|^2)
+//     |B' - b_ref/2|           <= 12 eps sqrt((cmax2 + |o|^2) |d|^2)    <  e2 = 2^-19 sqrt((cmax2 + |o|^2) |d|^2)
+// (eps = 2^-24, cmax2 = max |c|^2 + r^2; derivation in DESIGN.md "Culling").  Every survivor is then evaluated with the reference's exact
+// arithmetic (sphere_t), so the hit distance, the winner and every later
+// rounding are unchanged; culling only removes spheres the reference rejects.
+// Survivors are queued per lane and evaluated after the uniform loop, so the
+// warp does not diverge into the exact test once per sphere.
+//
+// Compounds.  A bounded convex body can only be hit where the ray passes its
+// bounding sphere (inflated on the host well beyond rounding); otherwise the
+// reference's recursion returns None.  Unbounded bodies carry r^2 < 0 and are
+// always evaluated.
+__device__ __forceinline__ Hit intersect_scene(const PrimTables &tb, const Ray &ray) {
+    Hit best;
+    best.t = 1.0e12f; best.obj = -1; best.code = RL_HIT_NONE;
+
+    const V3 o = ray.origin, d = ray.direction;
+    const float oo = fmaf(o.z, o.z, fmaf(o.y, o.y, o.x * o.x));
+    const float dd = fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x));
+    const float ndo = -fmaf(d.z, o.z, fmaf(d.y, o.y, d.x * o.x));
+    const float m2ox = -2.0f * o.x, m2oy = -2.0f * o.y, m2oz = -2.0f * o.z;
+    const float scale = (tb.sphere_cmax2 + oo) * fmaxf(1.0f, dd);
+    const float thr = -7.6293945e-6f * scale;                                          // -2^-17 * scale
+    const float bthr = -1.9073486e-6f * sqrtf((tb.sphere_cmax2 + oo) * dd) - 1.0e-30f;  // -2^-19 * ...
+
+    uint32_t cnt = 0;
+#pragma unroll 4
+    for (uint32_t i = 0; i < tb.n_spheres; i++) {
+        const float4 s = tb.sphere_k[i];                      // {cx, cy, cz, |c|^2 - r^2}
+        const float b = fmaf(d.x, s.x, fmaf(d.y, s.y, fmaf(d.z, s.z, ndo)));
+        const float c = fmaf(m2ox, s.x, fmaf(m2oy, s.y, fmaf(m2oz, s.z, s.w))) + oo;
+        const float disc = fmaf(b, b, -c);
+        if (disc >= thr && b >= bthr) {
+            tb.cand[cnt * blockDim.x + threadIdx.x] = (uint16_t)i;
+            cnt++;
+            if (cnt == RL_CAND_SLOTS) flush_candidates(tb, ray, best, cnt);
+        }
+    }
+    flush_candidates(tb, ray, best, cnt);
+
+    for (uint32_t i = 0; i < tb.n_planes; i++) {
+        const float4 n4 = tb.planes[2 * i], o4 = tb.planes[2 * i + 1];
+        float dn;
+        const float t = plane_t(mk(n4.x, n4.y, n4.z), mk(o4.x, o4.y, o4.z), ray, dn);
+        if (t > 0.0f) {
+            bool ok = true;
+            if (__float_as_uint(n4.w) == RL_SURFACE_CIRCLE) {  // geometry.rs:169-172
+                const V3 pos = ray.origin + ray.direction * t;
+                ok = magnitude_squared(pos - mk(o4.x, o4.y, o4.z)) <= o4.w;
+            }
+            if (ok) consider(best, t, (int)tb.plane_obj[i], (RL_HIT_PLANE << 28) | i);
+        }
+    }
+    for (uint32_t i = 0; i < tb.n_paraboloids; i++) {
+        const float t = paraboloid_t(tb.paraboloids + 3 * i, ray);
+        // the a == 0 branch admits t == 0 (geometry.rs:319: only t1 < 0 is rejected)
+        if (t >= 0.0f) consider(best, t, (int)tb.paraboloid_obj[i], (RL_HIT_PARABOLOID << 28) | i);
+    }
+    for (uint32_t i = 0; i < tb.n_compounds; i++) {
+        const float4 c4 = tb.compounds[2 * i], b4 = tb.compounds[2 * i + 1];
+        if (b4.w >= 0.0f) {
+            const float cx = b4.x - o.x, cy = b4.y - o.y, cz = b4.z - o.z;
+            const float bq = fmaf(cz, cz, fmaf(cy, cy, cx * cx));
+            const float bb = fmaf(d.z, cz, fmaf(d.y, cy, d.x * cx));
+            const float bc = bq - b4.w;                       // > 0: origin outside the bound
+            const bool behind = bc > 0.0f && bb < 0.0f;
+            const bool misses = fmaf(bb, bb, -(bc * dd)) < 0.0f;
+            if (behind || misses) continue;
+        }
         uint32_t leaf;
         const float t = compound_t(tb, __float_as_uint(c4.x), __float_as_uint(c4.z),
                                    __float_as_uint(c4.w), ray, leaf);

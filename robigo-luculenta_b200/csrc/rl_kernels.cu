@@ -118,11 +118,13 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
     if ((threadIdx.x & 31) == 0 && a.ray_counter) atomicAdd(a.ray_counter, (unsigned long long)rays);
 }
 
-size_t trace_smem_bytes(const DevScene &sc) { return (size_t)sc.blob_vec4 * sizeof(float4); }
+size_t trace_smem_bytes(const DevScene &sc, int threads) {
+    return (size_t)sc.blob_vec4 * sizeof(float4) + (size_t)RL_CAND_SLOTS * threads * sizeof(uint16_t);
+}
 
 cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count, cudaStream_t st) {
     if (p.n_photons == 0) return cudaSuccess;
-    const size_t smem = trace_smem_bytes(sc);
+    const size_t smem = trace_smem_bytes(sc, RL_TRACE_THREADS);
     cudaError_t err = cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem);
     if (err != cudaSuccess) return err;
@@ -400,13 +402,73 @@ __global__ void debug_intersect_kernel(const DevScene sc, const rl_ray *rays, ui
 cudaError_t launch_debug_intersect(const DevScene &sc, const rl_ray *rays, uint64_t n, rl_hit *out,
                                    cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    const size_t smem = trace_smem_bytes(sc);
+    const size_t smem = trace_smem_bytes(sc, 128);
     cudaError_t err = cudaFuncSetAttribute(debug_intersect_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     uint64_t want = (n + 127) / 128;
     unsigned grid = (unsigned)(want < 148 * 4 ? want : 148 * 4);
     debug_intersect_kernel<<<grid, 128, smem, st>>>(sc, rays, n, out);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// Traces paths with the brute-force Scene::intersect as the driver and
+// evaluates the culled one on every ray beside it; counts disagreements.
+__global__ void __launch_bounds__(128)
+debug_cull_check_kernel(const DevScene sc, uint64_t seed, float aspect, uint64_t first, uint64_t n,
+                        unsigned long long *rays_out, unsigned long long *mismatches) {
+    extern __shared__ float4 smem[];
+    for (uint32_t i = threadIdx.x; i < sc.blob_vec4; i += blockDim.x) smem[i] = sc.blob[i];
+    __syncthreads();
+    const PrimTables tb = make_tables(sc, smem);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long rays = 0, bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Rng rng;
+        rng.init(seed, first + i);
+        const float wavelength = rng.wavelength();
+        const float x = rng.bi_unit();
+        const float y = rng.bi_unit() / aspect;
+        const float t = rng.unit();
+        Ray ray = camera_ray(sc.camera, x, y, wavelength, t, rng);
+        float intensity = 1.0f, continue_chance = 1.0f;
+        for (;;) {
+            rays++;
+            const Hit hit = intersect_scene_brute(tb, ray);
+            const Hit culled = intersect_scene(tb, ray);
+            if (hit.obj != culled.obj || __float_as_uint(hit.t) != __float_as_uint(culled.t) ||
+                hit.code != culled.code)
+                bad++;
+            if (hit.obj < 0) break;
+            const float4 m = __ldg(sc.materials + hit.obj);
+            if (__float_as_uint(m.x) == RL_MATERIAL_BLACKBODY) break;
+            const Surf s = surface_at(tb, ray, hit);
+            float probability;
+            const V3 dir = material_bounce(m, ray, s, rng, probability);
+            intensity = intensity * probability;
+            ray.direction = dir;
+            ray.origin = s.position + dir * 0.00001f;
+            continue_chance = continue_chance * 0.96f;
+            if (rng.unit() * 0.85f > continue_chance * (1.0f - spec_exp(intensity * -20.0f))) break;
+        }
+    }
+    atomicAdd(rays_out, rays);
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t launch_debug_cull_check(const DevScene &sc, uint64_t seed, uint32_t width, uint32_t height,
+                                    uint64_t first, uint64_t n, unsigned long long *rays,
+                                    unsigned long long *mismatches, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const size_t smem = trace_smem_bytes(sc, 128);
+    cudaError_t err = cudaFuncSetAttribute(debug_cull_check_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    uint64_t want = (n + 127) / 128;
+    unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+    debug_cull_check_kernel<<<grid, 128, smem, st>>>(sc, seed, (float)width / (float)height, first, n,
+                                                     rays, mismatches);
     g_launches++;
     return cudaGetLastError();
 }

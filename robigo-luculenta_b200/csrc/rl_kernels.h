@@ -19,7 +19,7 @@ struct TraceLaunch {
 };
 
 // Dynamic shared memory the trace kernels need for a scene.
-size_t trace_smem_bytes(const DevScene &sc);
+size_t trace_smem_bytes(const DevScene &sc, int threads);
 // K1: TraceUnit::render (+ PlotUnit::plot when accum != nullptr).
 cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count, cudaStream_t st);
 // K2: PlotUnit::plot over device records.
@@ -45,6 +45,10 @@ cudaError_t launch_debug_tristimulus(const float *wl, uint64_t n, float *out, cu
 cudaError_t launch_debug_camera(const DevScene &sc, uint64_t seed, uint32_t width, uint32_t height,
                                 uint64_t first, uint64_t n, rl_ray *rays, rl_mapped_photon *xy,
                                 cudaStream_t st);
+
+cudaError_t launch_debug_cull_check(const DevScene &sc, uint64_t seed, uint32_t width, uint32_t height,
+                                    uint64_t first, uint64_t n, unsigned long long *rays,
+                                    unsigned long long *mismatches, cudaStream_t st);
 
 uint64_t kernel_launches();
 void kernel_launches_reset();

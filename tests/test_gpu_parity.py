@@ -454,3 +454,15 @@ def test_error_behaviour(gpu):
     with pytest.raises(gpu.RlError) as e:
         gpu.Scene(desc)
     assert e.value.code == gpu.RL_ERR_UNSUPPORTED
+
+
+# --------------------------------------------------------------------- culling
+@pytest.mark.parametrize("which,param,w,h,n", [(2, 0, 1024, 1024, 1 << 21), (3, 0, 1024, 1024, 1 << 20),
+                                               (4, 0, 2048, 2048, 1 << 17), (1, 0, 256, 256, 1 << 18)])
+def test_culls_are_result_preserving(gpu, which, param, w, h, n):
+    # every ray of n traced paths: culled Scene::intersect == brute force over all primitives
+    # (object, distance bits, primitive), evaluated side by side on the device
+    sc = gpu.Scene(gpu.SceneBuilder(which, param))
+    rays, bad = sc.cull_check(SEED + which, w, h, 7 * n, n)
+    assert rays >= n
+    assert bad == 0, f"{bad} of {rays} rays differ between culled and brute-force intersect"
