@@ -353,6 +353,8 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     ds.off_leaves = append(blob, fl.leaves);            ds.n_leaves = (uint32_t)fl.leaves.size() / 2;
     ds.off_compounds = append(blob, fl.compounds);      ds.n_compounds = (uint32_t)fl.compounds.size() / 2;
     ds.off_ops = append(blob, fl.ops);                  ds.n_ops = (uint32_t)fl.ops.size();
+    // the pre-test scans four records per step: pad with records no ray selects
+    while (fl.sphere_k.size() % 4 != 0) fl.sphere_k.push_back(make_float4(0.f, 0.f, 0.f, 1.0e30f));
     ds.off_sphere_k = append(blob, fl.sphere_k);
     if (fl.spheres.size() > 65535) {
         delete sc;

@@ -24,35 +24,17 @@
 
 #include "../../include/rl_b200.h"
 #include "rl_math.cuh"
+#include "rl_scene_layout.h"
 
 namespace rl {
 
-struct DevCamera {
-    uint32_t kind;
-    float px, py, pz;
-    float field_of_view, focal_distance, depth_of_field, chromatic_abberation;
-    float qx, qy, qz, qw;
-    float phi_base, phi_rate, alpha_base, alpha_rate, distance_base, distance_rate, focal_factor;
-};
+// Dynamic shared memory of every kernel that traces:
+//   [ PrimTables header | primitive blob | per-thread candidate queues ]
+extern __shared__ float4 rl_smem[];
 
-struct DevScene {
-    const float4 *blob;       // global copy of the primitive blob
-    uint32_t blob_vec4;       // its size in float4 units
-    // offsets into the blob, in float4 units
-    uint32_t off_spheres, n_spheres;
-    uint32_t off_planes, n_planes;
-    uint32_t off_paraboloids, n_paraboloids;
-    uint32_t off_leaves, n_leaves;
-    uint32_t off_compounds, n_compounds;
-    uint32_t off_ops, n_ops;
-    uint32_t off_sphere_obj, off_plane_obj, off_paraboloid_obj, off_compound_obj, off_sphere_k;
-    const float4 *materials;  // per object
-    uint32_t n_objects;
-    float sphere_cmax2;       // max (|centre|^2 + r^2) over the spheres (error bound of the pre-test)
-    DevCamera camera;
-};
-
-// Views into the blob once it sits in shared memory.
+// Views into the blob once it sits in shared memory.  The struct itself lives
+// at the start of shared memory so that out-of-line device functions reach the
+// tables without carrying them in registers or on the stack.
 struct PrimTables {
     const float4 *spheres;
     const float4 *sphere_k;   // {cx, cy, cz, |c|^2 - r^2} per sphere (pre-test record)
@@ -67,82 +49,131 @@ struct PrimTables {
     uint16_t *cand;           // per-thread candidate slots in shared memory: cand[slot * blockDim.x + tid]
 };
 
-__device__ __forceinline__ PrimTables make_tables(const DevScene &sc, const float4 *base) {
-    PrimTables t;
-    t.spheres = base + sc.off_spheres;
-    t.planes = base + sc.off_planes;
-    t.paraboloids = base + sc.off_paraboloids;
-    t.leaves = base + sc.off_leaves;
-    t.compounds = base + sc.off_compounds;
-    t.ops = reinterpret_cast<const uint32_t *>(base + sc.off_ops);
-    t.sphere_k = base + sc.off_sphere_k;
-    t.sphere_obj = reinterpret_cast<const uint32_t *>(base + sc.off_sphere_obj);
-    t.plane_obj = reinterpret_cast<const uint32_t *>(base + sc.off_plane_obj);
-    t.paraboloid_obj = reinterpret_cast<const uint32_t *>(base + sc.off_paraboloid_obj);
-    t.compound_obj = reinterpret_cast<const uint32_t *>(base + sc.off_compound_obj);
-    t.n_spheres = sc.n_spheres;
-    t.n_planes = sc.n_planes;
-    t.n_paraboloids = sc.n_paraboloids;
-    t.n_compounds = sc.n_compounds;
-    t.sphere_cmax2 = sc.sphere_cmax2;
-    t.cand = reinterpret_cast<uint16_t *>(const_cast<float4 *>(base) + sc.blob_vec4);
-    return t;
+#define RL_TABLES_VEC4 ((sizeof(PrimTables) + 15) / 16)
+#define RL_CAND_SLOTS 12       // queued sphere candidates per lane
+#define RL_COMPOUND_SLOTS 4    // queued compound candidates per lane
+
+__device__ __forceinline__ const PrimTables &tables() {
+    return *reinterpret_cast<const PrimTables *>(rl_smem);
+}
+
+// Block-wide: copy the blob into shared memory and publish the table views.
+__device__ __forceinline__ void setup_tables(const DevScene &sc) {
+    float4 *base = rl_smem + RL_TABLES_VEC4;
+    for (uint32_t i = threadIdx.x; i < sc.blob_vec4; i += blockDim.x) base[i] = sc.blob[i];
+    if (threadIdx.x == 0) {
+        PrimTables t;
+        t.spheres = base + sc.off_spheres;
+        t.planes = base + sc.off_planes;
+        t.paraboloids = base + sc.off_paraboloids;
+        t.leaves = base + sc.off_leaves;
+        t.compounds = base + sc.off_compounds;
+        t.ops = reinterpret_cast<const uint32_t *>(base + sc.off_ops);
+        t.sphere_k = base + sc.off_sphere_k;
+        t.sphere_obj = reinterpret_cast<const uint32_t *>(base + sc.off_sphere_obj);
+        t.plane_obj = reinterpret_cast<const uint32_t *>(base + sc.off_plane_obj);
+        t.paraboloid_obj = reinterpret_cast<const uint32_t *>(base + sc.off_paraboloid_obj);
+        t.compound_obj = reinterpret_cast<const uint32_t *>(base + sc.off_compound_obj);
+        t.n_spheres = sc.n_spheres;
+        t.n_planes = sc.n_planes;
+        t.n_paraboloids = sc.n_paraboloids;
+        t.n_compounds = sc.n_compounds;
+        t.sphere_cmax2 = sc.sphere_cmax2;
+        t.cand = reinterpret_cast<uint16_t *>(base + sc.blob_vec4);
+        *reinterpret_cast<PrimTables *>(rl_smem) = t;
+    }
+    __syncthreads();
+}
+
+// Shared memory a tracing kernel needs with `threads` threads per block.
+inline size_t tracing_smem_bytes(const DevScene &sc, int threads) {
+    return (RL_TABLES_VEC4 + (size_t)sc.blob_vec4) * sizeof(float4)
+           + (size_t)(RL_CAND_SLOTS + RL_COMPOUND_SLOTS) * threads * sizeof(uint16_t);
 }
 
 // ---------------------------------------------------------------------- RNG
 // Philox4x32-10, counter (photon_lo, photon_hi, block, 0), key (seed_lo,
 // seed_hi).  Stands in for rand::random (monte_carlo.rs:22-28).
+// One Philox4x32-10 block; out of line so that the ten draw sites share it.
+static __device__ __noinline__ uint4 philox_block(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
+                                                  uint32_t block) {
+    uint32_t x0 = c0, x1 = c1, x2 = block, x3 = 0u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, x0), l0 = 0xD2511F53u * x0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, x2), l1 = 0xCD9E8D57u * x2;
+        const uint32_t y0 = h1 ^ x1 ^ k0, y2 = h0 ^ x3 ^ k1;
+        x0 = y0; x1 = l1; x2 = y2; x3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(x0, x1, x2, x3);
+}
+
 struct Rng {
     uint32_t k0, k1, c0, c1, block;
     uint32_t b0, b1, b2, b3;
     uint32_t left;
 
-    RL_HD void init(uint64_t seed, uint64_t photon) {
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t photon) {
         k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
         c0 = (uint32_t)photon; c1 = (uint32_t)(photon >> 32);
         block = 0; left = 0; b0 = b1 = b2 = b3 = 0;
     }
-    RL_HD void refill() {
-        uint32_t x0 = c0, x1 = c1, x2 = block, x3 = 0u, ka = k0, kb = k1;
-#pragma unroll
-        for (int r = 0; r < 10; r++) {
-#if defined(__CUDA_ARCH__)
-            const uint32_t h0 = __umulhi(0xD2511F53u, x0), l0 = 0xD2511F53u * x0;
-            const uint32_t h1 = __umulhi(0xCD9E8D57u, x2), l1 = 0xCD9E8D57u * x2;
-#else
-            const uint64_t p0 = (uint64_t)0xD2511F53u * x0, p1 = (uint64_t)0xCD9E8D57u * x2;
-            const uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0;
-            const uint32_t h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
-#endif
-            const uint32_t y0 = h1 ^ x1 ^ ka, y2 = h0 ^ x3 ^ kb;
-            x0 = y0; x1 = l1; x2 = y2; x3 = l0;
-            ka += 0x9E3779B9u; kb += 0xBB67AE85u;
+    __device__ __forceinline__ uint32_t next_u32() {
+        if (left == 0) {
+            const uint4 v = philox_block(k0, k1, c0, c1, block);
+            b0 = v.x; b1 = v.y; b2 = v.z; b3 = v.w;
+            block++;
+            left = 4;
         }
-        b0 = x0; b1 = x1; b2 = x2; b3 = x3;
-        block++;
-        left = 4;
-    }
-    RL_HD uint32_t next_u32() {
-        if (left == 0) refill();
         const uint32_t v = b0;
         b0 = b1; b1 = b2; b2 = b3;
         left--;
         return v;
     }
-    // Closed01<f32> of rand 0.3.11 (monte_carlo.rs:25-28): in [0, 1]
-    RL_HD float unit() { return (float)(next_u32() >> 8) / 16777215.0f; }
+    // Closed01<f32> of rand 0.3.11 (monte_carlo.rs:25-28): n / (2^24 - 1) for the 24-bit n,
+    // in [0, 1].  n / (2^24 - 1) = n 2^-24 (1 + 2^-24 + ...) exceeds the exactly representable
+    // n 2^-24 by between half and one ulp, so the correctly rounded quotient is its successor:
+    // one integer add on the bit pattern instead of an IEEE division (identity checked for
+    // all 2^24 values in tests/test_oracle_kat.py; the checker does the division).
+    __device__ __forceinline__ float unit() {
+        const uint32_t n = next_u32() >> 8;
+        const float scaled = (float)n * 5.9604644775390625e-8f;
+        return n == 0u ? 0.0f : __uint_as_float(__float_as_uint(scaled) + 1u);
+    }
     // rand::random::<f32>() (monte_carlo.rs:37): in [0, 1)
-    RL_HD float half_open() { return (float)(next_u32() >> 8) * 5.9604644775390625e-8f; }
-    RL_HD float bi_unit() { return unit() * 2.0f - 1.0f; }             // monte_carlo.rs:31-33
-    RL_HD float longitude() { return half_open() * RL_PI * 2.0f; }     // monte_carlo.rs:36-38
-    RL_HD float wavelength() { return unit() * 400.0f + 380.0f; }      // monte_carlo.rs:41-43
+    __device__ __forceinline__ float half_open() { return (float)(next_u32() >> 8) * 5.9604644775390625e-8f; }
+    __device__ __forceinline__ float bi_unit() { return unit() * 2.0f - 1.0f; }             // monte_carlo.rs:31-33
+    __device__ __forceinline__ float longitude() { return half_open() * RL_PI * 2.0f; }     // monte_carlo.rs:36-38
+    __device__ __forceinline__ float wavelength() { return unit() * 400.0f + 380.0f; }      // monte_carlo.rs:41-43
 };
+
+// sin and cos through one shared out-of-line copy (seven call sites).
+static __device__ __noinline__ float2 sincos_call(float x) {
+    float s, c;
+    spec_sincos(x, s, c);
+    return make_float2(s, c);
+}
+__device__ __forceinline__ Quat rotation_dev(float x, float y, float z, float angle) {   // quaternion.rs:36-45
+    const float2 sc = sincos_call(angle * 0.5f);
+    return mkq(sc.x * x, sc.x * y, sc.x * z, sc.y);
+}
 
 struct Ray { V3 origin, direction; float wavelength; };
 
+// A ray that hits nothing and queues nothing: lanes without a live path trace
+// it so that the warp-wide votes inside intersect_scene stay convergent.
+__device__ __forceinline__ Ray idle_ray() {
+    Ray r;
+    r.origin = mk(1.0e6f, 1.0e6f, 1.0e6f);
+    r.direction = mk(1.0f, 0.0f, 0.0f);
+    r.wavelength = 0.0f;
+    return r;
+}
+
 // ------------------------------------------------------------------- camera
 // app.rs:327-357 (make_camera) in closed form, camera.rs:94-108 + :47-90.
-RL_HD Ray camera_ray(const DevCamera &cm, float x, float y, float wavelength, float t, Rng &rng) {
+__device__ __forceinline__ Ray camera_ray(const DevCamera &cm, float x, float y, float wavelength, float t, Rng &rng) {
     V3 position;
     Quat orientation;
     float focal_distance;
@@ -154,24 +185,24 @@ RL_HD Ray camera_ray(const DevCamera &cm, float x, float y, float wavelength, fl
         const float phi = RL_PI * (cm.phi_base + cm.phi_rate * t);
         const float alpha = RL_PI * (cm.alpha_base + cm.alpha_rate * t);
         const float distance = cm.distance_base + cm.distance_rate * t;
-        float sa, ca, sp, cp;
-        spec_sincos(alpha, sa, ca);
-        spec_sincos(phi, sp, cp);
+        const float2 a2 = sincos_call(alpha), p2 = sincos_call(phi);
+        const float sa = a2.x, ca = a2.y, sp = p2.x, cp = p2.y;
         position = mk(ca * sp * distance, ca * cp * distance, sa * distance);
-        orientation = rotation(0.0f, 0.0f, -1.0f, phi + RL_PI) * rotation(1.0f, 0.0f, 0.0f, -alpha);
+        orientation = rotation_dev(0.0f, 0.0f, -1.0f, phi + RL_PI) * rotation_dev(1.0f, 0.0f, 0.0f, -alpha);
         focal_distance = distance * cm.focal_factor;
     }
     const float dof_angle = rng.longitude();
     const float dof_radius = rng.unit() / cm.depth_of_field;
     const float d = (wavelength - 580.0f) / 200.0f;
     const float chromatic_zoom = 1.0f + d * cm.chromatic_abberation;
-    const float screen_distance = 1.0f / spec_tan(cm.field_of_view * 0.5f);
+    const float2 fov = sincos_call(cm.field_of_view * 0.5f);
+    const float screen_distance = 1.0f / (fov.x / fov.y);              // 1 / tan, spec_tan = sin / cos
     const float xs = x * chromatic_zoom;
     const float ys = y * chromatic_zoom;
     const V3 direction = normalise(mk(xs, screen_distance, -ys));
     const V3 focus_point = direction * (focal_distance / direction.y);
-    float sd, cd;
-    spec_sincos(dof_angle, sd, cd);
+    const float2 dof = sincos_call(dof_angle);
+    const float sd = dof.x, cd = dof.y;
     const V3 lens_point = mk(cd * dof_radius, 0.0f, sd * dof_radius);
     Ray r;
     r.origin = position + rotate(lens_point, orientation);
@@ -256,10 +287,9 @@ __device__ __forceinline__ float paraboloid_t(const float4 *p, const Ray &ray) {
 // op word: bits 0-1 kind (0 = leaf, 1 = compound); leaf: bits 8.. = leaf index
 // relative to the compound's first leaf; compound: lo = bits 8-15, mid = bits
 // 16-23, hi = bits 24-31 (children own leaves [lo, mid) and [mid, hi)).
-#define RL_MAX_COMPOUND_STACK 8
-__device__ __forceinline__ float compound_t(const PrimTables &tb, uint32_t first_leaf,
-                                            uint32_t first_op, uint32_t n_ops, const Ray &ray,
-                                            uint32_t &leaf_out) {
+__device__ __forceinline__ float compound_t(uint32_t first_leaf, uint32_t first_op, uint32_t n_ops,
+                                            const Ray &ray, uint32_t &leaf_out) {
+    const PrimTables &tb = tables();
     float st_t[RL_MAX_COMPOUND_STACK];
     uint32_t st_leaf[RL_MAX_COMPOUND_STACK];
     int sp = 0;
@@ -309,7 +339,8 @@ __device__ __forceinline__ float compound_t(const PrimTables &tb, uint32_t first
 // Scene::intersect (scene.rs:39-60): closest hit over all objects, every
 // primitive evaluated with the reference's arithmetic.  Kept as the in-kernel
 // reference the culled version below is checked against (rl_debug_cull_check).
-__device__ __forceinline__ Hit intersect_scene_brute(const PrimTables &tb, const Ray &ray) {
+__device__ __forceinline__ Hit intersect_scene_brute(const Ray &ray) {
+    const PrimTables &tb = tables();
     Hit best;
     best.t = 1.0e12f; best.obj = -1; best.code = RL_HIT_NONE;
     for (uint32_t i = 0; i < tb.n_spheres; i++) {
@@ -337,27 +368,45 @@ __device__ __forceinline__ Hit intersect_scene_brute(const PrimTables &tb, const
     for (uint32_t i = 0; i < tb.n_compounds; i++) {
         const float4 c4 = tb.compounds[2 * i];
         uint32_t leaf;
-        const float t = compound_t(tb, __float_as_uint(c4.x), __float_as_uint(c4.z),
-                                   __float_as_uint(c4.w), ray, leaf);
+        const float t = compound_t(__float_as_uint(c4.x), __float_as_uint(c4.z), __float_as_uint(c4.w), ray, leaf);
         if (t > 0.0f) consider(best, t, (int)tb.compound_obj[i], (RL_HIT_LEAF << 28) | leaf);
     }
     return best;
 }
 
-#define RL_CAND_SLOTS 8
-
-// Exact Sphere::intersect for the candidates a lane queued.
-__device__ __forceinline__ void flush_candidates(const PrimTables &tb, const Ray &ray, Hit &best,
-                                                 uint32_t &cnt) {
-    for (uint32_t k = 0; k < cnt; k++) {
-        const uint32_t i = tb.cand[k * blockDim.x + threadIdx.x];
-        const float t = sphere_t(tb.spheres[i], ray);
-        if (t > 0.0f) consider(best, t, (int)tb.sphere_obj[i], (RL_HIT_SPHERE << 28) | i);
+// Conservative slab test of a convex body against the ray, with every
+// half-space moved outwards by RL_SLAB_INFLATE.  A hit the reference returns
+// lies on one leaf plane and passes the f32 containment test of every other
+// leaf (each sits in a sibling subtree on the way to the root, geometry.rs:
+// 386-388), so it is inside the inflated body up to rounding (~1e-5 at the
+// scene's coordinate magnitudes); if the inflated body's [enter, exit]
+// interval is empty, ends before the origin, or starts beyond the best hit so
+// far, the exact evaluation cannot change the result and is skipped.
+#define RL_SLAB_INFLATE 2.0e-3f
+__device__ __forceinline__ bool slab_may_hit(uint32_t first_leaf, uint32_t n_leaves, const Ray &ray,
+                                             float best_t) {
+    const PrimTables &tb = tables();
+    float t_enter = 0.0f, t_exit = 3.0e38f;
+    bool outside_parallel = false;
+    for (uint32_t k = first_leaf; k < first_leaf + n_leaves; k++) {
+        const float4 n4 = tb.leaves[2 * k], o4 = tb.leaves[2 * k + 1];
+        const float dn = fmaf(n4.z, ray.direction.z, fmaf(n4.y, ray.direction.y, n4.x * ray.direction.x));
+        const float s0 = fmaf(n4.z, ray.origin.z - o4.z,
+                              fmaf(n4.y, ray.origin.y - o4.y, n4.x * (ray.origin.x - o4.x))) - RL_SLAB_INFLATE;
+        const float tk = __fdividef(-s0, dn);
+        if (dn < 0.0f) t_enter = fmaxf(t_enter, tk);
+        else if (dn > 0.0f) t_exit = fminf(t_exit, tk);
+        else if (s0 > 0.0f) outside_parallel = true;
     }
-    cnt = 0;
+    if (outside_parallel) return false;
+    if (t_exit < 0.0f) return false;
+    if (t_enter * 0.9999f - 1.0e-3f > t_exit) return false;
+    if (t_enter * 0.9999f - 1.0e-3f > best_t) return false;
+    return true;
 }
 
-// Scene::intersect with result-preserving culls.
+// Scene::intersect with result-preserving culls.  Must be called by all 32
+// lanes of a warp (lanes without a live path pass any finite ray).
 //
 // Spheres.  The reference accepts a sphere only if fl(b^2 - 4c) >= 0 and
 // t1 = (b - sqrt(disc)) / 2 > 0, which needs b > 0 (geometry.rs:204-240).
@@ -368,17 +417,23 @@ __device__ __forceinline__ void flush_candidates(const PrimTables &tb, const Ray
 // the rounding error of BOTH evaluations (reference and pre-test):
 //     |B'^2 - C' - disc_ref/4| <= 44 eps (cmax2 + |o|^2) max(1,|d|^2)   <  e1 = 2^-17 (cmax2 + |o|^2) max(1,|d|^2)
 //     |B' - b_ref/2|           <= 12 eps sqrt((cmax2 + |o|^2) |d|^2)    <  e2 = 2^-19 sqrt((cmax2 + |o|^2) |d|^2)
-// (eps = 2^-24, cmax2 = max |c|^2 + r^2; derivation in DESIGN.md "Culling").  Every survivor is then evaluated with the reference's exact
-// arithmetic (sphere_t), so the hit distance, the winner and every later
-// rounding are unchanged; culling only removes spheres the reference rejects.
-// Survivors are queued per lane and evaluated after the uniform loop, so the
-// warp does not diverge into the exact test once per sphere.
+// (eps = 2^-24, cmax2 = max |c|^2 + r^2; derivation in DESIGN.md "Culling").
+// Every survivor is then evaluated with the reference's exact arithmetic
+// (sphere_t), so the hit distance, the winner and every later rounding are
+// unchanged; culling only removes spheres the reference rejects.
+//
+// Survivors are queued per lane in shared memory and evaluated after the
+// uniform scan, each lane walking its own queue, so the warp does not diverge
+// into the exact test once per sphere.  When any lane's queue could overflow,
+// a warp vote ends the scan early, every lane drains, and the scan resumes:
+// each piece of code exists once.
 //
 // Compounds.  A bounded convex body can only be hit where the ray passes its
-// bounding sphere (inflated on the host well beyond rounding); otherwise the
-// reference's recursion returns None.  Unbounded bodies carry r^2 < 0 and are
-// always evaluated.
-__device__ __forceinline__ Hit intersect_scene(const PrimTables &tb, const Ray &ray) {
+// bounding sphere (inflated on the host well beyond rounding); survivors are
+// queued the same way, then the slab test above, then the reference's
+// recursion (compound_t).  Unbounded bodies carry r^2 < 0 and are always queued.
+__device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
+    const PrimTables &tb = tables();
     Hit best;
     best.t = 1.0e12f; best.obj = -1; best.code = RL_HIT_NONE;
 
@@ -391,23 +446,38 @@ __device__ __forceinline__ Hit intersect_scene(const PrimTables &tb, const Ray &
     const float thr = -7.6293945e-6f * scale;                                          // -2^-17 * scale
     const float bthr = -1.9073486e-6f * sqrtf((tb.sphere_cmax2 + oo) * dd) - 1.0e-30f;  // -2^-19 * ...
 
-    uint32_t cnt = 0;
-#pragma unroll 4
-    for (uint32_t i = 0; i < tb.n_spheres; i++) {
-        const float4 s = tb.sphere_k[i];                      // {cx, cy, cz, |c|^2 - r^2}
-        const float b = fmaf(d.x, s.x, fmaf(d.y, s.y, fmaf(d.z, s.z, ndo)));
-        const float c = fmaf(m2ox, s.x, fmaf(m2oy, s.y, fmaf(m2oz, s.z, s.w))) + oo;
-        const float disc = fmaf(b, b, -c);
-        if (disc >= thr && b >= bthr) {
-            tb.cand[cnt * blockDim.x + threadIdx.x] = (uint16_t)i;
-            cnt++;
-            if (cnt == RL_CAND_SLOTS) flush_candidates(tb, ray, best, cnt);
+    uint16_t *sq = tb.cand + threadIdx.x;                       // slot k at sq[k * blockDim.x]
+    const uint32_t qstride = blockDim.x;
+    const uint32_t n_spheres = tb.n_spheres;
+    uint32_t i = 0;
+    do {
+        uint32_t cnt = 0;
+        // uniform scan, four spheres per step; stop while every queue still has room for four
+        for (; i < n_spheres; i += 4) {
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) {
+                // the table is padded with never-hit records to a multiple of four
+                const float4 s = tb.sphere_k[i + j];            // {cx, cy, cz, |c|^2 - r^2}
+                const float b = fmaf(d.x, s.x, fmaf(d.y, s.y, fmaf(d.z, s.z, ndo)));
+                const float c = fmaf(m2ox, s.x, fmaf(m2oy, s.y, fmaf(m2oz, s.z, s.w))) + oo;
+                const float disc = fmaf(b, b, -c);
+                if (disc >= thr && b >= bthr) {
+                    sq[cnt * qstride] = (uint16_t)(i + j);
+                    cnt++;
+                }
+            }
+            if (__any_sync(0xffffffffu, cnt > RL_CAND_SLOTS - 4)) { i += 4; break; }
         }
-    }
-    flush_candidates(tb, ray, best, cnt);
+        // exact Sphere::intersect for the queued candidates of this lane
+        for (uint32_t k = 0; k < cnt; k++) {
+            const uint32_t idx = sq[k * qstride];
+            const float t = sphere_t(tb.spheres[idx], ray);
+            if (t > 0.0f) consider(best, t, (int)tb.sphere_obj[idx], (RL_HIT_SPHERE << 28) | idx);
+        }
+    } while (__any_sync(0xffffffffu, i < n_spheres));
 
-    for (uint32_t i = 0; i < tb.n_planes; i++) {
-        const float4 n4 = tb.planes[2 * i], o4 = tb.planes[2 * i + 1];
+    for (uint32_t k = 0; k < tb.n_planes; k++) {
+        const float4 n4 = tb.planes[2 * k], o4 = tb.planes[2 * k + 1];
         float dn;
         const float t = plane_t(mk(n4.x, n4.y, n4.z), mk(o4.x, o4.y, o4.z), ray, dn);
         if (t > 0.0f) {
@@ -416,30 +486,48 @@ __device__ __forceinline__ Hit intersect_scene(const PrimTables &tb, const Ray &
                 const V3 pos = ray.origin + ray.direction * t;
                 ok = magnitude_squared(pos - mk(o4.x, o4.y, o4.z)) <= o4.w;
             }
-            if (ok) consider(best, t, (int)tb.plane_obj[i], (RL_HIT_PLANE << 28) | i);
+            if (ok) consider(best, t, (int)tb.plane_obj[k], (RL_HIT_PLANE << 28) | k);
         }
     }
-    for (uint32_t i = 0; i < tb.n_paraboloids; i++) {
-        const float t = paraboloid_t(tb.paraboloids + 3 * i, ray);
+    for (uint32_t k = 0; k < tb.n_paraboloids; k++) {
+        const float t = paraboloid_t(tb.paraboloids + 3 * k, ray);
         // the a == 0 branch admits t == 0 (geometry.rs:319: only t1 < 0 is rejected)
-        if (t >= 0.0f) consider(best, t, (int)tb.paraboloid_obj[i], (RL_HIT_PARABOLOID << 28) | i);
+        if (t >= 0.0f) consider(best, t, (int)tb.paraboloid_obj[k], (RL_HIT_PARABOLOID << 28) | k);
     }
-    for (uint32_t i = 0; i < tb.n_compounds; i++) {
-        const float4 c4 = tb.compounds[2 * i], b4 = tb.compounds[2 * i + 1];
-        if (b4.w >= 0.0f) {
-            const float cx = b4.x - o.x, cy = b4.y - o.y, cz = b4.z - o.z;
-            const float bq = fmaf(cz, cz, fmaf(cy, cy, cx * cx));
-            const float bb = fmaf(d.z, cz, fmaf(d.y, cy, d.x * cx));
-            const float bc = bq - b4.w;                       // > 0: origin outside the bound
-            const bool behind = bc > 0.0f && bb < 0.0f;
-            const bool misses = fmaf(bb, bb, -(bc * dd)) < 0.0f;
-            if (behind || misses) continue;
+
+    uint16_t *cq = sq + RL_CAND_SLOTS * qstride;
+    const uint32_t n_compounds = tb.n_compounds;
+    i = 0;
+    do {
+        uint32_t cnt = 0;
+        for (; i < n_compounds; i++) {
+            const float4 b4 = tb.compounds[2 * i + 1];          // bounding sphere {c, r^2}
+            bool keep = true;
+            if (b4.w >= 0.0f) {
+                const float cx = b4.x - o.x, cy = b4.y - o.y, cz = b4.z - o.z;
+                const float bq = fmaf(cz, cz, fmaf(cy, cy, cx * cx));
+                const float bb = fmaf(d.z, cz, fmaf(d.y, cy, d.x * cx));
+                const float bc = bq - b4.w;                     // > 0: origin outside the bound
+                const bool behind = bc > 0.0f && bb < 0.0f;
+                const bool misses = fmaf(bb, bb, -(bc * dd)) < 0.0f;
+                keep = !(behind || misses);
+            }
+            if (keep) {
+                cq[cnt * qstride] = (uint16_t)i;
+                cnt++;
+            }
+            if (__any_sync(0xffffffffu, cnt == RL_COMPOUND_SLOTS)) { i++; break; }
         }
-        uint32_t leaf;
-        const float t = compound_t(tb, __float_as_uint(c4.x), __float_as_uint(c4.z),
-                                   __float_as_uint(c4.w), ray, leaf);
-        if (t > 0.0f) consider(best, t, (int)tb.compound_obj[i], (RL_HIT_LEAF << 28) | leaf);
-    }
+        for (uint32_t k = 0; k < cnt; k++) {
+            const uint32_t idx = cq[k * qstride];
+            const float4 c4 = tb.compounds[2 * idx];
+            const uint32_t first_leaf = __float_as_uint(c4.x), n_leaves = __float_as_uint(c4.y);
+            if (!slab_may_hit(first_leaf, n_leaves, ray, best.t)) continue;
+            uint32_t leaf;
+            const float t = compound_t(first_leaf, __float_as_uint(c4.z), __float_as_uint(c4.w), ray, leaf);
+            if (t > 0.0f) consider(best, t, (int)tb.compound_obj[idx], (RL_HIT_LEAF << 28) | leaf);
+        }
+    } while (__any_sync(0xffffffffu, i < n_compounds));
     return best;
 }
 
@@ -447,7 +535,8 @@ struct Surf { V3 position, normal, tangent; };
 
 // The Intersection record of the winning primitive (intersection.rs:19-32);
 // the reference builds it for every candidate, the result only needs the winner.
-__device__ __forceinline__ Surf surface_at(const PrimTables &tb, const Ray &ray, const Hit &hit) {
+__device__ __forceinline__ Surf surface_at(const Ray &ray, const Hit &hit) {
+    const PrimTables &tb = tables();
     Surf s;
     s.position = ray.origin + ray.direction * hit.t;
     s.tangent = mk(0.0f, 0.0f, 0.0f);
@@ -486,9 +575,8 @@ __device__ __forceinline__ V3 diffuse_direction(const Ray &in, const Surf &s, Rn
     const float phi = rng.longitude();
     const float rq = rng.unit();
     const float r = sqrtf(rq);
-    float sn, cs;
-    spec_sincos(phi, sn, cs);
-    const V3 hemi = mk(cs * r, sn * r, sqrtf(1.0f - rq));
+    const float2 sc = sincos_call(phi);
+    const V3 hemi = mk(sc.y * r, sc.x * r, sqrtf(1.0f - rq));
     const V3 normal = dot(in.direction, s.normal) < 0.0f ? s.normal : -s.normal;
     return rotate_towards(hemi, normal);
 }
@@ -498,27 +586,26 @@ __device__ __forceinline__ float soap_clamp(float x) {                 // materi
 }
 
 // Material::get_new_ray for the five reflective materials; returns the new
-// direction and the ray's probability (origin = intersection position).
+// direction and the ray's probability (origin = intersection position).  The
+// three diffuse-based materials share one copy of get_diffuse_ray.
 __device__ __forceinline__ V3 material_bounce(float4 m, const Ray &in, const Surf &s, Rng &rng,
                                               float &probability) {
     const uint32_t kind = __float_as_uint(m.x);
-    switch (kind) {
-    case RL_MATERIAL_DIFFUSE_GREY:                                     // material.rs:122-130
-        probability = m.y;
-        return diffuse_direction(in, s, rng);
-    case RL_MATERIAL_DIFFUSE_COLOURED: {                               // material.rs:155-168
-        const float p = (m.z - in.wavelength) / m.w;
-        const float q = spec_exp(-0.5f * p * p);
-        probability = m.y * q;
-        return diffuse_direction(in, s, rng);
+    if (kind <= RL_MATERIAL_GLOSSY_MIRROR) {
+        // grey (material.rs:122-130), coloured (:155-168), glossy (:185-196)
+        probability = kind == RL_MATERIAL_DIFFUSE_GREY ? m.y : 1.0f;
+        if (kind == RL_MATERIAL_DIFFUSE_COLOURED) {
+            const float p = (m.z - in.wavelength) / m.w;
+            probability = m.y * spec_exp(-0.5f * p * p);
+        }
+        V3 dir = diffuse_direction(in, s, rng);
+        if (kind == RL_MATERIAL_GLOSSY_MIRROR) {
+            const V3 reflection = reflect(in.direction, s.normal);
+            dir = normalise(dir * m.y + reflection * (1.0f - m.y));
+        }
+        return dir;
     }
-    case RL_MATERIAL_GLOSSY_MIRROR: {                                  // material.rs:185-196
-        const V3 diffuse = diffuse_direction(in, s, rng);
-        const V3 reflection = reflect(in.direction, s.normal);
-        probability = 1.0f;
-        return normalise(diffuse * m.y + reflection * (1.0f - m.y));
-    }
-    case RL_MATERIAL_SF10_GLASS: {                                     // material.rs:216-261
+    if (kind == RL_MATERIAL_SF10_GLASS) {                              // material.rs:216-261
         float cos_i = -dot(in.direction, s.normal);
         float ior = sf10_index_of_refraction(in.wavelength);
         V3 normal = s.normal;
@@ -534,21 +621,17 @@ __device__ __forceinline__ V3 material_bounce(float4 m, const Ray &in, const Sur
         const float cos_t = sqrtf(1.0f - sin_t_sqr);
         return in.direction * ior + normal * (ior * cos_i - cos_t);
     }
-    default: {  // RL_MATERIAL_SOAP_BUBBLE                                material.rs:267-306
-        const float cos_alpha = dot(in.direction, s.normal);
-        const V3 direction = (rng.unit() - 0.3f > fabsf(cos_alpha))
-                                 ? reflect(in.direction, s.normal)
-                                 : in.direction;
-        const float phase_shift = (in.wavelength - 380.0f) / 200.0f * RL_PI;
-        const float cos_phi = soap_clamp(dot(direction, s.normal));
-        const float cos_theta = soap_clamp(dot(direction, s.tangent));
-        float sn, cs;
-        spec_sincos(phase_shift - spec_acos(cos_phi) * 3.0f - spec_acos(cos_theta) * 2.0f
-                        + RL_PI * 0.5f, sn, cs);
-        probability = cs * 0.1f + 0.9f;
-        return direction;
-    }
-    }
+    // RL_MATERIAL_SOAP_BUBBLE                                            material.rs:267-306
+    const float cos_alpha = dot(in.direction, s.normal);
+    const V3 direction = (rng.unit() - 0.3f > fabsf(cos_alpha)) ? reflect(in.direction, s.normal)
+                                                                : in.direction;
+    const float phase_shift = (in.wavelength - 380.0f) / 200.0f * RL_PI;
+    const float cos_phi = soap_clamp(dot(direction, s.normal));
+    const float cos_theta = soap_clamp(dot(direction, s.tangent));
+    const float2 sc = sincos_call(phase_shift - spec_acos(cos_phi) * 3.0f - spec_acos(cos_theta) * 2.0f
+                                  + RL_PI * 0.5f);
+    probability = sc.y * 0.1f + 0.9f;
+    return direction;
 }
 
 // material.rs:101-105

@@ -10,6 +10,7 @@
 #include <atomic>
 
 #include "rl_kernels.h"
+#include "rl_device.cuh"
 
 namespace rl {
 
@@ -38,10 +39,7 @@ struct TraceArgs {
 // Scene::intersect plus one material interaction for every live lane.
 __global__ void __launch_bounds__(RL_TRACE_THREADS)
 trace_kernel(const DevScene sc, const TraceArgs a) {
-    extern __shared__ float4 smem[];
-    for (uint32_t i = threadIdx.x; i < sc.blob_vec4; i += blockDim.x) smem[i] = sc.blob[i];
-    __syncthreads();
-    const PrimTables tb = make_tables(sc, smem);
+    setup_tables(sc);
 
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint64_t next = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,10 +70,12 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
             alive = true;
         }
         if (!__any_sync(0xffffffffu, alive)) break;
+        // every lane takes part in the intersection (warp votes inside); idle lanes trace a
+        // ray that hits nothing
+        const Hit hit = intersect_scene(alive ? ray : idle_ray());
         if (alive) {
             // trace_unit.rs:91-131
             rays++;
-            const Hit hit = intersect_scene(tb, ray);
             bool done = false;
             float result = 0.0f;
             if (hit.obj < 0) {
@@ -86,7 +86,7 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
                     result = intensity * blackbody_intensity(m, ray.wavelength);  // :99-101
                     done = true;
                 } else {
-                    const Surf s = surface_at(tb, ray, hit);
+                    const Surf s = surface_at(ray, hit);
                     float probability;
                     const V3 dir = material_bounce(m, ray, s, rng, probability);  // :104-107
                     intensity = intensity * probability;
@@ -118,9 +118,7 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
     if ((threadIdx.x & 31) == 0 && a.ray_counter) atomicAdd(a.ray_counter, (unsigned long long)rays);
 }
 
-size_t trace_smem_bytes(const DevScene &sc, int threads) {
-    return (size_t)sc.blob_vec4 * sizeof(float4) + (size_t)RL_CAND_SLOTS * threads * sizeof(uint16_t);
-}
+size_t trace_smem_bytes(const DevScene &sc, int threads) { return tracing_smem_bytes(sc, threads); }
 
 cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count, cudaStream_t st) {
     if (p.n_photons == 0) return cudaSuccess;
@@ -373,23 +371,26 @@ cudaError_t launch_tonemap(const float *xyz, uint32_t width, uint32_t height, do
 
 // -------------------------------------------------------------------- probes
 __global__ void debug_intersect_kernel(const DevScene sc, const rl_ray *rays, uint64_t n, rl_hit *out) {
-    extern __shared__ float4 smem[];
-    for (uint32_t i = threadIdx.x; i < sc.blob_vec4; i += blockDim.x) smem[i] = sc.blob[i];
-    __syncthreads();
-    const PrimTables tb = make_tables(sc, smem);
+    setup_tables(sc);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Ray r;
-        r.origin = mk(rays[i].origin.x, rays[i].origin.y, rays[i].origin.z);
-        r.direction = mk(rays[i].direction.x, rays[i].direction.y, rays[i].direction.z);
-        r.wavelength = rays[i].wavelength;
-        const Hit h = intersect_scene(tb, r);
+    // warp-uniform trip count: intersect_scene votes across the whole warp
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+        const uint64_t i = base + threadIdx.x;
+        const bool live = i < n;
+        Ray r = idle_ray();
+        if (live) {
+            r.origin = mk(rays[i].origin.x, rays[i].origin.y, rays[i].origin.z);
+            r.direction = mk(rays[i].direction.x, rays[i].direction.y, rays[i].direction.z);
+            r.wavelength = rays[i].wavelength;
+        }
+        const Hit h = intersect_scene(r);
+        if (!live) continue;
         rl_hit o;
         o.object = h.obj;
         o.distance = 0.f;
         o.position = o.normal = o.tangent = rl_vec3{0.f, 0.f, 0.f};
         if (h.obj >= 0) {
-            const Surf s = surface_at(tb, r, h);
+            const Surf s = surface_at(r, h);
             o.distance = h.t;
             o.position = rl_vec3{s.position.x, s.position.y, s.position.z};
             o.normal = rl_vec3{s.normal.x, s.normal.y, s.normal.z};
@@ -418,40 +419,50 @@ cudaError_t launch_debug_intersect(const DevScene &sc, const rl_ray *rays, uint6
 __global__ void __launch_bounds__(128)
 debug_cull_check_kernel(const DevScene sc, uint64_t seed, float aspect, uint64_t first, uint64_t n,
                         unsigned long long *rays_out, unsigned long long *mismatches) {
-    extern __shared__ float4 smem[];
-    for (uint32_t i = threadIdx.x; i < sc.blob_vec4; i += blockDim.x) smem[i] = sc.blob[i];
-    __syncthreads();
-    const PrimTables tb = make_tables(sc, smem);
+    setup_tables(sc);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t next = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long rays = 0, bad = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Rng rng;
-        rng.init(seed, first + i);
-        const float wavelength = rng.wavelength();
-        const float x = rng.bi_unit();
-        const float y = rng.bi_unit() / aspect;
-        const float t = rng.unit();
-        Ray ray = camera_ray(sc.camera, x, y, wavelength, t, rng);
-        float intensity = 1.0f, continue_chance = 1.0f;
-        for (;;) {
-            rays++;
-            const Hit hit = intersect_scene_brute(tb, ray);
-            const Hit culled = intersect_scene(tb, ray);
-            if (hit.obj != culled.obj || __float_as_uint(hit.t) != __float_as_uint(culled.t) ||
-                hit.code != culled.code)
-                bad++;
-            if (hit.obj < 0) break;
-            const float4 m = __ldg(sc.materials + hit.obj);
-            if (__float_as_uint(m.x) == RL_MATERIAL_BLACKBODY) break;
-            const Surf s = surface_at(tb, ray, hit);
-            float probability;
-            const V3 dir = material_bounce(m, ray, s, rng, probability);
-            intensity = intensity * probability;
-            ray.direction = dir;
-            ray.origin = s.position + dir * 0.00001f;
-            continue_chance = continue_chance * 0.96f;
-            if (rng.unit() * 0.85f > continue_chance * (1.0f - spec_exp(intensity * -20.0f))) break;
+    bool alive = false;
+    Ray ray = idle_ray();
+    Rng rng;
+    rng.init(seed, 0);
+    float intensity = 1.0f, continue_chance = 1.0f;
+    for (;;) {
+        if (!alive && next < n) {
+            rng.init(seed, first + next);
+            next += stride;
+            const float wavelength = rng.wavelength();
+            const float x = rng.bi_unit();
+            const float y = rng.bi_unit() / aspect;
+            const float t = rng.unit();
+            ray = camera_ray(sc.camera, x, y, wavelength, t, rng);
+            intensity = 1.0f;
+            continue_chance = 1.0f;
+            alive = true;
         }
+        if (!__any_sync(0xffffffffu, alive)) break;
+        const Ray r = alive ? ray : idle_ray();
+        const Hit culled = intersect_scene(r);
+        if (!alive) continue;
+        const Hit hit = intersect_scene_brute(r);
+        rays++;
+        if (hit.obj != culled.obj || __float_as_uint(hit.t) != __float_as_uint(culled.t) ||
+            hit.code != culled.code)
+            bad++;
+        alive = false;
+        if (hit.obj < 0) continue;
+        const float4 m = __ldg(sc.materials + hit.obj);
+        if (__float_as_uint(m.x) == RL_MATERIAL_BLACKBODY) continue;
+        const Surf s = surface_at(ray, hit);
+        float probability;
+        const V3 dir = material_bounce(m, ray, s, rng, probability);
+        intensity = intensity * probability;
+        ray.direction = dir;
+        ray.origin = s.position + dir * 0.00001f;
+        continue_chance = continue_chance * 0.96f;
+        if (rng.unit() * 0.85f > continue_chance * (1.0f - spec_exp(intensity * -20.0f))) continue;
+        alive = true;
     }
     atomicAdd(rays_out, rays);
     if (bad) atomicAdd(mismatches, bad);

@@ -4,7 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "rl_device.cuh"
+#include "../../include/rl_b200.h"
+#include "rl_scene_layout.h"
 
 namespace rl {
 

@@ -1,0 +1,37 @@
+// rl_scene_layout.h -- the flattened scene as the kernels receive it (plain
+// host/device structs; the device functions over it are in rl_device.cuh).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define RL_MAX_COMPOUND_STACK 8   // deepest evaluation stack of a compound-surface program
+
+namespace rl {
+
+struct DevCamera {
+    uint32_t kind;
+    float px, py, pz;
+    float field_of_view, focal_distance, depth_of_field, chromatic_abberation;
+    float qx, qy, qz, qw;
+    float phi_base, phi_rate, alpha_base, alpha_rate, distance_base, distance_rate, focal_factor;
+};
+
+struct DevScene {
+    const float4 *blob;       // global copy of the primitive blob
+    uint32_t blob_vec4;       // its size in float4 units
+    // offsets into the blob, in float4 units
+    uint32_t off_spheres, n_spheres;
+    uint32_t off_planes, n_planes;
+    uint32_t off_paraboloids, n_paraboloids;
+    uint32_t off_leaves, n_leaves;
+    uint32_t off_compounds, n_compounds;
+    uint32_t off_ops, n_ops;
+    uint32_t off_sphere_obj, off_plane_obj, off_paraboloid_obj, off_compound_obj, off_sphere_k;
+    const float4 *materials;  // per object
+    uint32_t n_objects;
+    float sphere_cmax2;       // max (|centre|^2 + r^2) over the spheres (error bound of the pre-test)
+    DevCamera camera;
+};
+
+}  // namespace rl
