@@ -1,17 +1,17 @@
-// rl_device.cuh -- device-side scene layout and the per-ray functions of the
-// path: RNG draws, camera ray, Scene::intersect, materials, splat.
+// rl_device.cuh -- device-side functions of the path: RNG draws, camera ray,
+// Scene::intersect, materials, splat.  Included by rl_kernels.cu only.
 //
 // Layout in HBM / shared memory.  rl_scene_create flattens the descriptor into
 // one "primitive blob" of 16-byte records, grouped by primitive type so that a
 // warp walks each list with uniform (broadcast) shared-memory loads:
 //
-//   spheres      n_spheres     x float4 {cx, cy, cz, r^2}
+//   spheres      n_spheres     x float4   {cx, cy, cz, r^2}
+//   sphere_k     n_spheres(+3) x float4   {cx, cy, cz, |c|^2 - r^2}, record of the sphere pre-test
 //   planes       n_planes      x 2 float4 {n.xyz, kind} {offset.xyz, r^2}
 //   paraboloids  n_paraboloids x 3 float4 {offset,0} {normal,0} {focal_point,0}
 //   leaves       n_leaves      x 2 float4 {n.xyz, 0} {offset.xyz, 0}   half-spaces of compounds
 //   compounds    n_compounds   x 2 float4 {first_leaf, n_leaves, first_op, n_ops} {bound c.xyz, bound r^2 (< 0: unbounded)}
 //   ops          n_ops         x uint32   post-order program of the compound trees
-//   sphere_k     n_spheres     x float4   {cx, cy, cz, |c|^2 - r^2}, record of the sphere pre-test
 //   *_obj                      x uint32   object index of each sphere/plane/paraboloid/compound
 //
 // The kernel copies the blob into shared memory once per CTA.  Per-object
@@ -32,21 +32,17 @@ namespace rl {
 //   [ PrimTables header | primitive blob | per-thread candidate queues ]
 extern __shared__ float4 rl_smem[];
 
-// Views into the blob once it sits in shared memory.  The struct itself lives
-// at the start of shared memory so that out-of-line device functions reach the
-// tables without carrying them in registers or on the stack.
+// Views into the blob once it sits in shared memory, as offsets from rl_smem in
+// float4 units (32-bit shared-memory addressing: generic pointers kept in
+// shared memory would turn every table read into a 64-bit generic load).  The
+// struct lives at the start of shared memory so that every device function
+// reaches the tables without carrying them in registers.
 struct PrimTables {
-    const float4 *spheres;
-    const float4 *sphere_k;   // {cx, cy, cz, |c|^2 - r^2} per sphere (pre-test record)
-    const float4 *planes;
-    const float4 *paraboloids;
-    const float4 *leaves;
-    const float4 *compounds;
-    const uint32_t *ops;
-    const uint32_t *sphere_obj, *plane_obj, *paraboloid_obj, *compound_obj;
+    uint32_t spheres, sphere_k, planes, paraboloids, leaves, compounds, ops;
+    uint32_t sphere_obj, plane_obj, paraboloid_obj, compound_obj;
+    uint32_t queues;          // per-thread candidate slots: uint16 [slot * blockDim.x + tid]
     uint32_t n_spheres, n_planes, n_paraboloids, n_compounds;
     float sphere_cmax2;
-    uint16_t *cand;           // per-thread candidate slots in shared memory: cand[slot * blockDim.x + tid]
 };
 
 #define RL_TABLES_VEC4 ((sizeof(PrimTables) + 15) / 16)
@@ -56,30 +52,34 @@ struct PrimTables {
 __device__ __forceinline__ const PrimTables &tables() {
     return *reinterpret_cast<const PrimTables *>(rl_smem);
 }
+__device__ __forceinline__ const float4 *sm_vec(uint32_t off) { return rl_smem + off; }
+__device__ __forceinline__ const uint32_t *sm_u32(uint32_t off) {
+    return reinterpret_cast<const uint32_t *>(rl_smem + off);
+}
 
 // Block-wide: copy the blob into shared memory and publish the table views.
 __device__ __forceinline__ void setup_tables(const DevScene &sc) {
-    float4 *base = rl_smem + RL_TABLES_VEC4;
-    for (uint32_t i = threadIdx.x; i < sc.blob_vec4; i += blockDim.x) base[i] = sc.blob[i];
+    const uint32_t base = RL_TABLES_VEC4;
+    for (uint32_t i = threadIdx.x; i < sc.blob_vec4; i += blockDim.x) rl_smem[base + i] = sc.blob[i];
     if (threadIdx.x == 0) {
         PrimTables t;
         t.spheres = base + sc.off_spheres;
+        t.sphere_k = base + sc.off_sphere_k;
         t.planes = base + sc.off_planes;
         t.paraboloids = base + sc.off_paraboloids;
         t.leaves = base + sc.off_leaves;
         t.compounds = base + sc.off_compounds;
-        t.ops = reinterpret_cast<const uint32_t *>(base + sc.off_ops);
-        t.sphere_k = base + sc.off_sphere_k;
-        t.sphere_obj = reinterpret_cast<const uint32_t *>(base + sc.off_sphere_obj);
-        t.plane_obj = reinterpret_cast<const uint32_t *>(base + sc.off_plane_obj);
-        t.paraboloid_obj = reinterpret_cast<const uint32_t *>(base + sc.off_paraboloid_obj);
-        t.compound_obj = reinterpret_cast<const uint32_t *>(base + sc.off_compound_obj);
+        t.ops = base + sc.off_ops;
+        t.sphere_obj = base + sc.off_sphere_obj;
+        t.plane_obj = base + sc.off_plane_obj;
+        t.paraboloid_obj = base + sc.off_paraboloid_obj;
+        t.compound_obj = base + sc.off_compound_obj;
+        t.queues = base + sc.blob_vec4;
         t.n_spheres = sc.n_spheres;
         t.n_planes = sc.n_planes;
         t.n_paraboloids = sc.n_paraboloids;
         t.n_compounds = sc.n_compounds;
         t.sphere_cmax2 = sc.sphere_cmax2;
-        t.cand = reinterpret_cast<uint16_t *>(base + sc.blob_vec4);
         *reinterpret_cast<PrimTables *>(rl_smem) = t;
     }
     __syncthreads();
@@ -94,7 +94,7 @@ inline size_t tracing_smem_bytes(const DevScene &sc, int threads) {
 // ---------------------------------------------------------------------- RNG
 // Philox4x32-10, counter (photon_lo, photon_hi, block, 0), key (seed_lo,
 // seed_hi).  Stands in for rand::random (monte_carlo.rs:22-28).
-// One Philox4x32-10 block; out of line so that the ten draw sites share it.
+// One block is computed out of line so that the ten draw sites share it.
 static __device__ __noinline__ uint4 philox_block(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
                                                   uint32_t block) {
     uint32_t x0 = c0, x1 = c1, x2 = block, x3 = 0u;
@@ -148,7 +148,7 @@ struct Rng {
     __device__ __forceinline__ float wavelength() { return unit() * 400.0f + 380.0f; }      // monte_carlo.rs:41-43
 };
 
-// sin and cos through one shared out-of-line copy (seven call sites).
+// sin and cos through one shared out-of-line copy (eight call sites).
 static __device__ __noinline__ float2 sincos_call(float x) {
     float s, c;
     spec_sincos(x, s, c);
@@ -173,7 +173,8 @@ __device__ __forceinline__ Ray idle_ray() {
 
 // ------------------------------------------------------------------- camera
 // app.rs:327-357 (make_camera) in closed form, camera.rs:94-108 + :47-90.
-__device__ __forceinline__ Ray camera_ray(const DevCamera &cm, float x, float y, float wavelength, float t, Rng &rng) {
+__device__ __forceinline__ Ray camera_ray(const DevCamera &cm, float x, float y, float wavelength, float t,
+                                          Rng &rng) {
     V3 position;
     Quat orientation;
     float focal_distance;
@@ -290,14 +291,16 @@ __device__ __forceinline__ float paraboloid_t(const float4 *p, const Ray &ray) {
 __device__ __forceinline__ float compound_t(uint32_t first_leaf, uint32_t first_op, uint32_t n_ops,
                                             const Ray &ray, uint32_t &leaf_out) {
     const PrimTables &tb = tables();
+    const float4 *leaves = sm_vec(tb.leaves);
+    const uint32_t *ops = sm_u32(tb.ops);
     float st_t[RL_MAX_COMPOUND_STACK];
     uint32_t st_leaf[RL_MAX_COMPOUND_STACK];
     int sp = 0;
     for (uint32_t i = 0; i < n_ops; i++) {
-        const uint32_t op = tb.ops[first_op + i];
+        const uint32_t op = ops[first_op + i];
         if ((op & 3u) == 0u) {
             const uint32_t leaf = first_leaf + (op >> 8);
-            const float4 n4 = tb.leaves[2 * leaf], o4 = tb.leaves[2 * leaf + 1];
+            const float4 n4 = leaves[2 * leaf], o4 = leaves[2 * leaf + 1];
             float d;
             st_t[sp] = plane_t(mk(n4.x, n4.y, n4.z), mk(o4.x, o4.y, o4.z), ray, d);
             st_leaf[sp] = leaf;
@@ -312,14 +315,14 @@ __device__ __forceinline__ float compound_t(uint32_t first_leaf, uint32_t first_
             if (t1 > 0.0f) {  // surface2.lies_inside(i1.position)
                 const V3 pos = ray.origin + ray.direction * t1;
                 for (uint32_t k = mid; k < hi; k++) {
-                    const float4 n4 = tb.leaves[2 * k], o4 = tb.leaves[2 * k + 1];
+                    const float4 n4 = leaves[2 * k], o4 = leaves[2 * k + 1];
                     if (!(dot(pos - mk(o4.x, o4.y, o4.z), mk(n4.x, n4.y, n4.z)) < 0.0f)) { t1 = -1.0f; break; }
                 }
             }
             if (t2 > 0.0f) {  // surface1.lies_inside(i2.position)
                 const V3 pos = ray.origin + ray.direction * t2;
                 for (uint32_t k = lo; k < mid; k++) {
-                    const float4 n4 = tb.leaves[2 * k], o4 = tb.leaves[2 * k + 1];
+                    const float4 n4 = leaves[2 * k], o4 = leaves[2 * k + 1];
                     if (!(dot(pos - mk(o4.x, o4.y, o4.z), mk(n4.x, n4.y, n4.z)) < 0.0f)) { t2 = -1.0f; break; }
                 }
             }
@@ -336,6 +339,33 @@ __device__ __forceinline__ float compound_t(uint32_t first_leaf, uint32_t first_
     return st_t[0];
 }
 
+// Plane, Circle, top-level SpacePartitioning and Paraboloid objects: few per
+// scene, evaluated exactly for every ray (shared by both intersect variants).
+__device__ __forceinline__ void intersect_flat_surfaces(const PrimTables &tb, const Ray &ray, Hit &best) {
+    const float4 *planes = sm_vec(tb.planes);
+    const uint32_t *plane_obj = sm_u32(tb.plane_obj);
+    for (uint32_t k = 0; k < tb.n_planes; k++) {
+        const float4 n4 = planes[2 * k], o4 = planes[2 * k + 1];
+        float dn;
+        const float t = plane_t(mk(n4.x, n4.y, n4.z), mk(o4.x, o4.y, o4.z), ray, dn);
+        if (t > 0.0f) {
+            bool ok = true;
+            if (__float_as_uint(n4.w) == RL_SURFACE_CIRCLE) {  // geometry.rs:169-172
+                const V3 pos = ray.origin + ray.direction * t;
+                ok = magnitude_squared(pos - mk(o4.x, o4.y, o4.z)) <= o4.w;
+            }
+            if (ok) consider(best, t, (int)plane_obj[k], (RL_HIT_PLANE << 28) | k);
+        }
+    }
+    const float4 *paraboloids = sm_vec(tb.paraboloids);
+    const uint32_t *paraboloid_obj = sm_u32(tb.paraboloid_obj);
+    for (uint32_t k = 0; k < tb.n_paraboloids; k++) {
+        const float t = paraboloid_t(paraboloids + 3 * k, ray);
+        // the a == 0 branch admits t == 0 (geometry.rs:319: only t1 < 0 is rejected)
+        if (t >= 0.0f) consider(best, t, (int)paraboloid_obj[k], (RL_HIT_PARABOLOID << 28) | k);
+    }
+}
+
 // Scene::intersect (scene.rs:39-60): closest hit over all objects, every
 // primitive evaluated with the reference's arithmetic.  Kept as the in-kernel
 // reference the culled version below is checked against (rl_debug_cull_check).
@@ -343,33 +373,20 @@ __device__ __forceinline__ Hit intersect_scene_brute(const Ray &ray) {
     const PrimTables &tb = tables();
     Hit best;
     best.t = 1.0e12f; best.obj = -1; best.code = RL_HIT_NONE;
+    const float4 *spheres = sm_vec(tb.spheres);
+    const uint32_t *sphere_obj = sm_u32(tb.sphere_obj);
     for (uint32_t i = 0; i < tb.n_spheres; i++) {
-        const float t = sphere_t(tb.spheres[i], ray);
-        if (t > 0.0f) consider(best, t, (int)tb.sphere_obj[i], (RL_HIT_SPHERE << 28) | i);
+        const float t = sphere_t(spheres[i], ray);
+        if (t > 0.0f) consider(best, t, (int)sphere_obj[i], (RL_HIT_SPHERE << 28) | i);
     }
-    for (uint32_t i = 0; i < tb.n_planes; i++) {
-        const float4 n4 = tb.planes[2 * i], o4 = tb.planes[2 * i + 1];
-        float d;
-        const float t = plane_t(mk(n4.x, n4.y, n4.z), mk(o4.x, o4.y, o4.z), ray, d);
-        if (t > 0.0f) {
-            bool ok = true;
-            if (__float_as_uint(n4.w) == RL_SURFACE_CIRCLE) {  // geometry.rs:169-172
-                const V3 pos = ray.origin + ray.direction * t;
-                ok = magnitude_squared(pos - mk(o4.x, o4.y, o4.z)) <= o4.w;
-            }
-            if (ok) consider(best, t, (int)tb.plane_obj[i], (RL_HIT_PLANE << 28) | i);
-        }
-    }
-    for (uint32_t i = 0; i < tb.n_paraboloids; i++) {
-        const float t = paraboloid_t(tb.paraboloids + 3 * i, ray);
-        // the a == 0 branch admits t == 0 (geometry.rs:319: only t1 < 0 is rejected)
-        if (t >= 0.0f) consider(best, t, (int)tb.paraboloid_obj[i], (RL_HIT_PARABOLOID << 28) | i);
-    }
+    intersect_flat_surfaces(tb, ray, best);
+    const float4 *compounds = sm_vec(tb.compounds);
+    const uint32_t *compound_obj = sm_u32(tb.compound_obj);
     for (uint32_t i = 0; i < tb.n_compounds; i++) {
-        const float4 c4 = tb.compounds[2 * i];
+        const float4 c4 = compounds[2 * i];
         uint32_t leaf;
         const float t = compound_t(__float_as_uint(c4.x), __float_as_uint(c4.z), __float_as_uint(c4.w), ray, leaf);
-        if (t > 0.0f) consider(best, t, (int)tb.compound_obj[i], (RL_HIT_LEAF << 28) | leaf);
+        if (t > 0.0f) consider(best, t, (int)compound_obj[i], (RL_HIT_LEAF << 28) | leaf);
     }
     return best;
 }
@@ -385,11 +402,11 @@ __device__ __forceinline__ Hit intersect_scene_brute(const Ray &ray) {
 #define RL_SLAB_INFLATE 2.0e-3f
 __device__ __forceinline__ bool slab_may_hit(uint32_t first_leaf, uint32_t n_leaves, const Ray &ray,
                                              float best_t) {
-    const PrimTables &tb = tables();
+    const float4 *leaves = sm_vec(tables().leaves);
     float t_enter = 0.0f, t_exit = 3.0e38f;
     bool outside_parallel = false;
     for (uint32_t k = first_leaf; k < first_leaf + n_leaves; k++) {
-        const float4 n4 = tb.leaves[2 * k], o4 = tb.leaves[2 * k + 1];
+        const float4 n4 = leaves[2 * k], o4 = leaves[2 * k + 1];
         const float dn = fmaf(n4.z, ray.direction.z, fmaf(n4.y, ray.direction.y, n4.x * ray.direction.x));
         const float s0 = fmaf(n4.z, ray.origin.z - o4.z,
                               fmaf(n4.y, ray.origin.y - o4.y, n4.x * (ray.origin.x - o4.x))) - RL_SLAB_INFLATE;
@@ -406,7 +423,7 @@ __device__ __forceinline__ bool slab_may_hit(uint32_t first_leaf, uint32_t n_lea
 }
 
 // Scene::intersect with result-preserving culls.  Must be called by all 32
-// lanes of a warp (lanes without a live path pass any finite ray).
+// lanes of a warp (lanes without a live path pass idle_ray()).
 //
 // Spheres.  The reference accepts a sphere only if fl(b^2 - 4c) >= 0 and
 // t1 = (b - sqrt(disc)) / 2 > 0, which needs b > 0 (geometry.rs:204-240).
@@ -446,62 +463,51 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
     const float thr = -7.6293945e-6f * scale;                                          // -2^-17 * scale
     const float bthr = -1.9073486e-6f * sqrtf((tb.sphere_cmax2 + oo) * dd) - 1.0e-30f;  // -2^-19 * ...
 
-    uint16_t *sq = tb.cand + threadIdx.x;                       // slot k at sq[k * blockDim.x]
+    uint16_t *sq = reinterpret_cast<uint16_t *>(rl_smem + tb.queues) + threadIdx.x;  // slot k at sq[k * qstride]
     const uint32_t qstride = blockDim.x;
+    const float4 *spheres = sm_vec(tb.spheres);
+    const float4 *sphere_k = sm_vec(tb.sphere_k);
+    const uint32_t *sphere_obj = sm_u32(tb.sphere_obj);
     const uint32_t n_spheres = tb.n_spheres;
     uint32_t i = 0;
     do {
-        uint32_t cnt = 0;
-        // uniform scan, four spheres per step; stop while every queue still has room for four
+        uint16_t *tail = sq;                                    // next free slot of this lane's queue
+        uint16_t *const limit = sq + (RL_CAND_SLOTS - 4) * qstride;
+        // uniform scan, four spheres per step, while every queue has room for four more
         for (; i < n_spheres; i += 4) {
 #pragma unroll
             for (uint32_t j = 0; j < 4; j++) {
-                // the table is padded with never-hit records to a multiple of four
-                const float4 s = tb.sphere_k[i + j];            // {cx, cy, cz, |c|^2 - r^2}
+                // the table is padded with never-selected records to a multiple of four
+                const float4 s = sphere_k[i + j];               // {cx, cy, cz, |c|^2 - r^2}
                 const float b = fmaf(d.x, s.x, fmaf(d.y, s.y, fmaf(d.z, s.z, ndo)));
                 const float c = fmaf(m2ox, s.x, fmaf(m2oy, s.y, fmaf(m2oz, s.z, s.w))) + oo;
                 const float disc = fmaf(b, b, -c);
                 if (disc >= thr && b >= bthr) {
-                    sq[cnt * qstride] = (uint16_t)(i + j);
-                    cnt++;
+                    *tail = (uint16_t)(i + j);
+                    tail += qstride;
                 }
             }
-            if (__any_sync(0xffffffffu, cnt > RL_CAND_SLOTS - 4)) { i += 4; break; }
+            if (__any_sync(0xffffffffu, tail > limit)) { i += 4; break; }
         }
         // exact Sphere::intersect for the queued candidates of this lane
-        for (uint32_t k = 0; k < cnt; k++) {
-            const uint32_t idx = sq[k * qstride];
-            const float t = sphere_t(tb.spheres[idx], ray);
-            if (t > 0.0f) consider(best, t, (int)tb.sphere_obj[idx], (RL_HIT_SPHERE << 28) | idx);
+        for (const uint16_t *q = sq; q < tail; q += qstride) {
+            const uint32_t idx = *q;
+            const float t = sphere_t(spheres[idx], ray);
+            if (t > 0.0f) consider(best, t, (int)sphere_obj[idx], (RL_HIT_SPHERE << 28) | idx);
         }
     } while (__any_sync(0xffffffffu, i < n_spheres));
 
-    for (uint32_t k = 0; k < tb.n_planes; k++) {
-        const float4 n4 = tb.planes[2 * k], o4 = tb.planes[2 * k + 1];
-        float dn;
-        const float t = plane_t(mk(n4.x, n4.y, n4.z), mk(o4.x, o4.y, o4.z), ray, dn);
-        if (t > 0.0f) {
-            bool ok = true;
-            if (__float_as_uint(n4.w) == RL_SURFACE_CIRCLE) {  // geometry.rs:169-172
-                const V3 pos = ray.origin + ray.direction * t;
-                ok = magnitude_squared(pos - mk(o4.x, o4.y, o4.z)) <= o4.w;
-            }
-            if (ok) consider(best, t, (int)tb.plane_obj[k], (RL_HIT_PLANE << 28) | k);
-        }
-    }
-    for (uint32_t k = 0; k < tb.n_paraboloids; k++) {
-        const float t = paraboloid_t(tb.paraboloids + 3 * k, ray);
-        // the a == 0 branch admits t == 0 (geometry.rs:319: only t1 < 0 is rejected)
-        if (t >= 0.0f) consider(best, t, (int)tb.paraboloid_obj[k], (RL_HIT_PARABOLOID << 28) | k);
-    }
+    intersect_flat_surfaces(tb, ray, best);
 
     uint16_t *cq = sq + RL_CAND_SLOTS * qstride;
+    const float4 *compounds = sm_vec(tb.compounds);
+    const uint32_t *compound_obj = sm_u32(tb.compound_obj);
     const uint32_t n_compounds = tb.n_compounds;
     i = 0;
     do {
         uint32_t cnt = 0;
         for (; i < n_compounds; i++) {
-            const float4 b4 = tb.compounds[2 * i + 1];          // bounding sphere {c, r^2}
+            const float4 b4 = compounds[2 * i + 1];             // bounding sphere {c, r^2}
             bool keep = true;
             if (b4.w >= 0.0f) {
                 const float cx = b4.x - o.x, cy = b4.y - o.y, cz = b4.z - o.z;
@@ -520,12 +526,12 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
         }
         for (uint32_t k = 0; k < cnt; k++) {
             const uint32_t idx = cq[k * qstride];
-            const float4 c4 = tb.compounds[2 * idx];
+            const float4 c4 = compounds[2 * idx];
             const uint32_t first_leaf = __float_as_uint(c4.x), n_leaves = __float_as_uint(c4.y);
             if (!slab_may_hit(first_leaf, n_leaves, ray, best.t)) continue;
             uint32_t leaf;
             const float t = compound_t(first_leaf, __float_as_uint(c4.z), __float_as_uint(c4.w), ray, leaf);
-            if (t > 0.0f) consider(best, t, (int)tb.compound_obj[idx], (RL_HIT_LEAF << 28) | leaf);
+            if (t > 0.0f) consider(best, t, (int)compound_obj[idx], (RL_HIT_LEAF << 28) | leaf);
         }
     } while (__any_sync(0xffffffffu, i < n_compounds));
     return best;
@@ -542,11 +548,11 @@ __device__ __forceinline__ Surf surface_at(const Ray &ray, const Hit &hit) {
     s.tangent = mk(0.0f, 0.0f, 0.0f);
     const uint32_t type = hit.code >> 28, idx = hit.code & 0x0fffffffu;
     if (type == RL_HIT_SPHERE) {                                       // geometry.rs:243-251
-        const float4 sp = tb.spheres[idx];
+        const float4 sp = sm_vec(tb.spheres)[idx];
         s.normal = normalise(s.position - mk(sp.x, sp.y, sp.z));
         s.tangent = normalise(cross(mk(0.0f, 1.0f, 0.0f), s.normal));
     } else if (type == RL_HIT_PLANE) {
-        const float4 n4 = tb.planes[2 * idx];
+        const float4 n4 = sm_vec(tb.planes)[2 * idx];
         const V3 n = mk(n4.x, n4.y, n4.z);
         if (__float_as_uint(n4.w) == RL_SURFACE_HALFSPACE) {
             s.normal = n;                                              // geometry.rs:115
@@ -555,7 +561,7 @@ __device__ __forceinline__ Surf surface_at(const Ray &ray, const Hit &hit) {
             s.normal = d < 0.0f ? n : -n;                              // geometry.rs:80, :178
         }
     } else if (type == RL_HIT_PARABOLOID) {                            // geometry.rs:343-347
-        const float4 *p = tb.paraboloids + 3 * idx;
+        const float4 *p = sm_vec(tb.paraboloids) + 3 * idx;
         const V3 offset = mk(p[0].x, p[0].y, p[0].z);
         const V3 normal = mk(p[1].x, p[1].y, p[1].z);
         const V3 focal_point = mk(p[2].x, p[2].y, p[2].z);
@@ -563,7 +569,7 @@ __device__ __forceinline__ Surf surface_at(const Ray &ray, const Hit &hit) {
         const V3 plane_pr = local_pos - normal * dot(local_pos, normal);
         s.normal = normalise(focal_point - plane_pr);
     } else {                                                           // geometry.rs:115
-        const float4 n4 = tb.leaves[2 * idx];
+        const float4 n4 = sm_vec(tb.leaves)[2 * idx];
         s.normal = mk(n4.x, n4.y, n4.z);
     }
     return s;
