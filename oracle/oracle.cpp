@@ -1007,6 +1007,44 @@ int orc_render_mt(const rl_scene_desc *desc, uint64_t seed, uint32_t width, uint
     return RL_OK;
 }
 
+/* Dump the first `cap` rays (Scene::intersect inputs) of photons [first, first+n): analysis aid. */
+int orc_dump_rays(const rl_scene_desc *desc, uint64_t seed, uint32_t width, uint32_t height,
+                  uint64_t first_photon, uint64_t n, uint64_t cap, rl_ray *out, uint64_t *n_out) {
+    SceneView sc;
+    int rc = make_view(desc, sc);
+    if (rc != RL_OK) return rc;
+    float aspect = (float)width / (float)height;
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < n && k < cap; i++) {
+        Philox rng(seed, first_photon + i);
+        float wavelength = rng.wavelength();
+        float x = rng.bi_unit();
+        float y = rng.bi_unit() / aspect;
+        float t = rng.unit();
+        Camera cam = camera_at_time<SpecMath>(sc.camera, t);
+        Ray ray = camera_get_ray<SpecMath>(cam, x, y, wavelength, rng);
+        float continue_chance = 1.0f, intensity = 1.0f;
+        for (;;) {
+            if (k < cap) {
+                out[k].origin = to_rl(ray.origin); out[k].direction = to_rl(ray.direction);
+                out[k].wavelength = ray.wavelength; out[k].probability = intensity; k++;
+            }
+            Isect is;
+            int obj = scene_intersect(sc, ray, is, nullptr);
+            if (obj < 0) break;
+            const rl_material &mat = sc.objects[obj].material;
+            if (mat.kind == RL_MATERIAL_BLACKBODY) break;
+            ray = material_new_ray<SpecMath>(mat, ray, is, rng);
+            intensity = intensity * ray.probability;
+            ray.origin = ray.origin + ray.direction * 0.00001f;
+            continue_chance = continue_chance * 0.96f;
+            if (rng.unit() * 0.85f > continue_chance * (1.0f - SpecMath::exp(intensity * -20.0f))) break;
+        }
+    }
+    *n_out = k;
+    return RL_OK;
+}
+
 int orc_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

@@ -55,6 +55,8 @@ int orc_render_mt(const rl_scene_desc *desc, uint64_t seed, uint32_t width, uint
                   uint64_t first_photon, uint64_t n_photons, uint64_t batch, int threads,
                   int math_mode, float *xyz_out, orc_counters *counters,
                   double *seconds_trace_plot);
+int orc_dump_rays(const rl_scene_desc *desc, uint64_t seed, uint32_t width, uint32_t height,
+                  uint64_t first_photon, uint64_t n, uint64_t cap, rl_ray *out, uint64_t *n_out);
 int orc_hardware_threads(void);
 
 #ifdef __cplusplus
