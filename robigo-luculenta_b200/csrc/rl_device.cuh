@@ -135,7 +135,7 @@ struct Rng {
     // in [0, 1].  n / (2^24 - 1) = n 2^-24 (1 + 2^-24 + ...) exceeds the exactly representable
     // n 2^-24 by between half and one ulp, so the correctly rounded quotient is its successor:
     // one integer add on the bit pattern instead of an IEEE division (identity checked for
-    // all 2^24 values in tests/test_oracle_kat.py; the checker does the division).
+    // all 2^24 values by the CPU test suite, whose checker does the division).
     __device__ __forceinline__ float unit() {
         const uint32_t n = next_u32() >> 8;
         const float scaled = (float)n * 5.9604644775390625e-8f;

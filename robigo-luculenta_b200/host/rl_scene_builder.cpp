@@ -328,7 +328,7 @@ struct Pcg32 {  // O'Neill's PCG-XSH-RR 64/32
 void scene_c4(rl_scene_builder *b, uint32_t n) {
     if (n == 0) n = 4096;
     add_object(b, add_sphere(b, mk(0.f, 0.f, 0.f), 5.0f), blackbody(6504.0f, 1.0f));
-    add_object(b, add_plane(b, mk(0.f, 0.f, -1.f), mk(0.f, 0.f, 30.f)), blackbody(5000.0f, 0.6f));
+    add_object(b, add_plane(b, mk(0.f, 0.f, -1.f), mk(0.f, 0.f, 60.f)), blackbody(5000.0f, 0.6f));
     Pcg32 rng(4096);
     for (uint32_t i = 0; i < n; i++) {
         const float x = rng.unit() * 40.0f - 20.0f;

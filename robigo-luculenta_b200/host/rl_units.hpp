@@ -1,0 +1,190 @@
+// rl_units.hpp -- C++ mirror of the reference's four pipeline units over the
+// C ABI (include/rl_b200.h).  Same type names, methods and public fields as the
+// Rust structs the host drives (trace_unit.rs:40-168, plot_unit.rs:23-103,
+// gather_unit.rs:24-94, tonemap_unit.rs:22-101), so a scheduler written against
+// the reference's API compiles against these unchanged.  This is what the Rust
+// shims of INTEGRATION.md do, written in the language this image can build.
+//
+// Failures of the C ABI throw (the reference panics: app.rs:107,163).
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rl_b200.h"
+
+namespace robigo {
+
+struct Vector3 { float x, y, z; };                     // vector3.rs:20-25
+using MappedPhoton = rl_mapped_photon;                 // trace_unit.rs:23-37
+
+inline void expect(int status, const char *what) {
+    if (status != RL_OK) throw std::runtime_error(std::string(what) + ": " + rl_last_error());
+}
+
+// Stands in for Arc<Scene> (app.rs:63): the flattened scene on the device.
+class Scene {
+public:
+    explicit Scene(const rl_scene_desc &desc) { expect(rl_scene_create(&desc, &handle_), "rl_scene_create"); }
+    ~Scene() { rl_scene_destroy(handle_); }
+    Scene(const Scene &) = delete;
+    Scene &operator=(const Scene &) = delete;
+    const rl_scene *handle() const { return handle_; }
+
+private:
+    rl_scene *handle_ = nullptr;
+};
+
+class TraceUnit {
+public:
+    // trace_unit.rs:64-78.  `keep_on_device`: leave the records on the GPU for
+    // PlotUnit::plot(TraceUnit&) instead of filling `mapped_photons`.
+    TraceUnit(size_t id_, uint32_t width, uint32_t height, uint64_t seed = 0x5EED,
+              uint64_t batch = RL_BATCH_PHOTONS, bool keep_on_device = false)
+        : id(id_), keep_on_device_(keep_on_device) {
+        expect(rl_trace_unit_create(id_, width, height, seed, &handle_), "rl_trace_unit_create");
+        expect(rl_trace_unit_set_batch_size(handle_, batch), "rl_trace_unit_set_batch_size");
+        if (!keep_on_device) mapped_photons.assign(batch, MappedPhoton{0.f, 0.f, 0.f, 0.f});
+    }
+    ~TraceUnit() { rl_trace_unit_destroy(handle_); }
+    TraceUnit(const TraceUnit &) = delete;
+    TraceUnit &operator=(const TraceUnit &) = delete;
+
+    // trace_unit.rs:151-168
+    void render(const Scene &scene) {
+        expect(rl_trace_unit_render(handle_, scene.handle(), keep_on_device_ ? nullptr : mapped_photons.data()),
+               "rl_trace_unit_render");
+    }
+    uint64_t ray_count() {
+        uint64_t n = 0;
+        expect(rl_trace_unit_ray_count(handle_, &n), "rl_trace_unit_ray_count");
+        return n;
+    }
+    rl_trace_unit *handle() { return handle_; }
+
+    std::vector<MappedPhoton> mapped_photons;          // trace_unit.rs:56
+    size_t id;                                         // trace_unit.rs:59
+
+private:
+    rl_trace_unit *handle_ = nullptr;
+    bool keep_on_device_;
+};
+
+class PlotUnit {
+public:
+    // plot_unit.rs:43-53.  `mirror_on_host`: refresh `tristimulus_buffer` after
+    // every plot()/clear(), as the unchanged app.rs:146 reads the field.
+    PlotUnit(size_t id_, uint32_t width, uint32_t height, bool mirror_on_host = true)
+        : id(id_), mirror_(mirror_on_host) {
+        expect(rl_plot_unit_create(id_, width, height, &handle_), "rl_plot_unit_create");
+        if (mirror_) tristimulus_buffer.assign((size_t)width * height, Vector3{0.f, 0.f, 0.f});
+    }
+    ~PlotUnit() { rl_plot_unit_destroy(handle_); }
+    PlotUnit(const PlotUnit &) = delete;
+    PlotUnit &operator=(const PlotUnit &) = delete;
+
+    // plot_unit.rs:87-95
+    void plot(const std::vector<MappedPhoton> &photons) {
+        expect(rl_plot_unit_plot(handle_, photons.data(), photons.size()), "rl_plot_unit_plot");
+        refresh();
+    }
+    // the same on records a trace unit left on the device
+    void plot(TraceUnit &unit) {
+        expect(rl_plot_unit_plot_device(handle_, unit.handle()), "rl_plot_unit_plot_device");
+        refresh();
+    }
+    // plot_unit.rs:98-102
+    void clear() {
+        expect(rl_plot_unit_clear(handle_), "rl_plot_unit_clear");
+        if (mirror_) tristimulus_buffer.assign(tristimulus_buffer.size(), Vector3{0.f, 0.f, 0.f});
+    }
+    rl_plot_unit *handle() { return handle_; }
+
+    std::vector<Vector3> tristimulus_buffer;           // plot_unit.rs:34
+    size_t id;                                         // plot_unit.rs:37
+
+private:
+    void refresh() {
+        if (mirror_)
+            expect(rl_plot_unit_download(handle_, reinterpret_cast<float *>(tristimulus_buffer.data())),
+                   "rl_plot_unit_download");
+    }
+    rl_plot_unit *handle_ = nullptr;
+    bool mirror_;
+};
+
+class GatherUnit {
+public:
+    // gather_unit.rs:35-46: resumes from "buffer.raw" if it exists
+    GatherUnit(uint32_t width, uint32_t height, const char *resume_path = "buffer.raw", bool mirror_on_host = true)
+        : path_(resume_path ? resume_path : ""), mirror_(mirror_on_host) {
+        expect(rl_gather_unit_create(width, height, resume_path, &handle_), "rl_gather_unit_create");
+        if (mirror_) {
+            tristimulus_buffer.assign((size_t)width * height, Vector3{0.f, 0.f, 0.f});
+            refresh();
+        }
+    }
+    ~GatherUnit() { rl_gather_unit_destroy(handle_); }
+    GatherUnit(const GatherUnit &) = delete;
+    GatherUnit &operator=(const GatherUnit &) = delete;
+
+    // gather_unit.rs:49-64
+    void accumulate(const std::vector<Vector3> &tristimuli) {
+        expect(rl_gather_unit_accumulate(handle_, reinterpret_cast<const float *>(tristimuli.data())),
+               "rl_gather_unit_accumulate");
+        refresh();
+    }
+    // accumulate(&plot.tristimulus_buffer) + plot.clear() without the host trip (app.rs:145-148)
+    void accumulate(PlotUnit &plot, bool clear_plot) {
+        expect(rl_gather_unit_accumulate_plot(handle_, plot.handle(), clear_plot ? 1 : 0),
+               "rl_gather_unit_accumulate_plot");
+        refresh();
+    }
+    // gather_unit.rs:68-78
+    void save() {
+        if (!path_.empty()) expect(rl_gather_unit_save(handle_, path_.c_str()), "failed to open file");
+    }
+    rl_gather_unit *handle() { return handle_; }
+
+    std::vector<Vector3> tristimulus_buffer;           // gather_unit.rs:26
+
+private:
+    void refresh() {
+        if (mirror_)
+            expect(rl_gather_unit_download(handle_, reinterpret_cast<float *>(tristimulus_buffer.data()), nullptr),
+                   "rl_gather_unit_download");
+    }
+    rl_gather_unit *handle_ = nullptr;
+    std::string path_;
+    bool mirror_;
+};
+
+class TonemapUnit {
+public:
+    // tonemap_unit.rs:43-51
+    TonemapUnit(uint32_t width, uint32_t height) : rgb_buffer((size_t)width * height * 3, 0) {
+        expect(rl_tonemap_unit_create(width, height, &handle_), "rl_tonemap_unit_create");
+    }
+    ~TonemapUnit() { rl_tonemap_unit_destroy(handle_); }
+    TonemapUnit(const TonemapUnit &) = delete;
+    TonemapUnit &operator=(const TonemapUnit &) = delete;
+
+    // tonemap_unit.rs:73-100
+    void tonemap(const std::vector<Vector3> &tristimuli) {
+        expect(rl_tonemap_unit_tonemap(handle_, reinterpret_cast<const float *>(tristimuli.data()), rgb_buffer.data()),
+               "rl_tonemap_unit_tonemap");
+    }
+    void tonemap(GatherUnit &gather) {
+        expect(rl_tonemap_unit_tonemap_gather(handle_, gather.handle(), rgb_buffer.data()),
+               "rl_tonemap_unit_tonemap_gather");
+    }
+
+    std::vector<uint8_t> rgb_buffer;                   // tonemap_unit.rs:30
+
+private:
+    rl_tonemap_unit *handle_ = nullptr;
+};
+
+}  // namespace robigo

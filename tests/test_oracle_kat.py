@@ -303,3 +303,13 @@ def test_spec_math_close_to_libm(orc):
     wl = np.linspace(380.0, 780.0, 4001, dtype=np.float32)
     t = np.full_like(wl, 6504.0)
     assert ulps(orc.math(4, wl, t, mode=0), orc.math(4, wl, t, mode=1)).max() <= 1
+
+
+def test_closed_draw_is_successor_of_scaled_integer():
+    # The CUDA path computes Closed01<f32> = n / (2^24 - 1) as the float successor of n * 2^-24
+    # (csrc/rl_device.cuh, Rng::unit); exhaustive check of that identity against IEEE division.
+    n = np.arange(0, 1 << 24, dtype=np.uint32)
+    quotient = n.astype(np.float32) / np.float32(16777215.0)
+    succ = (n.astype(np.float32) * np.float32(2.0 ** -24)).view(np.uint32) + np.uint32(1)
+    succ[0] = 0
+    assert np.array_equal(quotient.view(np.uint32), succ)
