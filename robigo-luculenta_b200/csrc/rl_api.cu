@@ -1,6 +1,7 @@
 // rl_api.cu -- the extern "C" boundary (include/rl_b200.h): handles, scene
 // flattening, stream ordering between units.  No compute happens on the host;
 // without a CUDA device every compute entry point returns RL_ERR_CUDA.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -241,6 +242,50 @@ bool convex_bound(const std::vector<float4> &leaves, size_t first, size_t n, flo
     return true;
 }
 
+// Sphere clusters for the two-level pre-test: recursive median split of the
+// centres along the widest axis until a group has at most `leaf` members;
+// returns the permutation (cluster members contiguous) and, per cluster, its
+// range and bounding sphere {centre m, radius R >= max |c_i - m| + r_i}.
+struct Cluster { uint32_t first, count; double m[3], R; };
+
+void split_spheres(const std::vector<float4> &sph, std::vector<uint32_t> &idx, size_t lo, size_t hi,
+                   size_t leaf, std::vector<Cluster> &out) {
+    if (hi - lo <= leaf) {
+        Cluster c;
+        c.first = (uint32_t)lo; c.count = (uint32_t)(hi - lo);
+        double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+        for (size_t k = lo; k < hi; k++) {
+            const float4 s = sph[idx[k]];
+            const double p[3] = {s.x, s.y, s.z};
+            for (int a = 0; a < 3; a++) { mn[a] = fmin(mn[a], p[a]); mx[a] = fmax(mx[a], p[a]); }
+        }
+        for (int a = 0; a < 3; a++) c.m[a] = 0.5 * (mn[a] + mx[a]);
+        c.R = 0.0;
+        for (size_t k = lo; k < hi; k++) {
+            const float4 s = sph[idx[k]];
+            const double dx = s.x - c.m[0], dy = s.y - c.m[1], dz = s.z - c.m[2];
+            c.R = fmax(c.R, sqrt(dx * dx + dy * dy + dz * dz) + sqrt((double)s.w));
+        }
+        c.R = c.R * (1.0 + 1e-6) + 1e-6;
+        out.push_back(c);
+        return;
+    }
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (size_t k = lo; k < hi; k++) {
+        const float4 s = sph[idx[k]];
+        const double p[3] = {s.x, s.y, s.z};
+        for (int a = 0; a < 3; a++) { mn[a] = fmin(mn[a], p[a]); mx[a] = fmax(mx[a], p[a]); }
+    }
+    int axis = 0;
+    for (int a = 1; a < 3; a++) if (mx[a] - mn[a] > mx[axis] - mn[axis]) axis = a;
+    const size_t mid = lo + (hi - lo) / 2;
+    auto key = [&](uint32_t i) { const float4 s = sph[i]; return axis == 0 ? s.x : (axis == 1 ? s.y : s.z); };
+    std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi,
+                     [&](uint32_t a, uint32_t b) { return key(a) < key(b) || (key(a) == key(b) && a < b); });
+    split_spheres(sph, idx, lo, mid, leaf, out);
+    split_spheres(sph, idx, mid, hi, leaf, out);
+}
+
 int max_stack(const std::vector<uint32_t> &ops, size_t first, size_t n) {
     int sp = 0, mx = 0;
     for (size_t i = 0; i < n; i++) {
@@ -347,20 +392,65 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     std::vector<float4> blob;
     DevScene &ds = sc->ds;
     memset(&ds, 0, sizeof(ds));
+    // ---- spheres: cluster, reorder so that cluster members are contiguous, emit the pre-test records
+    if (fl.spheres.size() > 65535) {
+        delete sc;
+        return fail(RL_ERR_UNSUPPORTED, "more than 65535 spheres");
+    }
+    std::vector<float4> clusters;
+    std::vector<uint32_t> cluster_range;
+    double cluster_rmax = 0.0;
+    {
+        const size_t n = fl.spheres.size();
+        std::vector<uint32_t> idx(n);
+        for (size_t k = 0; k < n; k++) idx[k] = (uint32_t)k;
+        std::vector<Cluster> cl;
+        size_t leaf = (size_t)(0.38 * sqrt((double)n) + 0.5);
+        leaf = leaf < 4 ? 4 : (leaf > 32 ? 32 : leaf);
+        if (n) split_spheres(fl.spheres, idx, 0, n, leaf, cl);
+        std::vector<float4> spheres(n), sphere_k(n);
+        std::vector<uint32_t> sphere_obj(n);
+        for (size_t k = 0; k < n; k++) {
+            spheres[k] = fl.spheres[idx[k]];
+            sphere_k[k] = fl.sphere_k[idx[k]];
+            sphere_obj[k] = fl.sphere_obj[idx[k]];
+        }
+        fl.spheres.swap(spheres); fl.sphere_k.swap(sphere_k); fl.sphere_obj.swap(sphere_obj);
+        for (const Cluster &c : cl) {
+            const double m2 = c.m[0] * c.m[0] + c.m[1] * c.m[1] + c.m[2] * c.m[2];
+            const float4 rec = make_float4((float)c.m[0], (float)c.m[1], (float)c.m[2], 0.f);
+            // the record's centre is the f32-rounded one: bound the radius from it
+            double R = 0.0;
+            for (uint32_t k = c.first; k < c.first + c.count; k++) {
+                const float4 sp = fl.spheres[k];
+                const double dx = sp.x - rec.x, dy = sp.y - rec.y, dz = sp.z - rec.z;
+                R = fmax(R, sqrt(dx * dx + dy * dy + dz * dz) + sqrt((double)sp.w));
+            }
+            R = R * (1.0 + 1e-6) + 1e-6;
+            const double mr2 = (double)rec.x * rec.x + (double)rec.y * rec.y + (double)rec.z * rec.z;
+            (void)m2;
+            clusters.push_back(make_float4(rec.x, rec.y, rec.z, (float)(mr2 - R * R)));
+            cluster_range.push_back(c.first | (c.count << 16));
+            if (R > cluster_rmax) cluster_rmax = R;
+            if (mr2 + R * R > fl.cmax2) fl.cmax2 = mr2 + R * R;
+        }
+        // the cluster scan takes four records per step: pad with records no ray selects
+        while (clusters.size() % 4 != 0) {
+            clusters.push_back(make_float4(0.f, 0.f, 0.f, 1.0e30f));
+            cluster_range.push_back(0u);
+        }
+    }
     ds.off_spheres = append(blob, fl.spheres);          ds.n_spheres = (uint32_t)fl.spheres.size();
     ds.off_planes = append(blob, fl.planes);            ds.n_planes = (uint32_t)fl.planes.size() / 2;
     ds.off_paraboloids = append(blob, fl.paraboloids);  ds.n_paraboloids = (uint32_t)fl.paraboloids.size() / 3;
     ds.off_leaves = append(blob, fl.leaves);            ds.n_leaves = (uint32_t)fl.leaves.size() / 2;
     ds.off_compounds = append(blob, fl.compounds);      ds.n_compounds = (uint32_t)fl.compounds.size() / 2;
     ds.off_ops = append(blob, fl.ops);                  ds.n_ops = (uint32_t)fl.ops.size();
-    // the pre-test scans four records per step: pad with records no ray selects
-    while (fl.sphere_k.size() % 4 != 0) fl.sphere_k.push_back(make_float4(0.f, 0.f, 0.f, 1.0e30f));
     ds.off_sphere_k = append(blob, fl.sphere_k);
-    if (fl.spheres.size() > 65535) {
-        delete sc;
-        return fail(RL_ERR_UNSUPPORTED, "more than 65535 spheres");
-    }
+    ds.off_clusters = append(blob, clusters);           ds.n_clusters = (uint32_t)clusters.size();
+    ds.off_cluster_range = append(blob, cluster_range);
     ds.sphere_cmax2 = (float)(fl.cmax2 * 1.0001);
+    ds.cluster_rmax = (float)(cluster_rmax * 1.0001);
     ds.off_sphere_obj = append(blob, fl.sphere_obj);
     ds.off_plane_obj = append(blob, fl.plane_obj);
     ds.off_paraboloid_obj = append(blob, fl.paraboloid_obj);

@@ -6,7 +6,9 @@
 // warp walks each list with uniform (broadcast) shared-memory loads:
 //
 //   spheres      n_spheres     x float4   {cx, cy, cz, r^2}
-//   sphere_k     n_spheres(+3) x float4   {cx, cy, cz, |c|^2 - r^2}, record of the sphere pre-test
+//   sphere_k     n_spheres     x float4   {cx, cy, cz, |c|^2 - r^2}, record of the sphere pre-test
+//   clusters     n_clusters    x float4   {mx, my, mz, |m|^2 - R^2}, bounding sphere of a group of spheres
+//   cluster_range n_clusters   x uint32   first member | count << 16 (members are contiguous)
 //   planes       n_planes      x 2 float4 {n.xyz, kind} {offset.xyz, r^2}
 //   paraboloids  n_paraboloids x 3 float4 {offset,0} {normal,0} {focal_point,0}
 //   leaves       n_leaves      x 2 float4 {n.xyz, 0} {offset.xyz, 0}   half-spaces of compounds
@@ -38,16 +40,18 @@ extern __shared__ float4 rl_smem[];
 // struct lives at the start of shared memory so that every device function
 // reaches the tables without carrying them in registers.
 struct PrimTables {
-    uint32_t spheres, sphere_k, planes, paraboloids, leaves, compounds, ops;
+    uint32_t spheres, sphere_k, clusters, cluster_range, planes, paraboloids, leaves, compounds, ops;
     uint32_t sphere_obj, plane_obj, paraboloid_obj, compound_obj;
     uint32_t queues;          // per-thread candidate slots: uint16 [slot * blockDim.x + tid]
-    uint32_t n_spheres, n_planes, n_paraboloids, n_compounds;
-    float sphere_cmax2;
+    uint32_t n_spheres, n_clusters, n_planes, n_paraboloids, n_compounds;
+    float sphere_cmax2, cluster_rmax;
 };
 
 #define RL_TABLES_VEC4 ((sizeof(PrimTables) + 15) / 16)
+#define RL_CLUSTER_SLOTS 16    // queued sphere clusters per lane
 #define RL_CAND_SLOTS 12       // queued sphere candidates per lane
 #define RL_COMPOUND_SLOTS 4    // queued compound candidates per lane
+#define RL_QUEUE_SLOTS (RL_CLUSTER_SLOTS + RL_CAND_SLOTS + RL_COMPOUND_SLOTS)
 
 __device__ __forceinline__ const PrimTables &tables() {
     return *reinterpret_cast<const PrimTables *>(rl_smem);
@@ -65,6 +69,8 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         PrimTables t;
         t.spheres = base + sc.off_spheres;
         t.sphere_k = base + sc.off_sphere_k;
+        t.clusters = base + sc.off_clusters;
+        t.cluster_range = base + sc.off_cluster_range;
         t.planes = base + sc.off_planes;
         t.paraboloids = base + sc.off_paraboloids;
         t.leaves = base + sc.off_leaves;
@@ -76,10 +82,12 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         t.compound_obj = base + sc.off_compound_obj;
         t.queues = base + sc.blob_vec4;
         t.n_spheres = sc.n_spheres;
+        t.n_clusters = sc.n_clusters;
         t.n_planes = sc.n_planes;
         t.n_paraboloids = sc.n_paraboloids;
         t.n_compounds = sc.n_compounds;
         t.sphere_cmax2 = sc.sphere_cmax2;
+        t.cluster_rmax = sc.cluster_rmax;
         *reinterpret_cast<PrimTables *>(rl_smem) = t;
     }
     __syncthreads();
@@ -88,7 +96,7 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
 // Shared memory a tracing kernel needs with `threads` threads per block.
 inline size_t tracing_smem_bytes(const DevScene &sc, int threads) {
     return (RL_TABLES_VEC4 + (size_t)sc.blob_vec4) * sizeof(float4)
-           + (size_t)(RL_CAND_SLOTS + RL_COMPOUND_SLOTS) * threads * sizeof(uint16_t);
+           + (size_t)RL_QUEUE_SLOTS * threads * sizeof(uint16_t);
 }
 
 // ---------------------------------------------------------------------- RNG
@@ -463,43 +471,85 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
     const float thr = -7.6293945e-6f * scale;                                          // -2^-17 * scale
     const float bthr = -1.9073486e-6f * sqrtf((tb.sphere_cmax2 + oo) * dd) - 1.0e-30f;  // -2^-19 * ...
 
-    uint16_t *sq = reinterpret_cast<uint16_t *>(rl_smem + tb.queues) + threadIdx.x;  // slot k at sq[k * qstride]
+    // Two-level scan.  Level 1, uniform over the warp: the same pre-test against the bounding
+    // sphere {m, R} of each cluster of spheres, with thresholds widened so that a cluster is
+    // kept whenever the reference could accept one of its members: a member i the reference
+    // accepts has r_i^2 - dist(line, c_i)^2 >= -S/2 with S = 2 e1 + 2 |dd - 1| (cmax2 + |o|^2)
+    // (rounding of the reference's discriminant, and its use of B^2 - C for a direction that
+    // is only unit to rounding), hence dist(line, m) <= R + sqrt(S/2) and
+    // R^2 - dist(line, m)^2 >= -(2 R sqrt(S/2) + S/2); B_cluster >= B_i - |d| R.
+    uint16_t *clq = reinterpret_cast<uint16_t *>(rl_smem + tb.queues) + threadIdx.x;  // slot k at clq[k * qstride]
     const uint32_t qstride = blockDim.x;
+    uint16_t *sq = clq + RL_CLUSTER_SLOTS * qstride;
     const float4 *spheres = sm_vec(tb.spheres);
     const float4 *sphere_k = sm_vec(tb.sphere_k);
+    const float4 *clusters = sm_vec(tb.clusters);
+    const uint32_t *cluster_range = sm_u32(tb.cluster_range);
     const uint32_t *sphere_obj = sm_u32(tb.sphere_obj);
-    const uint32_t n_spheres = tb.n_spheres;
+    const uint32_t n_clusters = tb.n_clusters;
+    const float slack = -2.0f * thr + 2.0f * fabsf(dd - 1.0f) * (tb.sphere_cmax2 + oo);
+    const float thr_c = -(2.0f * tb.cluster_rmax * sqrtf(slack) + 2.0f * slack);
+    const float bthr_c = bthr - sqrtf(dd) * tb.cluster_rmax;
     uint32_t i = 0;
     do {
-        uint16_t *tail = sq;                                    // next free slot of this lane's queue
-        uint16_t *const limit = sq + (RL_CAND_SLOTS - 4) * qstride;
-        // uniform scan, four spheres per step, while every queue has room for four more
-        for (; i < n_spheres; i += 4) {
+        uint16_t *ctail = clq;                                  // next free slot of this lane's cluster queue
+        uint16_t *const climit = clq + (RL_CLUSTER_SLOTS - 4) * qstride;
+        for (; i < n_clusters; i += 4) {
 #pragma unroll
             for (uint32_t j = 0; j < 4; j++) {
                 // the table is padded with never-selected records to a multiple of four
-                const float4 s = sphere_k[i + j];               // {cx, cy, cz, |c|^2 - r^2}
+                const float4 s = clusters[i + j];               // {mx, my, mz, |m|^2 - R^2}
                 const float b = fmaf(d.x, s.x, fmaf(d.y, s.y, fmaf(d.z, s.z, ndo)));
                 const float c = fmaf(m2ox, s.x, fmaf(m2oy, s.y, fmaf(m2oz, s.z, s.w))) + oo;
                 const float disc = fmaf(b, b, -c);
-                if (disc >= thr && b >= bthr) {
-                    *tail = (uint16_t)(i + j);
+                if (disc >= thr_c && b >= bthr_c) {
+                    *ctail = (uint16_t)(i + j);
+                    ctail += qstride;
+                }
+            }
+            if (__any_sync(0xffffffffu, ctail > climit)) { i += 4; break; }
+        }
+        // Level 2, per lane: the members of the queued clusters, flattened into one loop so
+        // that lanes stay busy across cluster boundaries; survivors of the per-sphere pre-test
+        // go to the sphere queue (a full queue is drained on the spot).
+        uint16_t *tail = sq;
+        uint16_t *const limit = sq + RL_CAND_SLOTS * qstride;
+        const uint16_t *cnext = clq;
+        uint32_t cur = 0, end = 0;
+        for (;;) {
+            if (cur == end && cnext < ctail) {
+                const uint32_t r = cluster_range[*cnext];
+                cnext += qstride;
+                cur = r & 0xffffu;
+                end = cur + (r >> 16);
+            }
+            if (cur == end) break;
+            const float4 s = sphere_k[cur];                     // {cx, cy, cz, |c|^2 - r^2}
+            const float b = fmaf(d.x, s.x, fmaf(d.y, s.y, fmaf(d.z, s.z, ndo)));
+            const float c = fmaf(m2ox, s.x, fmaf(m2oy, s.y, fmaf(m2oz, s.z, s.w))) + oo;
+            const float disc = fmaf(b, b, -c);
+            if (disc >= thr && b >= bthr) {
+                if (tail == limit) {
+                    const float t = sphere_t(spheres[cur], ray);
+                    if (t > 0.0f) consider(best, t, (int)sphere_obj[cur], (RL_HIT_SPHERE << 28) | cur);
+                } else {
+                    *tail = (uint16_t)cur;
                     tail += qstride;
                 }
             }
-            if (__any_sync(0xffffffffu, tail > limit)) { i += 4; break; }
+            cur++;
         }
-        // exact Sphere::intersect for the queued candidates of this lane
+        // Level 3: exact Sphere::intersect for the queued candidates of this lane
         for (const uint16_t *q = sq; q < tail; q += qstride) {
             const uint32_t idx = *q;
             const float t = sphere_t(spheres[idx], ray);
             if (t > 0.0f) consider(best, t, (int)sphere_obj[idx], (RL_HIT_SPHERE << 28) | idx);
         }
-    } while (__any_sync(0xffffffffu, i < n_spheres));
+    } while (__any_sync(0xffffffffu, i < n_clusters));
 
     intersect_flat_surfaces(tb, ray, best);
 
-    uint16_t *cq = sq + RL_CAND_SLOTS * qstride;
+    uint16_t *cq = sq + RL_CAND_SLOTS * qstride;                // compound queue
     const float4 *compounds = sm_vec(tb.compounds);
     const uint32_t *compound_obj = sm_u32(tb.compound_obj);
     const uint32_t n_compounds = tb.n_compounds;

@@ -28,9 +28,11 @@ struct DevScene {
     uint32_t off_compounds, n_compounds;
     uint32_t off_ops, n_ops;
     uint32_t off_sphere_obj, off_plane_obj, off_paraboloid_obj, off_compound_obj, off_sphere_k;
+    uint32_t off_clusters, n_clusters, off_cluster_range;
     const float4 *materials;  // per object
     uint32_t n_objects;
-    float sphere_cmax2;       // max (|centre|^2 + r^2) over the spheres (error bound of the pre-test)
+    float sphere_cmax2;       // max (|centre|^2 + r^2) over spheres and clusters (error bound of the pre-test)
+    float cluster_rmax;       // largest cluster bounding radius
     DevCamera camera;
 };
 
