@@ -20,7 +20,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librl_b200.so")
+# RL_B200_LIB overrides the library path (tuning experiments build variants beside the default)
+LIB_PATH = os.environ.get("RL_B200_LIB") or os.path.join(_HERE, "librl_b200.so")
 
 BATCH_PHOTONS = 1024 * 512        # trace_unit.rs:67
 TEST_BATCH_PHOTONS = 1024         # trace_unit.rs:70

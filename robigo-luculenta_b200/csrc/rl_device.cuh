@@ -167,6 +167,24 @@ __device__ __forceinline__ Quat rotation_dev(float x, float y, float z, float an
     return mkq(sc.x * x, sc.x * y, sc.x * z, sc.y);
 }
 
+// Vector3::normalise (vector3.rs:56-67) through one shared out-of-line copy:
+// a square root and three IEEE divisions, nine call sites.
+static __device__ __noinline__ float3 normalise_call(float x, float y, float z) {
+    const V3 n = normalise(mk(x, y, z));
+    return make_float3(n.x, n.y, n.z);
+}
+__device__ __forceinline__ V3 normalise_dev(V3 a) {
+    const float3 n = normalise_call(a.x, a.y, a.z);
+    return mk(n.x, n.y, n.z);
+}
+__device__ __forceinline__ V3 rotate_towards_dev(V3 v, V3 n) {                            // vector3.rs:69-83
+    if (n.z > 0.9999f) return v;
+    if (n.z < -0.9999f) return mk(v.x, v.y, -v.z);
+    const V3 a1 = normalise_dev(cross(mk(0.0f, 0.0f, 1.0f), n));
+    const V3 a2 = normalise_dev(cross(a1, n));
+    return a1 * v.x + a2 * v.y + n * v.z;
+}
+
 struct Ray { V3 origin, direction; float wavelength; };
 
 // A ray that hits nothing and queues nothing: lanes without a live path trace
@@ -208,14 +226,14 @@ __device__ __forceinline__ Ray camera_ray(const DevCamera &cm, float x, float y,
     const float screen_distance = 1.0f / (fov.x / fov.y);              // 1 / tan, spec_tan = sin / cos
     const float xs = x * chromatic_zoom;
     const float ys = y * chromatic_zoom;
-    const V3 direction = normalise(mk(xs, screen_distance, -ys));
+    const V3 direction = normalise_dev(mk(xs, screen_distance, -ys));
     const V3 focus_point = direction * (focal_distance / direction.y);
     const float2 dof = sincos_call(dof_angle);
     const float sd = dof.x, cd = dof.y;
     const V3 lens_point = mk(cd * dof_radius, 0.0f, sd * dof_radius);
     Ray r;
     r.origin = position + rotate(lens_point, orientation);
-    r.direction = normalise(rotate(focus_point - lens_point, orientation));
+    r.direction = normalise_dev(rotate(focus_point - lens_point, orientation));
     r.wavelength = wavelength;
     return r;
 }
@@ -301,50 +319,50 @@ __device__ __forceinline__ float compound_t(uint32_t first_leaf, uint32_t first_
     const PrimTables &tb = tables();
     const float4 *leaves = sm_vec(tb.leaves);
     const uint32_t *ops = sm_u32(tb.ops);
-    float st_t[RL_MAX_COMPOUND_STACK];
-    uint32_t st_leaf[RL_MAX_COMPOUND_STACK];
-    int sp = 0;
+    // evaluation stack of (distance, leaf) pairs in registers, top at index 0; the host
+    // rejects programs that need more than RL_MAX_COMPOUND_STACK entries
+    float t0 = -1.0f, t1 = -1.0f, t2 = -1.0f, t3 = -1.0f, t4 = -1.0f;
+    uint32_t l0 = 0, l1 = 0, l2 = 0, l3 = 0, l4 = 0;
+#pragma unroll 1
     for (uint32_t i = 0; i < n_ops; i++) {
         const uint32_t op = ops[first_op + i];
         if ((op & 3u) == 0u) {
             const uint32_t leaf = first_leaf + (op >> 8);
             const float4 n4 = leaves[2 * leaf], o4 = leaves[2 * leaf + 1];
             float d;
-            st_t[sp] = plane_t(mk(n4.x, n4.y, n4.z), mk(o4.x, o4.y, o4.z), ray, d);
-            st_leaf[sp] = leaf;
-            sp++;
+            const float t = plane_t(mk(n4.x, n4.y, n4.z), mk(o4.x, o4.y, o4.z), ray, d);
+            t4 = t3; l4 = l3; t3 = t2; l3 = l2; t2 = t1; l2 = l1; t1 = t0; l1 = l0;
+            t0 = t; l0 = leaf;
         } else {
             const uint32_t lo = first_leaf + ((op >> 8) & 0xffu);
             const uint32_t mid = first_leaf + ((op >> 16) & 0xffu);
             const uint32_t hi = first_leaf + ((op >> 24) & 0xffu);
-            float t2 = st_t[sp - 1]; const uint32_t l2 = st_leaf[sp - 1];
-            float t1 = st_t[sp - 2]; const uint32_t l1 = st_leaf[sp - 2];
-            sp -= 2;
-            if (t1 > 0.0f) {  // surface2.lies_inside(i1.position)
-                const V3 pos = ray.origin + ray.direction * t1;
+            float b2 = t0; const uint32_t k2 = l0;              // surface2's hit
+            float b1 = t1; const uint32_t k1 = l1;              // surface1's hit
+            if (b1 > 0.0f) {  // surface2.lies_inside(i1.position)
+                const V3 pos = ray.origin + ray.direction * b1;
+#pragma unroll 1
                 for (uint32_t k = mid; k < hi; k++) {
                     const float4 n4 = leaves[2 * k], o4 = leaves[2 * k + 1];
-                    if (!(dot(pos - mk(o4.x, o4.y, o4.z), mk(n4.x, n4.y, n4.z)) < 0.0f)) { t1 = -1.0f; break; }
+                    if (!(dot(pos - mk(o4.x, o4.y, o4.z), mk(n4.x, n4.y, n4.z)) < 0.0f)) { b1 = -1.0f; break; }
                 }
             }
-            if (t2 > 0.0f) {  // surface1.lies_inside(i2.position)
-                const V3 pos = ray.origin + ray.direction * t2;
+            if (b2 > 0.0f) {  // surface1.lies_inside(i2.position)
+                const V3 pos = ray.origin + ray.direction * b2;
+#pragma unroll 1
                 for (uint32_t k = lo; k < mid; k++) {
                     const float4 n4 = leaves[2 * k], o4 = leaves[2 * k + 1];
-                    if (!(dot(pos - mk(o4.x, o4.y, o4.z), mk(n4.x, n4.y, n4.z)) < 0.0f)) { t2 = -1.0f; break; }
+                    if (!(dot(pos - mk(o4.x, o4.y, o4.z), mk(n4.x, n4.y, n4.z)) < 0.0f)) { b2 = -1.0f; break; }
                 }
             }
-            float t; uint32_t l;
-            if (t1 > 0.0f && t2 > 0.0f) {
-                if (t1 < t2) { t = t1; l = l1; } else { t = t2; l = l2; }
-            } else if (t1 > 0.0f) { t = t1; l = l1; }
-            else { t = t2; l = l2; }
-            st_t[sp] = t; st_leaf[sp] = l;
-            sp++;
+            // both valid: the nearer, ties to surface2 (geometry.rs:391-396); else whichever is valid
+            const bool first = b1 > 0.0f && (!(b2 > 0.0f) || b1 < b2);
+            t0 = first ? b1 : b2; l0 = first ? k1 : k2;
+            t1 = t2; l1 = l2; t2 = t3; l2 = l3; t3 = t4; l3 = l4;
         }
     }
-    leaf_out = st_leaf[0];
-    return st_t[0];
+    leaf_out = l0;
+    return t0;
 }
 
 // Plane, Circle, top-level SpacePartitioning and Paraboloid objects: few per
@@ -413,6 +431,7 @@ __device__ __forceinline__ bool slab_may_hit(uint32_t first_leaf, uint32_t n_lea
     const float4 *leaves = sm_vec(tables().leaves);
     float t_enter = 0.0f, t_exit = 3.0e38f;
     bool outside_parallel = false;
+#pragma unroll 1
     for (uint32_t k = first_leaf; k < first_leaf + n_leaves; k++) {
         const float4 n4 = leaves[2 * k], o4 = leaves[2 * k + 1];
         const float dn = fmaf(n4.z, ray.direction.z, fmaf(n4.y, ray.direction.y, n4.x * ray.direction.x));
@@ -574,13 +593,22 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
             }
             if (__any_sync(0xffffffffu, cnt == RL_COMPOUND_SLOTS)) { i++; break; }
         }
+        // slab test for every queued body first, compacting the survivors in place, so that the
+        // lanes which need the exact evaluation run it in the same (few) iterations
+        uint32_t kept = 0;
         for (uint32_t k = 0; k < cnt; k++) {
             const uint32_t idx = cq[k * qstride];
             const float4 c4 = compounds[2 * idx];
-            const uint32_t first_leaf = __float_as_uint(c4.x), n_leaves = __float_as_uint(c4.y);
-            if (!slab_may_hit(first_leaf, n_leaves, ray, best.t)) continue;
+            if (slab_may_hit(__float_as_uint(c4.x), __float_as_uint(c4.y), ray, best.t)) {
+                cq[kept * qstride] = (uint16_t)idx;
+                kept++;
+            }
+        }
+        for (uint32_t k = 0; k < kept; k++) {
+            const uint32_t idx = cq[k * qstride];
+            const float4 c4 = compounds[2 * idx];
             uint32_t leaf;
-            const float t = compound_t(first_leaf, __float_as_uint(c4.z), __float_as_uint(c4.w), ray, leaf);
+            const float t = compound_t(__float_as_uint(c4.x), __float_as_uint(c4.z), __float_as_uint(c4.w), ray, leaf);
             if (t > 0.0f) consider(best, t, (int)compound_obj[idx], (RL_HIT_LEAF << 28) | leaf);
         }
     } while (__any_sync(0xffffffffu, i < n_compounds));
@@ -599,8 +627,8 @@ __device__ __forceinline__ Surf surface_at(const Ray &ray, const Hit &hit) {
     const uint32_t type = hit.code >> 28, idx = hit.code & 0x0fffffffu;
     if (type == RL_HIT_SPHERE) {                                       // geometry.rs:243-251
         const float4 sp = sm_vec(tb.spheres)[idx];
-        s.normal = normalise(s.position - mk(sp.x, sp.y, sp.z));
-        s.tangent = normalise(cross(mk(0.0f, 1.0f, 0.0f), s.normal));
+        s.normal = normalise_dev(s.position - mk(sp.x, sp.y, sp.z));
+        s.tangent = normalise_dev(cross(mk(0.0f, 1.0f, 0.0f), s.normal));
     } else if (type == RL_HIT_PLANE) {
         const float4 n4 = sm_vec(tb.planes)[2 * idx];
         const V3 n = mk(n4.x, n4.y, n4.z);
@@ -617,7 +645,7 @@ __device__ __forceinline__ Surf surface_at(const Ray &ray, const Hit &hit) {
         const V3 focal_point = mk(p[2].x, p[2].y, p[2].z);
         const V3 local_pos = s.position - offset;
         const V3 plane_pr = local_pos - normal * dot(local_pos, normal);
-        s.normal = normalise(focal_point - plane_pr);
+        s.normal = normalise_dev(focal_point - plane_pr);
     } else {                                                           // geometry.rs:115
         const float4 n4 = sm_vec(tb.leaves)[2 * idx];
         s.normal = mk(n4.x, n4.y, n4.z);
@@ -634,7 +662,7 @@ __device__ __forceinline__ V3 diffuse_direction(const Ray &in, const Surf &s, Rn
     const float2 sc = sincos_call(phi);
     const V3 hemi = mk(sc.y * r, sc.x * r, sqrtf(1.0f - rq));
     const V3 normal = dot(in.direction, s.normal) < 0.0f ? s.normal : -s.normal;
-    return rotate_towards(hemi, normal);
+    return rotate_towards_dev(hemi, normal);
 }
 
 __device__ __forceinline__ float soap_clamp(float x) {                 // material.rs:290-294
@@ -657,7 +685,7 @@ __device__ __forceinline__ V3 material_bounce(float4 m, const Ray &in, const Sur
         V3 dir = diffuse_direction(in, s, rng);
         if (kind == RL_MATERIAL_GLOSSY_MIRROR) {
             const V3 reflection = reflect(in.direction, s.normal);
-            dir = normalise(dir * m.y + reflection * (1.0f - m.y));
+            dir = normalise_dev(dir * m.y + reflection * (1.0f - m.y));
         }
         return dir;
     }

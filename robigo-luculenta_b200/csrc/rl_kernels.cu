@@ -18,7 +18,12 @@ static std::atomic<uint64_t> g_launches{0};
 uint64_t kernel_launches() { return g_launches.load(); }
 void kernel_launches_reset() { g_launches.store(0); }
 
+#ifndef RL_TRACE_THREADS
 #define RL_TRACE_THREADS 256
+#endif
+#ifndef RL_TRACE_MIN_BLOCKS
+#define RL_TRACE_MIN_BLOCKS 3
+#endif
 
 // ------------------------------------------------------------------ K1 trace
 struct TraceArgs {
@@ -37,7 +42,7 @@ struct TraceArgs {
 // as its current path ends, so a warp never idles on its longest path.  The
 // primitive tables live in shared memory; each loop iteration is one
 // Scene::intersect plus one material interaction for every live lane.
-__global__ void __launch_bounds__(RL_TRACE_THREADS)
+__global__ void __launch_bounds__(RL_TRACE_THREADS, RL_TRACE_MIN_BLOCKS)
 trace_kernel(const DevScene sc, const TraceArgs a) {
     setup_tables(sc);
 

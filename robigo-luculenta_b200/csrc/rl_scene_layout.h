@@ -5,7 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define RL_MAX_COMPOUND_STACK 8   // deepest evaluation stack of a compound-surface program
+#define RL_MAX_COMPOUND_STACK 5   // deepest evaluation stack of a compound-surface program
 
 namespace rl {
 
