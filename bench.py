@@ -325,9 +325,12 @@ def main():
     n_splat = 1 << 25                                   # 512 MiB of records > L2
     tr2 = pkg.TraceUnit(100, WIDTH, HEIGHT, seed=SEED, batch=n_splat)
     tr2.set_stream(stream)
-    tr2.render_range(scene, 0, n_splat, download=False)
+    records = tr2.render_range(scene, 0, n_splat, download=True)
+    n_lit = int(np.count_nonzero(records["probability"]))   # only these carry accumulator payload
+    del records
     splat_ms = time_ms(lambda: plot.plot(tr2), 5)
     plot.clear()
+    splat_bytes = n_splat * 16 + n_lit * SPLAT_FUSED_BYTES_PER_PHOTON
     gw = 4096                                           # 4096^2: 192 MiB acc + 256 MiB plot > L2
     gp, gg = pkg.PlotUnit(101, gw, gw), pkg.GatherUnit(gw, gw)
     gp.set_stream(stream); gg.set_stream(stream)
@@ -337,10 +340,17 @@ def main():
     kernel_s = kernel_ms * 1e-3 / args.steps
     photons_per_launch = n
     achieved = photons_per_launch * SPLAT_FUSED_BYTES_PER_PHOTON / kernel_s / 1e9
+    # DRAM traffic of the kernel from the committed ncu capture (profiles/, 2^24-photon launch),
+    # scaled to this launch's photon count
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "trace_kernel_dram_bytes_per_photon.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)["dram_bytes_per_photon"] * photons_per_launch
     roofline = {
         "kernel": "trace_kernel (fused TraceUnit::render + PlotUnit::plot)",
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_photon": SPLAT_FUSED_BYTES_PER_PHOTON,
         "note": ("the fused kernel is FP32-issue/divergence bound, not HBM bound: scene tables sit in shared "
                  "memory and the 16.8 MB accumulator is L2-resident, so its HBM fraction is small by design; "
@@ -348,8 +358,9 @@ def main():
         "kernel_ms_per_launch": kernel_s * 1e3,
         "also": [
             {"kernel": "splat_kernel (PlotUnit::plot, 2^25 records)", "bound": "hbm",
-             "achieved": n_splat * SPLAT_BYTES_PER_PHOTON / (splat_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-             "frac": n_splat * SPLAT_BYTES_PER_PHOTON / (splat_ms * 1e-3) / 1e9 / peak, "ms": splat_ms},
+             "achieved": splat_bytes / (splat_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+             "frac": splat_bytes / (splat_ms * 1e-3) / 1e9 / peak, "ms": splat_ms,
+             "bytes": f"16 B x {n_splat} records + 48 B x {n_lit} contributing photons"},
             {"kernel": "gather_kernel (GatherUnit::accumulate + clear, 4096^2)", "bound": "hbm",
              "achieved": gw * gw * GATHER_BYTES_PER_PIXEL / (gather_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
              "frac": gw * gw * GATHER_BYTES_PER_PIXEL / (gather_ms * 1e-3) / 1e9 / peak, "ms": gather_ms},
