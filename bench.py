@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: gather kernel reads the peers' frames over NVLink (p2p) or NCCL reduce first")
     ap.add_argument("--photons", type=int, default=PHOTONS_PER_STEP, help=argparse.SUPPRESS)
     args = ap.parse_args()
 
@@ -214,14 +216,37 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
     first = rank * n                                                     # this rank's photon ids
 
+    # N > 1, p2p: every rank exports its accumulator; rank 0 maps them and its gather kernel
+    # reads all frames in one launch (peer loads over NVLink), one Kahan step per frame
+    peer_ptrs = None
+    use_p2p = world > 1 and args.reduce == "p2p"
+    if use_p2p:
+        handles = [None] * world
+        dist.all_gather_object(handles, plot.ipc_export())
+        if rank == 0:
+            peer_ptrs = [plot_ptr] + [pkg.ipc_open(handles[r]) for r in range(1, world)]
+
+    def combine():
+        """the path's one exchange step: frames of all ranks -> rank 0's gather unit"""
+        if world == 1:
+            gather.accumulate(plot, clear=True)
+        elif use_p2p:
+            dist.barrier()                       # every rank's trace kernel has finished
+            if rank == 0:
+                gather.accumulate_device(peer_ptrs)
+                gather.sync()
+            dist.barrier()                       # frames consumed: owners may clear them
+            plot.clear()
+        else:
+            dist.reduce(plot_view, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                gather.accumulate(plot, clear=True)
+            else:
+                plot.clear()
+
     def step():
         trace.render_fused(scene, plot, first, n)
-        if world > 1:
-            dist.reduce(plot_view, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            gather.accumulate(plot, clear=True)
-        elif world > 1:
-            plot.clear()
+        combine()
 
     def barrier():
         if world > 1:
@@ -244,12 +269,7 @@ def main():
         a.record()
         trace.render_fused(scene, plot, first, n)
         b.record()                           # [a, b] = the trace+splat kernel alone
-        if world > 1:
-            dist.reduce(plot_view, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            gather.accumulate(plot, clear=True)
-        elif world > 1:
-            plot.clear()
+        combine()
         c.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -272,16 +292,13 @@ def main():
     host_xyz = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float32).pin_memory().numpy()
     h2d = desc.n_surfaces * 52 + desc.n_objects * 20 + 84
     d2h = WIDTH * HEIGHT * 12
-    e2e_gather = pkg.GatherUnit(WIDTH, HEIGHT)
-    e2e_gather.set_stream(stream)
 
     def e2e_step():
         sc = pkg.Scene(desc)
         trace.render_fused(sc, plot, first, n)
-        if world > 1:
-            dist.reduce(plot_view, dst=0, op=dist.ReduceOp.SUM)
-        e2e_gather.accumulate(plot, clear=True)
-        e2e_gather.download(out=host_xyz)
+        combine()
+        if rank == 0:
+            gather.download(out=host_xyz)
         return sc
 
     e2e_step()
@@ -385,7 +402,9 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "photons_per_step_per_gpu": n, "seed": SEED,
                    "l2": "flushed (256 MiB write) between timed steps",
-                   "parallelism": f"photon-id partition x{world}, one NCCL reduce of the XYZ framebuffer per step"
+                   "parallelism": f"photon-id partition x{world}, XYZ frames combined on rank 0 per step by "
+                                  + ("the gather kernel reading peer frames over NVLink (CUDA IPC)" if use_p2p
+                                     else "one NCCL reduce")
                    if world > 1 else "single GPU"},
         "rays_per_photon": total_rays / (n * world * args.steps),
         "mphotons_per_s": n * world * args.steps / (step_ms * 1e-3) / 1e6,

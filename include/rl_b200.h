@@ -228,6 +228,15 @@ int rl_plot_unit_download(rl_plot_unit *unit, float *xyz);
  * (X, Y, Z, 0), for zero-copy views (NCCL reduce, peer access). */
 int rl_plot_unit_device_buffer(rl_plot_unit *unit, void **out_ptr, size_t *out_bytes);
 int rl_plot_unit_sync(rl_plot_unit *unit);
+/* Cross-process sharing of the accumulator (one process per GPU): export a
+ * 64-byte handle (cudaIpcMemHandle_t) in the owning process, open it in the
+ * gathering process to get a device pointer usable as a source of
+ * rl_gather_unit_accumulate_device -- the cross-GPU sum is then fused into the
+ * gather kernel as peer loads over NVLink. */
+#define RL_IPC_HANDLE_BYTES 64
+int rl_plot_unit_ipc_export(rl_plot_unit *unit, void *handle_out);
+int rl_ipc_open(const void *handle, void **out_ptr);
+int rl_ipc_close(void *ptr);
 
 /* ---------------------------------------------------------- GatherUnit   */
 

@@ -124,6 +124,9 @@ SYMBOLS = {
     "rl_plot_unit_download": (_I, [_P, _P]),
     "rl_plot_unit_device_buffer": (_I, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "rl_plot_unit_sync": (_I, [_P]),
+    "rl_plot_unit_ipc_export": (_I, [_P, _P]),
+    "rl_ipc_open": (_I, [_P, C.POINTER(_P)]),
+    "rl_ipc_close": (_I, [_P]),
     "rl_gather_unit_create": (_I, [_U32, _U32, C.c_char_p, C.POINTER(_P)]),
     "rl_gather_unit_destroy": (_I, [_P]),
     "rl_gather_unit_set_stream": (_I, [_P, _P]),
@@ -413,6 +416,12 @@ class PlotUnit:
     def sync(self):
         _check(lib().rl_plot_unit_sync(self._h))
 
+    def ipc_export(self):
+        """64-byte handle another process can open with ipc_open()."""
+        buf = C.create_string_buffer(64)
+        _check(lib().rl_plot_unit_ipc_export(self._h, buf))
+        return buf.raw
+
 
 class GatherUnit:
     """gather_unit.rs:24-94"""
@@ -497,6 +506,17 @@ class TonemapUnit:
         v = C.c_float()
         _check(lib().rl_tonemap_unit_last_exposure(self._h, C.byref(v)))
         return float(v.value)
+
+
+def ipc_open(handle_bytes):
+    """Device pointer of a peer process's accumulator (see PlotUnit.ipc_export)."""
+    p = _P()
+    _check(lib().rl_ipc_open(handle_bytes, C.byref(p)))
+    return p.value
+
+
+def ipc_close(ptr):
+    _check(lib().rl_ipc_close(_P(ptr)))
 
 
 # --------------------------------------------------------------- math probes

@@ -717,6 +717,30 @@ int rl_plot_unit_device_buffer(rl_plot_unit *u, void **out_ptr, size_t *out_byte
     return RL_OK;
 }
 
+int rl_plot_unit_ipc_export(rl_plot_unit *u, void *handle_out) {
+    if (!u || !handle_out) return fail(RL_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == RL_IPC_HANDLE_BYTES, "IPC handle size");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    cudaIpcMemHandle_t h;
+    RL_CUDA(cudaIpcGetMemHandle(&h, u->d_accum));
+    memcpy(handle_out, &h, sizeof(h));
+    return RL_OK;
+}
+
+int rl_ipc_open(const void *handle, void **out_ptr) {
+    if (!handle || !out_ptr) return fail(RL_ERR_INVALID, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    RL_CUDA(cudaIpcOpenMemHandle(out_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RL_OK;
+}
+
+int rl_ipc_close(void *ptr) {
+    if (!ptr) return RL_OK;
+    RL_CUDA(cudaIpcCloseMemHandle(ptr));
+    return RL_OK;
+}
+
 int rl_plot_unit_sync(rl_plot_unit *u) {
     if (!u) return fail(RL_ERR_INVALID, "null unit");
     RL_CUDA(cudaSetDevice(u->dev.index));
