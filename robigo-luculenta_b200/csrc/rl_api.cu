@@ -407,6 +407,7 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
         std::vector<Cluster> cl;
         size_t leaf = (size_t)(0.38 * sqrt((double)n) + 0.5);
         leaf = leaf < 4 ? 4 : (leaf > 32 ? 32 : leaf);
+        if (leaf < (n + 999) / 1000) leaf = (n + 999) / 1000;   // pair records index clusters with 11 bits
         if (n) split_spheres(fl.spheres, idx, 0, n, leaf, cl);
         std::vector<float4> spheres(n), sphere_k(n);
         std::vector<uint32_t> sphere_obj(n);

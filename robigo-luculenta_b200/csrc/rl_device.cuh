@@ -31,7 +31,7 @@
 namespace rl {
 
 // Dynamic shared memory of every kernel that traces:
-//   [ PrimTables header | primitive blob | per-thread candidate queues ]
+//   [ PrimTables header | primitive blob | scratch: ray table, candidate queues, pair lists, counters ]
 extern __shared__ float4 rl_smem[];
 
 // Views into the blob once it sits in shared memory, as offsets from rl_smem in
@@ -42,16 +42,17 @@ extern __shared__ float4 rl_smem[];
 struct PrimTables {
     uint32_t spheres, sphere_k, clusters, cluster_range, planes, paraboloids, leaves, compounds, ops;
     uint32_t sphere_obj, plane_obj, paraboloid_obj, compound_obj;
-    uint32_t queues;          // per-thread candidate slots: uint16 [slot * blockDim.x + tid]
+    uint32_t scratch;         // per-block scratch behind the blob (see Scratch)
     uint32_t n_spheres, n_clusters, n_planes, n_paraboloids, n_compounds;
     float sphere_cmax2, cluster_rmax;
 };
 
 #define RL_TABLES_VEC4 ((sizeof(PrimTables) + 15) / 16)
-#define RL_CLUSTER_SLOTS 16    // queued sphere clusters per lane
-#define RL_CAND_SLOTS 12       // queued sphere candidates per lane
+#define RL_CAND_SLOTS 16       // queued sphere candidates per lane
 #define RL_COMPOUND_SLOTS 4    // queued compound candidates per lane
-#define RL_QUEUE_SLOTS (RL_CLUSTER_SLOTS + RL_CAND_SLOTS + RL_COMPOUND_SLOTS)
+#define RL_PAIR_CAP 512        // (lane, cluster) pairs per warp and round
+// scratch bytes per thread: ray table 48 + sphere queue 32 + compound queue 8 + pair list 32 + counters 8
+#define RL_SCRATCH_BYTES_PER_THREAD (48 + 2 * RL_CAND_SLOTS + 2 * RL_COMPOUND_SLOTS + 2 * RL_PAIR_CAP / 32 + 8)
 
 __device__ __forceinline__ const PrimTables &tables() {
     return *reinterpret_cast<const PrimTables *>(rl_smem);
@@ -80,7 +81,7 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         t.plane_obj = base + sc.off_plane_obj;
         t.paraboloid_obj = base + sc.off_paraboloid_obj;
         t.compound_obj = base + sc.off_compound_obj;
-        t.queues = base + sc.blob_vec4;
+        t.scratch = base + sc.blob_vec4;
         t.n_spheres = sc.n_spheres;
         t.n_clusters = sc.n_clusters;
         t.n_planes = sc.n_planes;
@@ -96,7 +97,7 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
 // Shared memory a tracing kernel needs with `threads` threads per block.
 inline size_t tracing_smem_bytes(const DevScene &sc, int threads) {
     return (RL_TABLES_VEC4 + (size_t)sc.blob_vec4) * sizeof(float4)
-           + (size_t)RL_QUEUE_SLOTS * threads * sizeof(uint16_t);
+           + (size_t)RL_SCRATCH_BYTES_PER_THREAD * threads;
 }
 
 // ---------------------------------------------------------------------- RNG
@@ -490,6 +491,25 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
     const float thr = -7.6293945e-6f * scale;                                          // -2^-17 * scale
     const float bthr = -1.9073486e-6f * sqrtf((tb.sphere_cmax2 + oo) * dd) - 1.0e-30f;  // -2^-19 * ...
 
+    // Scratch views (per block): ray table [3 float4 per thread], sphere queues
+    // [slot][thread], compound queues [slot][thread], pair list [RL_PAIR_CAP per warp],
+    // queue counters [thread].
+    const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
+    const uint32_t lane = tid & 31u, wbase = tid & ~31u;
+    float4 *ray_tab = rl_smem + tb.scratch;
+    uint16_t *sq_base = reinterpret_cast<uint16_t *>(ray_tab + 3 * nthreads);
+    uint16_t *cq_base = sq_base + RL_CAND_SLOTS * nthreads;
+    uint16_t *pairs = cq_base + RL_COMPOUND_SLOTS * nthreads + (wbase >> 5) * RL_PAIR_CAP;
+    uint32_t *sq_cnt = reinterpret_cast<uint32_t *>(cq_base + RL_COMPOUND_SLOTS * nthreads
+                                                    + (nthreads >> 5) * RL_PAIR_CAP);
+    // publish this lane's pre-test constants so that any lane of the warp can test a sphere for it
+    ray_tab[3 * tid + 0] = make_float4(m2ox, m2oy, m2oz, oo);
+    ray_tab[3 * tid + 1] = make_float4(d.x, d.y, d.z, ndo);
+    ray_tab[3 * tid + 2] = make_float4(thr, bthr, 0.0f, 0.0f);
+    uint32_t *cq_cnt = sq_cnt + nthreads;
+    sq_cnt[tid] = 0u;
+    cq_cnt[tid] = 0u;
+
     // Two-level scan.  Level 1, uniform over the warp: the same pre-test against the bounding
     // sphere {m, R} of each cluster of spheres, with thresholds widened so that a cluster is
     // kept whenever the reference could accept one of its members: a member i the reference
@@ -497,9 +517,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
     // (rounding of the reference's discriminant, and its use of B^2 - C for a direction that
     // is only unit to rounding), hence dist(line, m) <= R + sqrt(S/2) and
     // R^2 - dist(line, m)^2 >= -(2 R sqrt(S/2) + S/2); B_cluster >= B_i - |d| R.
-    uint16_t *clq = reinterpret_cast<uint16_t *>(rl_smem + tb.queues) + threadIdx.x;  // slot k at clq[k * qstride]
-    const uint32_t qstride = blockDim.x;
-    uint16_t *sq = clq + RL_CLUSTER_SLOTS * qstride;
+    // Kept (lane, cluster) pairs are compacted with a ballot into one list per warp.
     const float4 *spheres = sm_vec(tb.spheres);
     const float4 *sphere_k = sm_vec(tb.sphere_k);
     const float4 *clusters = sm_vec(tb.clusters);
@@ -509,11 +527,11 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
     const float slack = -2.0f * thr + 2.0f * fabsf(dd - 1.0f) * (tb.sphere_cmax2 + oo);
     const float thr_c = -(2.0f * tb.cluster_rmax * sqrtf(slack) + 2.0f * slack);
     const float bthr_c = bthr - sqrtf(dd) * tb.cluster_rmax;
+    const uint32_t lanes_below = (1u << lane) - 1u;
     uint32_t i = 0;
     do {
-        uint16_t *ctail = clq;                                  // next free slot of this lane's cluster queue
-        uint16_t *const climit = clq + (RL_CLUSTER_SLOTS - 4) * qstride;
-        for (; i < n_clusters; i += 4) {
+        uint32_t npairs = 0;                                    // warp-uniform
+        for (; i < n_clusters && npairs <= RL_PAIR_CAP - 128; i += 4) {
 #pragma unroll
             for (uint32_t j = 0; j < 4; j++) {
                 // the table is padded with never-selected records to a multiple of four
@@ -521,61 +539,77 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
                 const float b = fmaf(d.x, s.x, fmaf(d.y, s.y, fmaf(d.z, s.z, ndo)));
                 const float c = fmaf(m2ox, s.x, fmaf(m2oy, s.y, fmaf(m2oz, s.z, s.w))) + oo;
                 const float disc = fmaf(b, b, -c);
-                if (disc >= thr_c && b >= bthr_c) {
-                    *ctail = (uint16_t)(i + j);
-                    ctail += qstride;
+                const bool keep = disc >= thr_c && b >= bthr_c;
+                const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+                if (keep) pairs[npairs + __popc(mask & lanes_below)] = (uint16_t)((lane << 11) | (i + j));
+                npairs += __popc(mask);
+            }
+        }
+        __syncwarp();
+        // Level 2, warp-cooperative: eight lanes take one (lane, cluster) pair and test one
+        // member each with the owner's constants, so the work of lanes with many candidate
+        // clusters is spread over the warp; survivors go to the owner's sphere queue.
+#pragma unroll 1
+        for (uint32_t pb = 0; pb < npairs; pb += 4) {
+            const uint32_t p = pb + (lane >> 3);
+            if (p < npairs) {
+                const uint32_t pair = pairs[p];
+                const uint32_t owner = wbase + (pair >> 11);
+                const uint32_t r = cluster_range[pair & 2047u];
+                const uint32_t end = (r & 0xffffu) + (r >> 16);
+                const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1], rt = ray_tab[3 * owner + 2];
+#pragma unroll 1
+                for (uint32_t m = (r & 0xffffu) + (lane & 7u); m < end; m += 8) {
+                    const float4 s = sphere_k[m];               // {cx, cy, cz, |c|^2 - r^2}
+                    const float b = fmaf(rd.x, s.x, fmaf(rd.y, s.y, fmaf(rd.z, s.z, rd.w)));
+                    const float c = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w))) + ro.w;
+                    const float disc = fmaf(b, b, -c);
+                    if (disc >= rt.x && b >= rt.y) {
+                        const uint32_t slot = atomicAdd(&sq_cnt[owner], 1u);
+                        if (slot < RL_CAND_SLOTS) sq_base[slot * nthreads + owner] = (uint16_t)m;
+                    }
                 }
             }
-            if (__any_sync(0xffffffffu, ctail > climit)) { i += 4; break; }
         }
-        // Level 2, per lane: the members of the queued clusters, flattened into one loop so
-        // that lanes stay busy across cluster boundaries; survivors of the per-sphere pre-test
-        // go to the sphere queue (a full queue is drained on the spot).
-        uint16_t *tail = sq;
-        uint16_t *const limit = sq + RL_CAND_SLOTS * qstride;
-        const uint16_t *cnext = clq;
-        uint32_t cur = 0, end = 0;
-        for (;;) {
-            if (cur == end && cnext < ctail) {
-                const uint32_t r = cluster_range[*cnext];
-                cnext += qstride;
-                cur = r & 0xffffu;
-                end = cur + (r >> 16);
+        __syncwarp();
+        // Level 3, per lane: exact Sphere::intersect for the candidates queued for this lane
+        const uint32_t cnt = sq_cnt[tid];
+        if (cnt > RL_CAND_SLOTS) {
+            // more candidates than slots (pathological): evaluate every sphere exactly
+#pragma unroll 1
+            for (uint32_t k = 0; k < tb.n_spheres; k++) {
+                const float t = sphere_t(spheres[k], ray);
+                if (t > 0.0f) consider(best, t, (int)sphere_obj[k], (RL_HIT_SPHERE << 28) | k);
             }
-            if (cur == end) break;
-            const float4 s = sphere_k[cur];                     // {cx, cy, cz, |c|^2 - r^2}
-            const float b = fmaf(d.x, s.x, fmaf(d.y, s.y, fmaf(d.z, s.z, ndo)));
-            const float c = fmaf(m2ox, s.x, fmaf(m2oy, s.y, fmaf(m2oz, s.z, s.w))) + oo;
-            const float disc = fmaf(b, b, -c);
-            if (disc >= thr && b >= bthr) {
-                if (tail == limit) {
-                    const float t = sphere_t(spheres[cur], ray);
-                    if (t > 0.0f) consider(best, t, (int)sphere_obj[cur], (RL_HIT_SPHERE << 28) | cur);
-                } else {
-                    *tail = (uint16_t)cur;
-                    tail += qstride;
-                }
+        } else {
+#pragma unroll 1
+            for (uint32_t k = 0; k < cnt; k++) {
+                const uint32_t idx = sq_base[k * nthreads + tid];
+                const float t = sphere_t(spheres[idx], ray);
+                if (t > 0.0f) consider(best, t, (int)sphere_obj[idx], (RL_HIT_SPHERE << 28) | idx);
             }
-            cur++;
         }
-        // Level 3: exact Sphere::intersect for the queued candidates of this lane
-        for (const uint16_t *q = sq; q < tail; q += qstride) {
-            const uint32_t idx = *q;
-            const float t = sphere_t(spheres[idx], ray);
-            if (t > 0.0f) consider(best, t, (int)sphere_obj[idx], (RL_HIT_SPHERE << 28) | idx);
-        }
-    } while (__any_sync(0xffffffffu, i < n_clusters));
+        sq_cnt[tid] = 0u;
+        __syncwarp();
+    } while (i < n_clusters);
 
     intersect_flat_surfaces(tb, ray, best);
 
-    uint16_t *cq = sq + RL_CAND_SLOTS * qstride;                // compound queue
+    // Compound bodies.  Bounding-sphere test in a uniform loop, kept (lane, body) pairs compacted
+    // with a ballot; then the slab test warp-cooperatively (eight lanes per pair, one leaf each,
+    // shuffle reduction of the interval); bodies that may be hit go to the owner's queue, and
+    // each lane runs the reference's recursion (compound_t) for its own queue.
+    ray_tab[3 * tid + 2].z = best.t;                            // nearest hit so far: bodies beyond it are skipped
     const float4 *compounds = sm_vec(tb.compounds);
+    const float4 *leaves = sm_vec(tb.leaves);
     const uint32_t *compound_obj = sm_u32(tb.compound_obj);
     const uint32_t n_compounds = tb.n_compounds;
+    const uint32_t group = lane >> 3, sub = lane & 7u;
     i = 0;
     do {
-        uint32_t cnt = 0;
-        for (; i < n_compounds; i++) {
+        uint32_t npairs = 0;                                    // warp-uniform
+#pragma unroll 1
+        for (; i < n_compounds && npairs <= RL_PAIR_CAP - 32; i++) {
             const float4 b4 = compounds[2 * i + 1];             // bounding sphere {c, r^2}
             bool keep = true;
             if (b4.w >= 0.0f) {
@@ -587,31 +621,73 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
                 const bool misses = fmaf(bb, bb, -(bc * dd)) < 0.0f;
                 keep = !(behind || misses);
             }
-            if (keep) {
-                cq[cnt * qstride] = (uint16_t)i;
-                cnt++;
+            const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            if (keep) pairs[npairs + __popc(mask & lanes_below)] = (uint16_t)((lane << 11) | i);
+            npairs += __popc(mask);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t pb = 0; pb < npairs; pb += 4) {
+            const uint32_t p = pb + group;
+            const bool valid = p < npairs;                      // uniform within a group of eight
+            const uint32_t pair = valid ? pairs[p] : 0u;
+            const uint32_t owner = wbase + (pair >> 11), body = pair & 2047u;
+            const float4 c4 = compounds[2 * body];
+            const uint32_t first_leaf = __float_as_uint(c4.x);
+            const uint32_t n_leaves = valid ? __float_as_uint(c4.y) : 0u;
+            const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1];
+            const float best_t = ray_tab[3 * owner + 2].z;
+            const float ox = -0.5f * ro.x, oy = -0.5f * ro.y, oz = -0.5f * ro.z;   // ro = -2 o, exactly
+            // slab_may_hit, one leaf per lane
+            float t_enter = 0.0f, t_exit = 3.0e38f;
+            bool outside_parallel = false;
+#pragma unroll 1
+            for (uint32_t k = first_leaf + sub; k < first_leaf + n_leaves; k += 8) {
+                const float4 n4 = leaves[2 * k], o4 = leaves[2 * k + 1];
+                const float dn = fmaf(n4.z, rd.z, fmaf(n4.y, rd.y, n4.x * rd.x));
+                const float s0 = fmaf(n4.z, oz - o4.z, fmaf(n4.y, oy - o4.y, n4.x * (ox - o4.x))) - RL_SLAB_INFLATE;
+                const float tk = __fdividef(-s0, dn);
+                if (dn < 0.0f) t_enter = fmaxf(t_enter, tk);
+                else if (dn > 0.0f) t_exit = fminf(t_exit, tk);
+                else if (s0 > 0.0f) outside_parallel = true;
             }
-            if (__any_sync(0xffffffffu, cnt == RL_COMPOUND_SLOTS)) { i++; break; }
-        }
-        // slab test for every queued body first, compacting the survivors in place, so that the
-        // lanes which need the exact evaluation run it in the same (few) iterations
-        uint32_t kept = 0;
-        for (uint32_t k = 0; k < cnt; k++) {
-            const uint32_t idx = cq[k * qstride];
-            const float4 c4 = compounds[2 * idx];
-            if (slab_may_hit(__float_as_uint(c4.x), __float_as_uint(c4.y), ray, best.t)) {
-                cq[kept * qstride] = (uint16_t)idx;
-                kept++;
+#pragma unroll
+            for (uint32_t sh = 1; sh < 8; sh <<= 1) {
+                t_enter = fmaxf(t_enter, __shfl_xor_sync(0xffffffffu, t_enter, sh));
+                t_exit = fminf(t_exit, __shfl_xor_sync(0xffffffffu, t_exit, sh));
+                outside_parallel |= (__shfl_xor_sync(0xffffffffu, (int)outside_parallel, sh) != 0);
+            }
+            const float start = t_enter * 0.9999f - 1.0e-3f;
+            const bool may_hit = !outside_parallel && !(t_exit < 0.0f) && !(start > t_exit) && !(start > best_t);
+            if (valid && sub == 0u && may_hit) {
+                const uint32_t slot = atomicAdd(&cq_cnt[owner], 1u);
+                if (slot < RL_COMPOUND_SLOTS) cq_base[slot * nthreads + owner] = (uint16_t)body;
             }
         }
-        for (uint32_t k = 0; k < kept; k++) {
-            const uint32_t idx = cq[k * qstride];
-            const float4 c4 = compounds[2 * idx];
-            uint32_t leaf;
-            const float t = compound_t(__float_as_uint(c4.x), __float_as_uint(c4.z), __float_as_uint(c4.w), ray, leaf);
-            if (t > 0.0f) consider(best, t, (int)compound_obj[idx], (RL_HIT_LEAF << 28) | leaf);
+        __syncwarp();
+        const uint32_t cnt = cq_cnt[tid];
+        if (cnt > RL_COMPOUND_SLOTS) {
+            // more candidate bodies than slots (pathological): evaluate every body exactly
+#pragma unroll 1
+            for (uint32_t k = 0; k < n_compounds; k++) {
+                const float4 c4 = compounds[2 * k];
+                uint32_t leaf;
+                const float t = compound_t(__float_as_uint(c4.x), __float_as_uint(c4.z), __float_as_uint(c4.w), ray, leaf);
+                if (t > 0.0f) consider(best, t, (int)compound_obj[k], (RL_HIT_LEAF << 28) | leaf);
+            }
+        } else {
+#pragma unroll 1
+            for (uint32_t k = 0; k < cnt; k++) {
+                const uint32_t idx = cq_base[k * nthreads + tid];
+                const float4 c4 = compounds[2 * idx];
+                uint32_t leaf;
+                const float t = compound_t(__float_as_uint(c4.x), __float_as_uint(c4.z), __float_as_uint(c4.w), ray, leaf);
+                if (t > 0.0f) consider(best, t, (int)compound_obj[idx], (RL_HIT_LEAF << 28) | leaf);
+            }
         }
-    } while (__any_sync(0xffffffffu, i < n_compounds));
+        cq_cnt[tid] = 0u;
+        __syncwarp();
+    } while (i < n_compounds);
     return best;
 }
 
