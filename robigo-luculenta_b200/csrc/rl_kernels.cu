@@ -157,10 +157,43 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
 __global__ void __launch_bounds__(256)
 splat_kernel(const float4 *__restrict__ records, uint64_t n, float4 *accum, int width, int height,
              float aspect) {
+    // Streaming read of the records with four independent 16-byte loads in flight per thread
+    // (L1 bypassed: every record is used once).  Only ~8 % of the photons of the built-in scene
+    // carry light, so splatting in place would run the splat code for two or three lanes of a
+    // warp at a time: contributing records are compacted into a per-warp staging buffer with a
+    // ballot and splatted 32 at a time with every lane busy.
+    __shared__ float4 stage[8][64];
+    float4 *mine = stage[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31u, lanes_below = (1u << lane) - 1u;
+    uint32_t count = 0;                                         // warp-uniform
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float4 ph = __ldg(records + i);  // {x, y, probability, wavelength}
-        if (ph.z != 0.0f) splat_photon(accum, width, height, aspect, ph.x, ph.y, ph.w, ph.z);
+    const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);  // warp-uniform trip count
+    for (uint64_t base = first; base < n; base += 4 * stride) {
+        float4 ph[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint64_t i = base + k * stride + lane;
+            ph[k] = i < n ? __ldcs(records + i) : make_float4(0.f, 0.f, 0.f, 0.f);  // {x, y, probability, wavelength}
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool lit = ph[k].z != 0.0f;                   // adding cie * 0 changes nothing (plot_unit.rs:80-83)
+            const uint32_t mask = __ballot_sync(0xffffffffu, lit);
+            if (lit) mine[count + __popc(mask & lanes_below)] = ph[k];
+            count += __popc(mask);
+            if (count >= 32) {
+                __syncwarp();
+                const float4 r = mine[count - 32 + lane];
+                __syncwarp();
+                count -= 32;
+                splat_photon(accum, width, height, aspect, r.x, r.y, r.w, r.z);
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < count) {
+        const float4 r = mine[lane];
+        splat_photon(accum, width, height, aspect, r.x, r.y, r.w, r.z);
     }
 }
 
