@@ -405,8 +405,10 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
         std::vector<uint32_t> idx(n);
         for (size_t k = 0; k < n; k++) idx[k] = (uint32_t)k;
         std::vector<Cluster> cl;
-        size_t leaf = (size_t)(0.38 * sqrt((double)n) + 0.5);
-        leaf = leaf < 4 ? 4 : (leaf > 32 ? 32 : leaf);
+        // eight lanes share one cluster in the cooperative member test: at least eight members
+        // per cluster, more for large scenes (balances the uniform cluster scan against it)
+        size_t leaf = (size_t)(0.45 * sqrt((double)n) + 0.5);
+        leaf = leaf < 8 ? 8 : (leaf > 32 ? 32 : leaf);
         if (leaf < (n + 999) / 1000) leaf = (n + 999) / 1000;   // pair records index clusters with 11 bits
         if (n) split_spheres(fl.spheres, idx, 0, n, leaf, cl);
         std::vector<float4> spheres(n), sphere_k(n);

@@ -704,7 +704,7 @@ __device__ __forceinline__ Surf surface_at(const Ray &ray, const Hit &hit) {
     if (type == RL_HIT_SPHERE) {                                       // geometry.rs:243-251
         const float4 sp = sm_vec(tb.spheres)[idx];
         s.normal = normalise_dev(s.position - mk(sp.x, sp.y, sp.z));
-        s.tangent = normalise_dev(cross(mk(0.0f, 1.0f, 0.0f), s.normal));
+        // the tangent (geometry.rs:250-251) is read by one material only: sphere_tangent() below
     } else if (type == RL_HIT_PLANE) {
         const float4 n4 = sm_vec(tb.planes)[2 * idx];
         const V3 n = mk(n4.x, n4.y, n4.z);
@@ -729,6 +729,13 @@ __device__ __forceinline__ Surf surface_at(const Ray &ray, const Hit &hit) {
     return s;
 }
 
+// Sphere::intersect's tangent, normalise(cross((0,1,0), normal)) (geometry.rs:250-251); every
+// other surface leaves it zero.  Computed where it is read (SoapBubbleMaterial, material.rs:297).
+__device__ __forceinline__ V3 sphere_tangent(const Hit &hit, const Surf &s) {
+    if ((hit.code >> 28) != RL_HIT_SPHERE) return mk(0.0f, 0.0f, 0.0f);
+    return normalise_dev(cross(mk(0.0f, 1.0f, 0.0f), s.normal));
+}
+
 // ---------------------------------------------------------------- materials
 // material.rs:38-58 with monte_carlo.rs:47-58
 __device__ __forceinline__ V3 diffuse_direction(const Ray &in, const Surf &s, Rng &rng) {
@@ -748,7 +755,7 @@ __device__ __forceinline__ float soap_clamp(float x) {                 // materi
 // Material::get_new_ray for the five reflective materials; returns the new
 // direction and the ray's probability (origin = intersection position).  The
 // three diffuse-based materials share one copy of get_diffuse_ray.
-__device__ __forceinline__ V3 material_bounce(float4 m, const Ray &in, const Surf &s, Rng &rng,
+__device__ __forceinline__ V3 material_bounce(float4 m, const Ray &in, const Hit &hit, const Surf &s, Rng &rng,
                                               float &probability) {
     const uint32_t kind = __float_as_uint(m.x);
     if (kind <= RL_MATERIAL_GLOSSY_MIRROR) {
@@ -787,7 +794,7 @@ __device__ __forceinline__ V3 material_bounce(float4 m, const Ray &in, const Sur
                                                                 : in.direction;
     const float phase_shift = (in.wavelength - 380.0f) / 200.0f * RL_PI;
     const float cos_phi = soap_clamp(dot(direction, s.normal));
-    const float cos_theta = soap_clamp(dot(direction, s.tangent));
+    const float cos_theta = soap_clamp(dot(direction, sphere_tangent(hit, s)));
     const float2 sc = sincos_call(phase_shift - spec_acos(cos_phi) * 3.0f - spec_acos(cos_theta) * 2.0f
                                   + RL_PI * 0.5f);
     probability = sc.y * 0.1f + 0.9f;

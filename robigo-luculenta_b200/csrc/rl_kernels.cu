@@ -93,7 +93,7 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
                 } else {
                     const Surf s = surface_at(ray, hit);
                     float probability;
-                    const V3 dir = material_bounce(m, ray, s, rng, probability);  // :104-107
+                    const V3 dir = material_bounce(m, ray, hit, s, rng, probability);  // :104-107
                     intensity = intensity * probability;
                     ray.direction = dir;
                     ray.origin = s.position + dir * 0.00001f;                      // :114
@@ -428,7 +428,8 @@ __global__ void debug_intersect_kernel(const DevScene sc, const rl_ray *rays, ui
         o.distance = 0.f;
         o.position = o.normal = o.tangent = rl_vec3{0.f, 0.f, 0.f};
         if (h.obj >= 0) {
-            const Surf s = surface_at(r, h);
+            Surf s = surface_at(r, h);
+            s.tangent = sphere_tangent(h, s);
             o.distance = h.t;
             o.position = rl_vec3{s.position.x, s.position.y, s.position.z};
             o.normal = rl_vec3{s.normal.x, s.normal.y, s.normal.z};
@@ -494,7 +495,7 @@ debug_cull_check_kernel(const DevScene sc, uint64_t seed, float aspect, uint64_t
         if (__float_as_uint(m.x) == RL_MATERIAL_BLACKBODY) continue;
         const Surf s = surface_at(ray, hit);
         float probability;
-        const V3 dir = material_bounce(m, ray, s, rng, probability);
+        const V3 dir = material_bounce(m, ray, hit, s, rng, probability);
         intensity = intensity * probability;
         ray.direction = dir;
         ray.origin = s.position + dir * 0.00001f;
