@@ -48,11 +48,14 @@ struct PrimTables {
 };
 
 #define RL_TABLES_VEC4 ((sizeof(PrimTables) + 15) / 16)
-#define RL_CAND_SLOTS 16       // queued sphere candidates per lane
-#define RL_COMPOUND_SLOTS 4    // queued compound candidates per lane
-#define RL_PAIR_CAP 512        // (lane, cluster) pairs per warp and round
-// scratch bytes per thread: ray table 48 + sphere queue 32 + compound queue 8 + pair list 32 + counters 8
-#define RL_SCRATCH_BYTES_PER_THREAD (48 + 2 * RL_CAND_SLOTS + 2 * RL_COMPOUND_SLOTS + 2 * RL_PAIR_CAP / 32 + 8)
+#define RL_CAND_SLOTS 8        // queued sphere candidates per lane
+#define RL_COMPOUND_SLOTS 4    // body results per lane, and body tasks per thread of the block list
+#define RL_PAIR_CAP 768        // (lane, cluster) or (lane, body) pairs per warp and round
+#define RL_BODIES_PER_ROUND (RL_PAIR_CAP / 32)
+// scratch bytes per thread: ray table 48, body results 8 per slot, block task list 4 per slot,
+// three counters 12, sphere queue 2 per slot, pair list 2 * RL_PAIR_CAP / 32
+#define RL_SCRATCH_BYTES_PER_THREAD \
+    (48 + 8 * RL_COMPOUND_SLOTS + 4 * RL_COMPOUND_SLOTS + 12 + 2 * RL_CAND_SLOTS + 2 * RL_PAIR_CAP / 32)
 
 __device__ __forceinline__ const PrimTables &tables() {
     return *reinterpret_cast<const PrimTables *>(rl_smem);
@@ -90,6 +93,14 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         t.sphere_cmax2 = sc.sphere_cmax2;
         t.cluster_rmax = sc.cluster_rmax;
         *reinterpret_cast<PrimTables *>(rl_smem) = t;
+    }
+    // zero the scratch counters (same layout as in intersect_scene)
+    {
+        float4 *ray_tab = rl_smem + base + sc.blob_vec4;
+        float2 *results = reinterpret_cast<float2 *>(ray_tab + 3 * blockDim.x);
+        uint32_t *counters = reinterpret_cast<uint32_t *>(results + RL_COMPOUND_SLOTS * blockDim.x)
+                             + RL_COMPOUND_SLOTS * blockDim.x;
+        for (uint32_t k = threadIdx.x; k < 3 * blockDim.x; k += blockDim.x) counters[k] = 0u;
     }
     __syncthreads();
 }
@@ -315,8 +326,12 @@ __device__ __forceinline__ float paraboloid_t(const float4 *p, const Ray &ray) {
 // op word: bits 0-1 kind (0 = leaf, 1 = compound); leaf: bits 8.. = leaf index
 // relative to the compound's first leaf; compound: lo = bits 8-15, mid = bits
 // 16-23, hi = bits 24-31 (children own leaves [lo, mid) and [mid, hi)).
-__device__ __forceinline__ float compound_t(uint32_t first_leaf, uint32_t first_op, uint32_t n_ops,
-                                            const Ray &ray, uint32_t &leaf_out) {
+static __device__ __forceinline__ float2 compound_call(uint32_t first_leaf, uint32_t first_op, uint32_t n_ops,
+                                                    float ox, float oy, float oz, float dx, float dy, float dz) {
+    Ray ray;
+    ray.origin = mk(ox, oy, oz);
+    ray.direction = mk(dx, dy, dz);
+    ray.wavelength = 0.0f;
     const PrimTables &tb = tables();
     const float4 *leaves = sm_vec(tb.leaves);
     const uint32_t *ops = sm_u32(tb.ops);
@@ -362,8 +377,16 @@ __device__ __forceinline__ float compound_t(uint32_t first_leaf, uint32_t first_
             t1 = t2; l1 = l2; t2 = t3; l2 = l3; t3 = t4; l3 = l4;
         }
     }
-    leaf_out = l0;
-    return t0;
+    return make_float2(t0, __uint_as_float(l0));
+}
+
+// One shared out-of-line copy of the interpreter (three call sites).
+__device__ __forceinline__ float compound_t(uint32_t first_leaf, uint32_t first_op, uint32_t n_ops,
+                                            const Ray &ray, uint32_t &leaf_out) {
+    const float2 r = compound_call(first_leaf, first_op, n_ops, ray.origin.x, ray.origin.y, ray.origin.z,
+                                   ray.direction.x, ray.direction.y, ray.direction.z);
+    leaf_out = __float_as_uint(r.y);
+    return r.x;
 }
 
 // Plane, Circle, top-level SpacePartitioning and Paraboloid objects: few per
@@ -491,24 +514,25 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
     const float thr = -7.6293945e-6f * scale;                                          // -2^-17 * scale
     const float bthr = -1.9073486e-6f * sqrtf((tb.sphere_cmax2 + oo) * dd) - 1.0e-30f;  // -2^-19 * ...
 
-    // Scratch views (per block): ray table [3 float4 per thread], sphere queues
-    // [slot][thread], compound queues [slot][thread], pair list [RL_PAIR_CAP per warp],
-    // queue counters [thread].
+    // Scratch views (per block): ray table [3 float4 per thread], body results [slot][thread]
+    // (distance, code), block task list [RL_COMPOUND_SLOTS per thread], counters [3][thread],
+    // sphere queues [slot][thread], pair list [RL_PAIR_CAP per warp].
     const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
     const uint32_t lane = tid & 31u, wbase = tid & ~31u;
     float4 *ray_tab = rl_smem + tb.scratch;
-    uint16_t *sq_base = reinterpret_cast<uint16_t *>(ray_tab + 3 * nthreads);
-    uint16_t *cq_base = sq_base + RL_CAND_SLOTS * nthreads;
-    uint16_t *pairs = cq_base + RL_COMPOUND_SLOTS * nthreads + (wbase >> 5) * RL_PAIR_CAP;
-    uint32_t *sq_cnt = reinterpret_cast<uint32_t *>(cq_base + RL_COMPOUND_SLOTS * nthreads
-                                                    + (nthreads >> 5) * RL_PAIR_CAP);
+    float2 *results = reinterpret_cast<float2 *>(ray_tab + 3 * nthreads);
+    uint32_t *btasks = reinterpret_cast<uint32_t *>(results + RL_COMPOUND_SLOTS * nthreads);
+    uint32_t *sq_cnt = btasks + RL_COMPOUND_SLOTS * nthreads;
+    uint16_t *sq_base = reinterpret_cast<uint16_t *>(sq_cnt + 3 * nthreads);
+    uint16_t *pairs = sq_base + RL_CAND_SLOTS * nthreads + (wbase >> 5) * RL_PAIR_CAP;
     // publish this lane's pre-test constants so that any lane of the warp can test a sphere for it
     ray_tab[3 * tid + 0] = make_float4(m2ox, m2oy, m2oz, oo);
     ray_tab[3 * tid + 1] = make_float4(d.x, d.y, d.z, ndo);
     ray_tab[3 * tid + 2] = make_float4(thr, bthr, 0.0f, 0.0f);
-    uint32_t *cq_cnt = sq_cnt + nthreads;
+    uint32_t *res_cnt = sq_cnt + nthreads;                      // results other threads computed for this one
+    uint32_t *bcount = sq_cnt + 2 * nthreads;                   // [0]: entries in the block task list
     sq_cnt[tid] = 0u;
-    cq_cnt[tid] = 0u;
+    res_cnt[tid] = 0u;
 
     // Two-level scan.  Level 1, uniform over the warp: the same pre-test against the bounding
     // sphere {m, R} of each cluster of spheres, with thresholds widened so that a cluster is
@@ -595,21 +619,26 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
 
     intersect_flat_surfaces(tb, ray, best);
 
-    // Compound bodies.  Bounding-sphere test in a uniform loop, kept (lane, body) pairs compacted
-    // with a ballot; then the slab test warp-cooperatively (eight lanes per pair, one leaf each,
-    // shuffle reduction of the interval); bodies that may be hit go to the owner's queue, and
-    // each lane runs the reference's recursion (compound_t) for its own queue.
+    // Compound bodies (block-wide; every thread of the block calls intersect_scene together).
+    //  1. bounding-sphere test in a uniform loop, kept (lane, body) pairs compacted with a ballot;
+    //  2. slab test warp-cooperatively: eight lanes per pair, one leaf each, shuffle reduction of
+    //     the interval; survivors are appended to ONE task list per block;
+    //  3. after a block barrier the threads take one task each -- the reference's recursion
+    //     (compound_t) for the owner's ray -- so the few rays of a block that really meet a body
+    //     are evaluated side by side in full warps instead of two or three lanes per warp;
+    //  4. after a second barrier every thread merges the results computed for its ray.
     ray_tab[3 * tid + 2].z = best.t;                            // nearest hit so far: bodies beyond it are skipped
     const float4 *compounds = sm_vec(tb.compounds);
     const float4 *leaves = sm_vec(tb.leaves);
     const uint32_t *compound_obj = sm_u32(tb.compound_obj);
     const uint32_t n_compounds = tb.n_compounds;
     const uint32_t group = lane >> 3, sub = lane & 7u;
-    i = 0;
-    do {
+    const uint32_t task_cap = RL_COMPOUND_SLOTS * nthreads;
+    for (uint32_t round = 0; round < n_compounds; round += RL_BODIES_PER_ROUND) {   // block-uniform trip count
+        const uint32_t round_end = min(round + RL_BODIES_PER_ROUND, n_compounds);
         uint32_t npairs = 0;                                    // warp-uniform
 #pragma unroll 1
-        for (; i < n_compounds && npairs <= RL_PAIR_CAP - 32; i++) {
+        for (uint32_t i = round; i < round_end; i++) {
             const float4 b4 = compounds[2 * i + 1];             // bounding sphere {c, r^2}
             bool keep = true;
             if (b4.w >= 0.0f) {
@@ -660,16 +689,37 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
             const float start = t_enter * 0.9999f - 1.0e-3f;
             const bool may_hit = !outside_parallel && !(t_exit < 0.0f) && !(start > t_exit) && !(start > best_t);
             if (valid && sub == 0u && may_hit) {
-                const uint32_t slot = atomicAdd(&cq_cnt[owner], 1u);
-                if (slot < RL_COMPOUND_SLOTS) cq_base[slot * nthreads + owner] = (uint16_t)body;
+                const uint32_t slot = atomicAdd(bcount, 1u);
+                if (slot < task_cap) btasks[slot] = (owner << 16) | body;
+                else atomicAdd(&res_cnt[owner], RL_COMPOUND_SLOTS + 1u);   // no room: the owner evaluates every body
             }
         }
-        __syncwarp();
-        const uint32_t cnt = cq_cnt[tid];
-        if (cnt > RL_COMPOUND_SLOTS) {
-            // more candidate bodies than slots (pathological): evaluate every body exactly
+        __syncthreads();
+        const uint32_t ntasks = min(*bcount, task_cap);
 #pragma unroll 1
-            for (uint32_t k = 0; k < n_compounds; k++) {
+        for (uint32_t q = tid; q < ntasks; q += nthreads) {
+            const uint32_t task = btasks[q];
+            const uint32_t owner = task >> 16, body = task & 0xffffu;
+            const float4 c4 = compounds[2 * body];
+            const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1];
+            Ray oray;                                           // the owner's ray, bit for bit
+            oray.origin = mk(-0.5f * ro.x, -0.5f * ro.y, -0.5f * ro.z);
+            oray.direction = mk(rd.x, rd.y, rd.z);
+            oray.wavelength = 0.0f;
+            uint32_t leaf;
+            const float t = compound_t(__float_as_uint(c4.x), __float_as_uint(c4.z), __float_as_uint(c4.w), oray, leaf);
+            if (t > 0.0f) {
+                const uint32_t slot = atomicAdd(&res_cnt[owner], 1u);
+                if (slot < RL_COMPOUND_SLOTS)
+                    results[slot * nthreads + owner] = make_float2(t, __uint_as_float((body << 16) | leaf));
+            }
+        }
+        __syncthreads();
+        const uint32_t nres = res_cnt[tid];
+        if (nres > RL_COMPOUND_SLOTS) {
+            // more hits or tasks than slots (pathological): evaluate every body of the round here
+#pragma unroll 1
+            for (uint32_t k = round; k < round_end; k++) {
                 const float4 c4 = compounds[2 * k];
                 uint32_t leaf;
                 const float t = compound_t(__float_as_uint(c4.x), __float_as_uint(c4.z), __float_as_uint(c4.w), ray, leaf);
@@ -677,17 +727,18 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
             }
         } else {
 #pragma unroll 1
-            for (uint32_t k = 0; k < cnt; k++) {
-                const uint32_t idx = cq_base[k * nthreads + tid];
-                const float4 c4 = compounds[2 * idx];
-                uint32_t leaf;
-                const float t = compound_t(__float_as_uint(c4.x), __float_as_uint(c4.z), __float_as_uint(c4.w), ray, leaf);
-                if (t > 0.0f) consider(best, t, (int)compound_obj[idx], (RL_HIT_LEAF << 28) | leaf);
+            for (uint32_t k = 0; k < nres; k++) {
+                const float2 r = results[k * nthreads + tid];
+                const uint32_t code = __float_as_uint(r.y);
+                consider(best, r.x, (int)compound_obj[code >> 16], (RL_HIT_LEAF << 28) | (code & 0xffffu));
             }
         }
-        cq_cnt[tid] = 0u;
-        __syncwarp();
-    } while (i < n_compounds);
+        res_cnt[tid] = 0u;
+        if (tid == 0) *bcount = 0u;
+        // the next use of the task list (next round or next call) is behind at least one more
+        // block barrier, which also orders these resets
+        if (round + RL_BODIES_PER_ROUND < n_compounds) __syncthreads();
+    }
     return best;
 }
 

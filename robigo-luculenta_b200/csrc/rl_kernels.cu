@@ -74,9 +74,9 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
             continue_chance = 1.0f;
             alive = true;
         }
-        if (!__any_sync(0xffffffffu, alive)) break;
-        // every lane takes part in the intersection (warp votes inside); idle lanes trace a
-        // ray that hits nothing
+        // every thread of the block takes part in the intersection (block barriers and warp
+        // votes inside); idle lanes trace a ray that hits nothing
+        if (!__syncthreads_or(alive)) break;
         const Hit hit = intersect_scene(alive ? ray : idle_ray());
         if (alive) {
             // trace_unit.rs:91-131
@@ -480,7 +480,7 @@ debug_cull_check_kernel(const DevScene sc, uint64_t seed, float aspect, uint64_t
             continue_chance = 1.0f;
             alive = true;
         }
-        if (!__any_sync(0xffffffffu, alive)) break;
+        if (!__syncthreads_or(alive)) break;
         const Ray r = alive ? ray : idle_ray();
         const Hit culled = intersect_scene(r);
         if (!alive) continue;
