@@ -48,14 +48,16 @@ struct PrimTables {
 };
 
 #define RL_TABLES_VEC4 ((sizeof(PrimTables) + 15) / 16)
+#define RL_CLUSTER_SLOTS 16    // candidate clusters a lane queues privately per round
 #define RL_CAND_SLOTS 8        // queued sphere candidates per lane
 #define RL_COMPOUND_SLOTS 4    // body results per lane, and body tasks per thread of the block list
 #define RL_PAIR_CAP 768        // (lane, cluster) or (lane, body) pairs per warp and round
 #define RL_BODIES_PER_ROUND (RL_PAIR_CAP / 32)
-// scratch bytes per thread: ray table 48, body results 8 per slot, block task list 4 per slot,
-// three counters 12, sphere queue 2 per slot, pair list 2 * RL_PAIR_CAP / 32
-#define RL_SCRATCH_BYTES_PER_THREAD \
-    (48 + 8 * RL_COMPOUND_SLOTS + 4 * RL_COMPOUND_SLOTS + 12 + 2 * RL_CAND_SLOTS + 2 * RL_PAIR_CAP / 32)
+// scratch bytes per thread: ray table 48; one 32-byte area that is the private cluster queue,
+// then the sphere queue (sphere phase), then the body results (body phase); block task list 4 per
+// slot; three counters 12; pair list 2 * RL_PAIR_CAP / 32
+#define RL_SCRATCH_BYTES_PER_THREAD (48 + 32 + 4 * RL_COMPOUND_SLOTS + 12 + 2 * RL_PAIR_CAP / 32)
+static_assert(2 * RL_CLUSTER_SLOTS <= 32 && 2 * RL_CAND_SLOTS <= 32 && 8 * RL_COMPOUND_SLOTS <= 32, "shared 32-byte area");
 
 __device__ __forceinline__ const PrimTables &tables() {
     return *reinterpret_cast<const PrimTables *>(rl_smem);
@@ -514,17 +516,19 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
     const float thr = -7.6293945e-6f * scale;                                          // -2^-17 * scale
     const float bthr = -1.9073486e-6f * sqrtf((tb.sphere_cmax2 + oo) * dd) - 1.0e-30f;  // -2^-19 * ...
 
-    // Scratch views (per block): ray table [3 float4 per thread], body results [slot][thread]
-    // (distance, code), block task list [RL_COMPOUND_SLOTS per thread], counters [3][thread],
-    // sphere queues [slot][thread], pair list [RL_PAIR_CAP per warp].
+    // Scratch views (per block): ray table [3 float4 per thread]; a 32-byte-per-thread area used
+    // in turn as private cluster queue [slot][thread], sphere queue [slot][thread] and body
+    // results [slot][thread] (distance, code); block task list [RL_COMPOUND_SLOTS per thread];
+    // counters [3][thread]; pair list [RL_PAIR_CAP per warp].
     const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
     const uint32_t lane = tid & 31u, wbase = tid & ~31u;
     float4 *ray_tab = rl_smem + tb.scratch;
     float2 *results = reinterpret_cast<float2 *>(ray_tab + 3 * nthreads);
+    uint16_t *lq_base = reinterpret_cast<uint16_t *>(results);  // same area, sphere phase
+    uint16_t *sq_base = lq_base;                                // same area, after the cluster queues are drained
     uint32_t *btasks = reinterpret_cast<uint32_t *>(results + RL_COMPOUND_SLOTS * nthreads);
     uint32_t *sq_cnt = btasks + RL_COMPOUND_SLOTS * nthreads;
-    uint16_t *sq_base = reinterpret_cast<uint16_t *>(sq_cnt + 3 * nthreads);
-    uint16_t *pairs = sq_base + RL_CAND_SLOTS * nthreads + (wbase >> 5) * RL_PAIR_CAP;
+    uint16_t *pairs = reinterpret_cast<uint16_t *>(sq_cnt + 3 * nthreads) + (wbase >> 5) * RL_PAIR_CAP;
     // publish this lane's pre-test constants so that any lane of the warp can test a sphere for it
     ray_tab[3 * tid + 0] = make_float4(m2ox, m2oy, m2oz, oo);
     ray_tab[3 * tid + 1] = make_float4(d.x, d.y, d.z, ndo);
@@ -552,10 +556,13 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
     const float thr_c = -(2.0f * tb.cluster_rmax * sqrtf(slack) + 2.0f * slack);
     const float bthr_c = bthr - sqrtf(dd) * tb.cluster_rmax;
     const uint32_t lanes_below = (1u << lane) - 1u;
+    uint16_t *myq = lq_base + tid;                              // private cluster queue, slot k at myq[k * nthreads]
     uint32_t i = 0;
     do {
-        uint32_t npairs = 0;                                    // warp-uniform
-        for (; i < n_clusters && npairs <= RL_PAIR_CAP - 128; i += 4) {
+        // each lane queues its candidate clusters privately (three predicated instructions per
+        // cluster), until any queue could overflow
+        uint32_t mine = 0;
+        for (; i < n_clusters; i += 4) {
 #pragma unroll
             for (uint32_t j = 0; j < 4; j++) {
                 // the table is padded with never-selected records to a multiple of four
@@ -563,12 +570,24 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
                 const float b = fmaf(d.x, s.x, fmaf(d.y, s.y, fmaf(d.z, s.z, ndo)));
                 const float c = fmaf(m2ox, s.x, fmaf(m2oy, s.y, fmaf(m2oz, s.z, s.w))) + oo;
                 const float disc = fmaf(b, b, -c);
-                const bool keep = disc >= thr_c && b >= bthr_c;
-                const uint32_t mask = __ballot_sync(0xffffffffu, keep);
-                if (keep) pairs[npairs + __popc(mask & lanes_below)] = (uint16_t)((lane << 11) | (i + j));
-                npairs += __popc(mask);
+                if (disc >= thr_c && b >= bthr_c) {
+                    myq[mine * nthreads] = (uint16_t)(i + j);
+                    mine++;
+                }
             }
+            if (__any_sync(0xffffffffu, mine > RL_CLUSTER_SLOTS - 4)) { i += 4; break; }
         }
+        // the queues are compacted into one (lane, cluster) list per warp: prefix sum of the counts
+        uint32_t incl = mine;
+#pragma unroll
+        for (uint32_t sh = 1; sh < 32; sh <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, sh);
+            if (lane >= sh) incl += v;
+        }
+        const uint32_t npairs = __shfl_sync(0xffffffffu, incl, 31);    // warp-uniform
+        uint16_t *dst = pairs + (incl - mine);
+#pragma unroll 1
+        for (uint32_t k = 0; k < mine; k++) dst[k] = (uint16_t)((lane << 11) | myq[k * nthreads]);
         __syncwarp();
         // Level 2, warp-cooperative: eight lanes take one (lane, cluster) pair and test one
         // member each with the owner's constants, so the work of lanes with many candidate
@@ -615,7 +634,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
         }
         sq_cnt[tid] = 0u;
         __syncwarp();
-    } while (i < n_clusters);
+    } while (__any_sync(0xffffffffu, i < n_clusters));
 
     intersect_flat_surfaces(tb, ray, best);
 
