@@ -444,39 +444,17 @@ __device__ __forceinline__ Hit intersect_scene_brute(const Ray &ray) {
 }
 
 // Conservative slab test of a convex body against the ray, with every
-// half-space moved outwards by RL_SLAB_INFLATE.  A hit the reference returns
-// lies on one leaf plane and passes the f32 containment test of every other
-// leaf (each sits in a sibling subtree on the way to the root, geometry.rs:
-// 386-388), so it is inside the inflated body up to rounding (~1e-5 at the
-// scene's coordinate magnitudes); if the inflated body's [enter, exit]
-// interval is empty, ends before the origin, or starts beyond the best hit so
-// far, the exact evaluation cannot change the result and is skipped.
+// half-space moved outwards by RL_SLAB_INFLATE (evaluated eight lanes per body
+// inside intersect_scene).  A hit the reference returns lies on one leaf plane
+// and passes the f32 containment test of every other leaf (each sits in a
+// sibling subtree on the way to the root, geometry.rs:386-388), so it is inside
+// the inflated body up to rounding (~1e-5 at the scene's coordinate
+// magnitudes); if the inflated body's [enter, exit] interval is empty, ends
+// before the origin, or starts beyond the best hit so far, the exact evaluation
+// cannot change the result and is skipped.
 #define RL_SLAB_INFLATE 2.0e-3f
-__device__ __forceinline__ bool slab_may_hit(uint32_t first_leaf, uint32_t n_leaves, const Ray &ray,
-                                             float best_t) {
-    const float4 *leaves = sm_vec(tables().leaves);
-    float t_enter = 0.0f, t_exit = 3.0e38f;
-    bool outside_parallel = false;
-#pragma unroll 1
-    for (uint32_t k = first_leaf; k < first_leaf + n_leaves; k++) {
-        const float4 n4 = leaves[2 * k], o4 = leaves[2 * k + 1];
-        const float dn = fmaf(n4.z, ray.direction.z, fmaf(n4.y, ray.direction.y, n4.x * ray.direction.x));
-        const float s0 = fmaf(n4.z, ray.origin.z - o4.z,
-                              fmaf(n4.y, ray.origin.y - o4.y, n4.x * (ray.origin.x - o4.x))) - RL_SLAB_INFLATE;
-        const float tk = __fdividef(-s0, dn);
-        if (dn < 0.0f) t_enter = fmaxf(t_enter, tk);
-        else if (dn > 0.0f) t_exit = fminf(t_exit, tk);
-        else if (s0 > 0.0f) outside_parallel = true;
-    }
-    if (outside_parallel) return false;
-    if (t_exit < 0.0f) return false;
-    if (t_enter * 0.9999f - 1.0e-3f > t_exit) return false;
-    if (t_enter * 0.9999f - 1.0e-3f > best_t) return false;
-    return true;
-}
 
-// Scene::intersect with result-preserving culls.  Must be called by all 32
-// lanes of a warp (lanes without a live path pass idle_ray()).
+// Scene::intersect with result-preserving culls.
 //
 // Spheres.  The reference accepts a sphere only if fl(b^2 - 4c) >= 0 and
 // t1 = (b - sqrt(disc)) / 2 > 0, which needs b > 0 (geometry.rs:204-240).
@@ -492,16 +470,24 @@ __device__ __forceinline__ bool slab_may_hit(uint32_t first_leaf, uint32_t n_lea
 // (sphere_t), so the hit distance, the winner and every later rounding are
 // unchanged; culling only removes spheres the reference rejects.
 //
-// Survivors are queued per lane in shared memory and evaluated after the
-// uniform scan, each lane walking its own queue, so the warp does not diverge
-// into the exact test once per sphere.  When any lane's queue could overflow,
-// a warp vote ends the scan early, every lane drains, and the scan resumes:
-// each piece of code exists once.
+// The spheres are grouped into clusters with bounding spheres (host side):
+// level 1 runs the pre-test against the cluster bounds in a uniform loop, each
+// lane queueing its candidate clusters privately; the queues are compacted into
+// one (lane, cluster) list per warp; level 2 tests the members eight lanes per
+// pair with the owner's constants from a shared ray table, so that lanes with
+// many candidates do not hold the warp back; level 3 is the exact sphere_t, each
+// lane for the few candidates queued for it.
 //
 // Compounds.  A bounded convex body can only be hit where the ray passes its
-// bounding sphere (inflated on the host well beyond rounding); survivors are
-// queued the same way, then the slab test above, then the reference's
-// recursion (compound_t).  Unbounded bodies carry r^2 < 0 and are always queued.
+// bounding sphere (inflated on the host well beyond rounding); survivors go
+// through the slab test above (eight lanes per body), and what remains is
+// evaluated by the reference's recursion (compound_t) from ONE task list per
+// block, so that the few rays of a block that really meet a body are processed
+// side by side in full warps.  Unbounded bodies carry r^2 < 0 and always pass
+// the bounding test.
+//
+// Must be called by every thread of the block together (block barriers and
+// warp votes inside); threads without a live path pass idle_ray().
 __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
     const PrimTables &tb = tables();
     Hit best;
@@ -686,7 +672,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
             const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1];
             const float best_t = ray_tab[3 * owner + 2].z;
             const float ox = -0.5f * ro.x, oy = -0.5f * ro.y, oz = -0.5f * ro.z;   // ro = -2 o, exactly
-            // slab_may_hit, one leaf per lane
+            // the slab test, one leaf per lane
             float t_enter = 0.0f, t_exit = 3.0e38f;
             bool outside_parallel = false;
 #pragma unroll 1
