@@ -224,7 +224,7 @@ class SceneBuilder:
             _check(lib().rl_scene_builder_builtin(self._h, builtin, param))
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib().rl_scene_builder_destroy(self._h)
             self._h = None
 
@@ -294,7 +294,7 @@ class Scene:
         _check(lib().rl_scene_create(C.byref(self.desc), C.byref(self._h)))
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib().rl_scene_destroy(self._h)
             self._h = None
 
@@ -331,7 +331,7 @@ class TraceUnit:
         self.mapped_photons = np.zeros(0, dtype=MAPPED_PHOTON)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib().rl_trace_unit_destroy(self._h)
             self._h = None
 
@@ -379,7 +379,7 @@ class PlotUnit:
         self._buffer = None
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib().rl_plot_unit_destroy(self._h)
             self._h = None
 
@@ -433,7 +433,7 @@ class GatherUnit:
         _check(lib().rl_gather_unit_create(width, height, path, C.byref(self._h)))
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib().rl_gather_unit_destroy(self._h)
             self._h = None
 
@@ -484,7 +484,7 @@ class TonemapUnit:
         self.rgb_buffer = np.zeros((height, width, 3), dtype=np.uint8)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib().rl_tonemap_unit_destroy(self._h)
             self._h = None
 

@@ -443,9 +443,13 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
             cluster_range.push_back(0u);
         }
     }
-    ds.off_spheres = append(blob, fl.spheres);          ds.n_spheres = (uint32_t)fl.spheres.size();
+    ds.n_spheres = (uint32_t)fl.spheres.size();
     ds.off_planes = append(blob, fl.planes);            ds.n_planes = (uint32_t)fl.planes.size() / 2;
     ds.off_paraboloids = append(blob, fl.paraboloids);  ds.n_paraboloids = (uint32_t)fl.paraboloids.size() / 3;
+    if (fl.leaves.size() / 2 > 65535u) {
+        delete sc;
+        return fail(RL_ERR_UNSUPPORTED, "more than 65535 half-spaces in compound surfaces");
+    }
     ds.off_leaves = append(blob, fl.leaves);            ds.n_leaves = (uint32_t)fl.leaves.size() / 2;
     ds.off_compounds = append(blob, fl.compounds);      ds.n_compounds = (uint32_t)fl.compounds.size() / 2;
     ds.off_ops = append(blob, fl.ops);                  ds.n_ops = (uint32_t)fl.ops.size();
@@ -454,10 +458,13 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     ds.off_cluster_range = append(blob, cluster_range);
     ds.sphere_cmax2 = (float)(fl.cmax2 * 1.0001);
     ds.cluster_rmax = (float)(cluster_rmax * 1.0001);
-    ds.off_sphere_obj = append(blob, fl.sphere_obj);
     ds.off_plane_obj = append(blob, fl.plane_obj);
     ds.off_paraboloid_obj = append(blob, fl.paraboloid_obj);
     ds.off_compound_obj = append(blob, fl.compound_obj);
+    if (blob.empty()) blob.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
+    ds.smem_vec4 = (uint32_t)blob.size();               // everything above goes to shared memory
+    ds.off_spheres = append(blob, fl.spheres);          // exact records: global memory only
+    ds.off_sphere_obj = append(blob, fl.sphere_obj);
     if (blob.empty()) blob.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
     ds.blob_vec4 = (uint32_t)blob.size();
     ds.n_objects = desc->n_objects;

@@ -5,7 +5,7 @@
 // one "primitive blob" of 16-byte records, grouped by primitive type so that a
 // warp walks each list with uniform (broadcast) shared-memory loads:
 //
-//   spheres      n_spheres     x float4   {cx, cy, cz, r^2}
+//   spheres      n_spheres     x float4   {cx, cy, cz, r^2}            (global memory only)
 //   sphere_k     n_spheres     x float4   {cx, cy, cz, |c|^2 - r^2}, record of the sphere pre-test
 //   clusters     n_clusters    x float4   {mx, my, mz, |m|^2 - R^2}, bounding sphere of a group of spheres
 //   cluster_range n_clusters   x uint32   first member | count << 16 (members are contiguous)
@@ -16,7 +16,8 @@
 //   ops          n_ops         x uint32   post-order program of the compound trees
 //   *_obj                      x uint32   object index of each sphere/plane/paraboloid/compound
 //
-// The kernel copies the blob into shared memory once per CTA.  Per-object
+// The kernel copies the blob -- all but the exact sphere records and their
+// object indices, which sit at its end -- into shared memory once per CTA.  Per-object
 // material records {kind, p0, p1, p2} stay in global memory (one read per
 // bounce, L1-resident).
 #pragma once
@@ -40,8 +41,12 @@ extern __shared__ float4 rl_smem[];
 // struct lives at the start of shared memory so that every device function
 // reaches the tables without carrying them in registers.
 struct PrimTables {
-    uint32_t spheres, sphere_k, clusters, cluster_range, planes, paraboloids, leaves, compounds, ops;
-    uint32_t sphere_obj, plane_obj, paraboloid_obj, compound_obj;
+    // exact sphere records and their object indices are read for the few candidates only:
+    // they stay in global memory (L1/L2-resident), which halves the shared memory of big scenes
+    const float4 *spheres;
+    const uint32_t *sphere_obj;
+    uint32_t sphere_k, clusters, cluster_range, planes, paraboloids, leaves, compounds, ops;
+    uint32_t plane_obj, paraboloid_obj, compound_obj;
     uint32_t scratch;         // per-block scratch behind the blob (see Scratch)
     uint32_t n_spheres, n_clusters, n_planes, n_paraboloids, n_compounds;
     float sphere_cmax2, cluster_rmax;
@@ -70,10 +75,11 @@ __device__ __forceinline__ const uint32_t *sm_u32(uint32_t off) {
 // Block-wide: copy the blob into shared memory and publish the table views.
 __device__ __forceinline__ void setup_tables(const DevScene &sc) {
     const uint32_t base = RL_TABLES_VEC4;
-    for (uint32_t i = threadIdx.x; i < sc.blob_vec4; i += blockDim.x) rl_smem[base + i] = sc.blob[i];
+    for (uint32_t i = threadIdx.x; i < sc.smem_vec4; i += blockDim.x) rl_smem[base + i] = sc.blob[i];
     if (threadIdx.x == 0) {
         PrimTables t;
-        t.spheres = base + sc.off_spheres;
+        t.spheres = sc.blob + sc.off_spheres;
+        t.sphere_obj = reinterpret_cast<const uint32_t *>(sc.blob + sc.off_sphere_obj);
         t.sphere_k = base + sc.off_sphere_k;
         t.clusters = base + sc.off_clusters;
         t.cluster_range = base + sc.off_cluster_range;
@@ -82,11 +88,10 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         t.leaves = base + sc.off_leaves;
         t.compounds = base + sc.off_compounds;
         t.ops = base + sc.off_ops;
-        t.sphere_obj = base + sc.off_sphere_obj;
         t.plane_obj = base + sc.off_plane_obj;
         t.paraboloid_obj = base + sc.off_paraboloid_obj;
         t.compound_obj = base + sc.off_compound_obj;
-        t.scratch = base + sc.blob_vec4;
+        t.scratch = base + sc.smem_vec4;
         t.n_spheres = sc.n_spheres;
         t.n_clusters = sc.n_clusters;
         t.n_planes = sc.n_planes;
@@ -98,7 +103,7 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
     }
     // zero the scratch counters (same layout as in intersect_scene)
     {
-        float4 *ray_tab = rl_smem + base + sc.blob_vec4;
+        float4 *ray_tab = rl_smem + base + sc.smem_vec4;
         float2 *results = reinterpret_cast<float2 *>(ray_tab + 3 * blockDim.x);
         uint32_t *counters = reinterpret_cast<uint32_t *>(results + RL_COMPOUND_SLOTS * blockDim.x)
                              + RL_COMPOUND_SLOTS * blockDim.x;
@@ -109,7 +114,7 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
 
 // Shared memory a tracing kernel needs with `threads` threads per block.
 inline size_t tracing_smem_bytes(const DevScene &sc, int threads) {
-    return (RL_TABLES_VEC4 + (size_t)sc.blob_vec4) * sizeof(float4)
+    return (RL_TABLES_VEC4 + (size_t)sc.smem_vec4) * sizeof(float4)
            + (size_t)RL_SCRATCH_BYTES_PER_THREAD * threads;
 }
 
@@ -425,11 +430,11 @@ __device__ __forceinline__ Hit intersect_scene_brute(const Ray &ray) {
     const PrimTables &tb = tables();
     Hit best;
     best.t = 1.0e12f; best.obj = -1; best.code = RL_HIT_NONE;
-    const float4 *spheres = sm_vec(tb.spheres);
-    const uint32_t *sphere_obj = sm_u32(tb.sphere_obj);
+    const float4 *spheres = tb.spheres;
+    const uint32_t *sphere_obj = tb.sphere_obj;
     for (uint32_t i = 0; i < tb.n_spheres; i++) {
-        const float t = sphere_t(spheres[i], ray);
-        if (t > 0.0f) consider(best, t, (int)sphere_obj[i], (RL_HIT_SPHERE << 28) | i);
+        const float t = sphere_t(__ldg(spheres + i), ray);
+        if (t > 0.0f) consider(best, t, (int)__ldg(sphere_obj + i), (RL_HIT_SPHERE << 28) | i);
     }
     intersect_flat_surfaces(tb, ray, best);
     const float4 *compounds = sm_vec(tb.compounds);
@@ -532,11 +537,11 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
     // is only unit to rounding), hence dist(line, m) <= R + sqrt(S/2) and
     // R^2 - dist(line, m)^2 >= -(2 R sqrt(S/2) + S/2); B_cluster >= B_i - |d| R.
     // Kept (lane, cluster) pairs are compacted with a ballot into one list per warp.
-    const float4 *spheres = sm_vec(tb.spheres);
+    const float4 *spheres = tb.spheres;
     const float4 *sphere_k = sm_vec(tb.sphere_k);
     const float4 *clusters = sm_vec(tb.clusters);
     const uint32_t *cluster_range = sm_u32(tb.cluster_range);
-    const uint32_t *sphere_obj = sm_u32(tb.sphere_obj);
+    const uint32_t *sphere_obj = tb.sphere_obj;
     const uint32_t n_clusters = tb.n_clusters;
     const float slack = -2.0f * thr + 2.0f * fabsf(dd - 1.0f) * (tb.sphere_cmax2 + oo);
     const float thr_c = -(2.0f * tb.cluster_rmax * sqrtf(slack) + 2.0f * slack);
@@ -607,15 +612,15 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
             // more candidates than slots (pathological): evaluate every sphere exactly
 #pragma unroll 1
             for (uint32_t k = 0; k < tb.n_spheres; k++) {
-                const float t = sphere_t(spheres[k], ray);
-                if (t > 0.0f) consider(best, t, (int)sphere_obj[k], (RL_HIT_SPHERE << 28) | k);
+                const float t = sphere_t(__ldg(spheres + k), ray);
+                if (t > 0.0f) consider(best, t, (int)__ldg(sphere_obj + k), (RL_HIT_SPHERE << 28) | k);
             }
         } else {
 #pragma unroll 1
             for (uint32_t k = 0; k < cnt; k++) {
                 const uint32_t idx = sq_base[k * nthreads + tid];
-                const float t = sphere_t(spheres[idx], ray);
-                if (t > 0.0f) consider(best, t, (int)sphere_obj[idx], (RL_HIT_SPHERE << 28) | idx);
+                const float t = sphere_t(__ldg(spheres + idx), ray);
+                if (t > 0.0f) consider(best, t, (int)__ldg(sphere_obj + idx), (RL_HIT_SPHERE << 28) | idx);
             }
         }
         sq_cnt[tid] = 0u;
@@ -758,7 +763,7 @@ __device__ __forceinline__ Surf surface_at(const Ray &ray, const Hit &hit) {
     s.tangent = mk(0.0f, 0.0f, 0.0f);
     const uint32_t type = hit.code >> 28, idx = hit.code & 0x0fffffffu;
     if (type == RL_HIT_SPHERE) {                                       // geometry.rs:243-251
-        const float4 sp = sm_vec(tb.spheres)[idx];
+        const float4 sp = __ldg(tb.spheres + idx);
         s.normal = normalise_dev(s.position - mk(sp.x, sp.y, sp.z));
         // the tangent (geometry.rs:250-251) is read by one material only: sphere_tangent() below
     } else if (type == RL_HIT_PLANE) {

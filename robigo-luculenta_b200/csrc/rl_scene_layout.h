@@ -20,6 +20,7 @@ struct DevCamera {
 struct DevScene {
     const float4 *blob;       // global copy of the primitive blob
     uint32_t blob_vec4;       // its size in float4 units
+    uint32_t smem_vec4;       // leading part that the kernels copy into shared memory
     // offsets into the blob, in float4 units
     uint32_t off_spheres, n_spheres;
     uint32_t off_planes, n_planes;
