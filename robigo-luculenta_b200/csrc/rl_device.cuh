@@ -136,19 +136,21 @@ static __device__ __noinline__ uint4 philox_block(uint32_t k0, uint32_t k1, uint
     return make_uint4(x0, x1, x2, x3);
 }
 
+// The stream a path draws from is named by (seed, photon id); the generator itself only
+// carries the position in that stream (block, words left) and the unread words, so that a
+// path's state stays small: the key is rebuilt from the launch arguments where a draw is made.
+struct RngKey { uint64_t seed, photon; };
+
 struct Rng {
-    uint32_t k0, k1, c0, c1, block;
+    uint32_t block;
     uint32_t b0, b1, b2, b3;
     uint32_t left;
 
-    __device__ __forceinline__ void init(uint64_t seed, uint64_t photon) {
-        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
-        c0 = (uint32_t)photon; c1 = (uint32_t)(photon >> 32);
-        block = 0; left = 0; b0 = b1 = b2 = b3 = 0;
-    }
-    __device__ __forceinline__ uint32_t next_u32() {
+    __device__ __forceinline__ void init() { block = 0; left = 0; b0 = b1 = b2 = b3 = 0; }
+    __device__ __forceinline__ uint32_t next_u32(const RngKey &k) {
         if (left == 0) {
-            const uint4 v = philox_block(k0, k1, c0, c1, block);
+            const uint4 v = philox_block((uint32_t)k.seed, (uint32_t)(k.seed >> 32), (uint32_t)k.photon,
+                                         (uint32_t)(k.photon >> 32), block);
             b0 = v.x; b1 = v.y; b2 = v.z; b3 = v.w;
             block++;
             left = 4;
@@ -163,16 +165,16 @@ struct Rng {
     // n 2^-24 by between half and one ulp, so the correctly rounded quotient is its successor:
     // one integer add on the bit pattern instead of an IEEE division (identity checked for
     // all 2^24 values by the CPU test suite, whose checker does the division).
-    __device__ __forceinline__ float unit() {
-        const uint32_t n = next_u32() >> 8;
+    __device__ __forceinline__ float unit(const RngKey &k) {
+        const uint32_t n = next_u32(k) >> 8;
         const float scaled = (float)n * 5.9604644775390625e-8f;
         return n == 0u ? 0.0f : __uint_as_float(__float_as_uint(scaled) + 1u);
     }
     // rand::random::<f32>() (monte_carlo.rs:37): in [0, 1)
-    __device__ __forceinline__ float half_open() { return (float)(next_u32() >> 8) * 5.9604644775390625e-8f; }
-    __device__ __forceinline__ float bi_unit() { return unit() * 2.0f - 1.0f; }             // monte_carlo.rs:31-33
-    __device__ __forceinline__ float longitude() { return half_open() * RL_PI * 2.0f; }     // monte_carlo.rs:36-38
-    __device__ __forceinline__ float wavelength() { return unit() * 400.0f + 380.0f; }      // monte_carlo.rs:41-43
+    __device__ __forceinline__ float half_open(const RngKey &k) { return (float)(next_u32(k) >> 8) * 5.9604644775390625e-8f; }
+    __device__ __forceinline__ float bi_unit(const RngKey &k) { return unit(k) * 2.0f - 1.0f; }             // monte_carlo.rs:31-33
+    __device__ __forceinline__ float longitude(const RngKey &k) { return half_open(k) * RL_PI * 2.0f; }     // monte_carlo.rs:36-38
+    __device__ __forceinline__ float wavelength(const RngKey &k) { return unit(k) * 400.0f + 380.0f; }      // monte_carlo.rs:41-43
 };
 
 // sin and cos through one shared out-of-line copy (eight call sites).
@@ -219,7 +221,7 @@ __device__ __forceinline__ Ray idle_ray() {
 // ------------------------------------------------------------------- camera
 // app.rs:327-357 (make_camera) in closed form, camera.rs:94-108 + :47-90.
 __device__ __forceinline__ Ray camera_ray(const DevCamera &cm, float x, float y, float wavelength, float t,
-                                          Rng &rng) {
+                                          Rng &rng, const RngKey &key) {
     V3 position;
     Quat orientation;
     float focal_distance;
@@ -237,8 +239,8 @@ __device__ __forceinline__ Ray camera_ray(const DevCamera &cm, float x, float y,
         orientation = rotation_dev(0.0f, 0.0f, -1.0f, phi + RL_PI) * rotation_dev(1.0f, 0.0f, 0.0f, -alpha);
         focal_distance = distance * cm.focal_factor;
     }
-    const float dof_angle = rng.longitude();
-    const float dof_radius = rng.unit() / cm.depth_of_field;
+    const float dof_angle = rng.longitude(key);
+    const float dof_radius = rng.unit(key) / cm.depth_of_field;
     const float d = (wavelength - 580.0f) / 200.0f;
     const float chromatic_zoom = 1.0f + d * cm.chromatic_abberation;
     const float2 fov = sincos_call(cm.field_of_view * 0.5f);
@@ -799,9 +801,9 @@ __device__ __forceinline__ V3 sphere_tangent(const Hit &hit, const Surf &s) {
 
 // ---------------------------------------------------------------- materials
 // material.rs:38-58 with monte_carlo.rs:47-58
-__device__ __forceinline__ V3 diffuse_direction(const Ray &in, const Surf &s, Rng &rng) {
-    const float phi = rng.longitude();
-    const float rq = rng.unit();
+__device__ __forceinline__ V3 diffuse_direction(const Ray &in, const Surf &s, Rng &rng, const RngKey &key) {
+    const float phi = rng.longitude(key);
+    const float rq = rng.unit(key);
     const float r = sqrtf(rq);
     const float2 sc = sincos_call(phi);
     const V3 hemi = mk(sc.y * r, sc.x * r, sqrtf(1.0f - rq));
@@ -817,7 +819,7 @@ __device__ __forceinline__ float soap_clamp(float x) {                 // materi
 // direction and the ray's probability (origin = intersection position).  The
 // three diffuse-based materials share one copy of get_diffuse_ray.
 __device__ __forceinline__ V3 material_bounce(float4 m, const Ray &in, const Hit &hit, const Surf &s, Rng &rng,
-                                              float &probability) {
+                                              const RngKey &key, float &probability) {
     const uint32_t kind = __float_as_uint(m.x);
     if (kind <= RL_MATERIAL_GLOSSY_MIRROR) {
         // grey (material.rs:122-130), coloured (:155-168), glossy (:185-196)
@@ -826,7 +828,7 @@ __device__ __forceinline__ V3 material_bounce(float4 m, const Ray &in, const Hit
             const float p = (m.z - in.wavelength) / m.w;
             probability = m.y * spec_exp(-0.5f * p * p);
         }
-        V3 dir = diffuse_direction(in, s, rng);
+        V3 dir = diffuse_direction(in, s, rng, key);
         if (kind == RL_MATERIAL_GLOSSY_MIRROR) {
             const V3 reflection = reflect(in.direction, s.normal);
             dir = normalise_dev(dir * m.y + reflection * (1.0f - m.y));
@@ -851,7 +853,7 @@ __device__ __forceinline__ V3 material_bounce(float4 m, const Ray &in, const Hit
     }
     // RL_MATERIAL_SOAP_BUBBLE                                            material.rs:267-306
     const float cos_alpha = dot(in.direction, s.normal);
-    const V3 direction = (rng.unit() - 0.3f > fabsf(cos_alpha)) ? reflect(in.direction, s.normal)
+    const V3 direction = (rng.unit(key) - 0.3f > fabsf(cos_alpha)) ? reflect(in.direction, s.normal)
                                                                 : in.direction;
     const float phase_shift = (in.wavelength - 380.0f) / 200.0f * RL_PI;
     const float cos_phi = soap_clamp(dot(direction, s.normal));

@@ -8,6 +8,7 @@
 //
 // Compile with -fmad=false: see rl_math.cuh.
 #include <atomic>
+#include <cstdlib>
 
 #include "rl_kernels.h"
 #include "rl_device.cuh"
@@ -46,30 +47,33 @@ __global__ void __launch_bounds__(RL_TRACE_THREADS, RL_TRACE_MIN_BLOCKS)
 trace_kernel(const DevScene sc, const TraceArgs a) {
     setup_tables(sc);
 
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint64_t next = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // photon indices within the launch fit 32 bits (launch_trace splits larger requests)
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t n_photons = (uint32_t)a.n_photons;
+    uint32_t next = blockIdx.x * blockDim.x + threadIdx.x;
 
     bool alive = false;
-    uint64_t cur = 0;
+    uint32_t cur = 0;
     Ray ray;
     ray.origin = mk(0.f, 0.f, 0.f); ray.direction = mk(0.f, 0.f, 0.f); ray.wavelength = 0.f;
     float sx = 0.f, sy = 0.f;
     float intensity = 1.0f, continue_chance = 1.0f;
     Rng rng;
-    rng.init(a.seed, 0);
+    rng.init();
     uint32_t rays = 0;
 
     for (;;) {
-        if (!alive && next < a.n_photons) {
+        if (!alive && next < n_photons) {
             // trace_unit.rs:151-158 and :136-145
             cur = next;
-            next += stride;
-            rng.init(a.seed, a.first_photon + cur);
-            const float wavelength = rng.wavelength();
-            sx = rng.bi_unit();
-            sy = rng.bi_unit() / a.aspect;
-            const float t = rng.unit();
-            ray = camera_ray(sc.camera, sx, sy, wavelength, t, rng);
+            next = next + stride < next ? 0xffffffffu : next + stride;   // saturate: 2^32 - 1 is never a valid index
+            const RngKey key = {a.seed, a.first_photon + cur};
+            rng.init();
+            const float wavelength = rng.wavelength(key);
+            sx = rng.bi_unit(key);
+            sy = rng.bi_unit(key) / a.aspect;
+            const float t = rng.unit(key);
+            ray = camera_ray(sc.camera, sx, sy, wavelength, t, rng, key);
             intensity = 1.0f;
             continue_chance = 1.0f;
             alive = true;
@@ -92,13 +96,14 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
                     done = true;
                 } else {
                     const Surf s = surface_at(ray, hit);
+                    const RngKey key = {a.seed, a.first_photon + cur};
                     float probability;
-                    const V3 dir = material_bounce(m, ray, hit, s, rng, probability);  // :104-107
+                    const V3 dir = material_bounce(m, ray, hit, s, rng, key, probability);  // :104-107
                     intensity = intensity * probability;
                     ray.direction = dir;
                     ray.origin = s.position + dir * 0.00001f;                      // :114
                     continue_chance = continue_chance * 0.96f;                    // :117
-                    if (rng.unit() * 0.85f
+                    if (rng.unit(key) * 0.85f
                         > continue_chance * (1.0f - spec_exp(intensity * -20.0f)))  // :122-125
                         done = true;
                 }
@@ -135,22 +140,37 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel, RL_TRACE_THREADS, smem);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
+    // carve out only the shared memory the resident CTAs need (+1 KB each that the system
+    // reserves); the rest of the 228 KB stays L1 for the material records, the exact sphere
+    // records and the few spilled registers
+    {
+        const char *env = getenv("RL_TRACE_CARVEOUT");
+        int pct = env ? atoi(env) : (int)((per_sm * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+        if (pct >= 0) cudaFuncSetAttribute(trace_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     uint64_t want = (p.n_photons + RL_TRACE_THREADS - 1) / RL_TRACE_THREADS;
     uint64_t full = (uint64_t)sm_count * per_sm;
     unsigned grid = (unsigned)(want < full ? want : full);
-    TraceArgs a;
-    a.seed = p.seed;
-    a.first_photon = p.first_photon;
-    a.n_photons = p.n_photons;
-    a.width = (int)p.width;
-    a.height = (int)p.height;
-    a.aspect = (float)p.width / (float)p.height;  // trace_unit.rs:73, plot_unit.rs:49
-    a.records = p.records;
-    a.accum = p.accum;
-    a.ray_counter = p.ray_counter;
-    trace_kernel<<<grid, RL_TRACE_THREADS, smem, st>>>(sc, a);
-    g_launches++;
-    return cudaGetLastError();
+    // the kernel indexes photons of a launch with 32 bits: larger requests take several launches
+    const uint64_t chunk = 1ull << 31;
+    for (uint64_t done = 0; done < p.n_photons; done += chunk) {
+        TraceArgs a;
+        a.seed = p.seed;
+        a.first_photon = p.first_photon + done;
+        a.n_photons = p.n_photons - done < chunk ? p.n_photons - done : chunk;
+        a.width = (int)p.width;
+        a.height = (int)p.height;
+        a.aspect = (float)p.width / (float)p.height;  // trace_unit.rs:73, plot_unit.rs:49
+        a.records = p.records ? p.records + done : nullptr;
+        a.accum = p.accum;
+        a.ray_counter = p.ray_counter;
+        trace_kernel<<<grid, RL_TRACE_THREADS, smem, st>>>(sc, a);
+        g_launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 // ------------------------------------------------------------------ K2 splat
@@ -465,17 +485,19 @@ debug_cull_check_kernel(const DevScene sc, uint64_t seed, float aspect, uint64_t
     bool alive = false;
     Ray ray = idle_ray();
     Rng rng;
-    rng.init(seed, 0);
+    rng.init();
+    RngKey key = {seed, first};
     float intensity = 1.0f, continue_chance = 1.0f;
     for (;;) {
         if (!alive && next < n) {
-            rng.init(seed, first + next);
+            key.photon = first + next;
+            rng.init();
             next += stride;
-            const float wavelength = rng.wavelength();
-            const float x = rng.bi_unit();
-            const float y = rng.bi_unit() / aspect;
-            const float t = rng.unit();
-            ray = camera_ray(sc.camera, x, y, wavelength, t, rng);
+            const float wavelength = rng.wavelength(key);
+            const float x = rng.bi_unit(key);
+            const float y = rng.bi_unit(key) / aspect;
+            const float t = rng.unit(key);
+            ray = camera_ray(sc.camera, x, y, wavelength, t, rng, key);
             intensity = 1.0f;
             continue_chance = 1.0f;
             alive = true;
@@ -495,12 +517,12 @@ debug_cull_check_kernel(const DevScene sc, uint64_t seed, float aspect, uint64_t
         if (__float_as_uint(m.x) == RL_MATERIAL_BLACKBODY) continue;
         const Surf s = surface_at(ray, hit);
         float probability;
-        const V3 dir = material_bounce(m, ray, hit, s, rng, probability);
+        const V3 dir = material_bounce(m, ray, hit, s, rng, key, probability);
         intensity = intensity * probability;
         ray.direction = dir;
         ray.origin = s.position + dir * 0.00001f;
         continue_chance = continue_chance * 0.96f;
-        if (rng.unit() * 0.85f > continue_chance * (1.0f - spec_exp(intensity * -20.0f))) continue;
+        if (rng.unit(key) * 0.85f > continue_chance * (1.0f - spec_exp(intensity * -20.0f))) continue;
         alive = true;
     }
     atomicAdd(rays_out, rays);
@@ -575,12 +597,13 @@ __global__ void debug_camera_kernel(const DevScene sc, uint64_t seed, float aspe
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         Rng rng;
-        rng.init(seed, first + i);
-        const float wavelength = rng.wavelength();
-        const float x = rng.bi_unit();
-        const float y = rng.bi_unit() / aspect;
-        const float t = rng.unit();
-        const Ray r = camera_ray(sc.camera, x, y, wavelength, t, rng);
+        rng.init();
+        const RngKey key = {seed, first + i};
+        const float wavelength = rng.wavelength(key);
+        const float x = rng.bi_unit(key);
+        const float y = rng.bi_unit(key) / aspect;
+        const float t = rng.unit(key);
+        const Ray r = camera_ray(sc.camera, x, y, wavelength, t, rng, key);
         rl_ray o;
         o.origin = rl_vec3{r.origin.x, r.origin.y, r.origin.z};
         o.direction = rl_vec3{r.direction.x, r.direction.y, r.direction.z};
