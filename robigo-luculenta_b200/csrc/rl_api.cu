@@ -468,7 +468,7 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     if (blob.empty()) blob.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
     ds.blob_vec4 = (uint32_t)blob.size();
     ds.n_objects = desc->n_objects;
-    sc->smem = trace_smem_bytes(ds, 256);
+    sc->smem = trace_smem_bytes(ds, 128);   // the smallest CTA the kernels are launched with
     if (sc->smem > sc->dev.max_smem) {
         delete sc;
         return fail(RL_ERR_UNSUPPORTED, "scene primitive tables exceed shared memory per CTA");

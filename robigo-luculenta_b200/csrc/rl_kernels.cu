@@ -20,10 +20,10 @@ uint64_t kernel_launches() { return g_launches.load(); }
 void kernel_launches_reset() { g_launches.store(0); }
 
 #ifndef RL_TRACE_THREADS
-#define RL_TRACE_THREADS 256
+#define RL_TRACE_THREADS 768
 #endif
 #ifndef RL_TRACE_MIN_BLOCKS
-#define RL_TRACE_MIN_BLOCKS 3
+#define RL_TRACE_MIN_BLOCKS 1
 #endif
 
 // ------------------------------------------------------------------ K1 trace
@@ -132,12 +132,19 @@ size_t trace_smem_bytes(const DevScene &sc, int threads) { return tracing_smem_b
 
 cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count, cudaStream_t st) {
     if (p.n_photons == 0) return cudaSuccess;
-    const size_t smem = trace_smem_bytes(sc, RL_TRACE_THREADS);
-    cudaError_t err = cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem);
+    // the largest CTA (up to RL_TRACE_THREADS) whose tables + scratch fit the shared memory of an SM:
+    // big CTAs fill the per-CTA task list of the body evaluation best
+    int dev = 0, max_smem = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err == cudaSuccess) err = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (err != cudaSuccess) return err;
+    int threads = RL_TRACE_THREADS;
+    while (threads > 128 && trace_smem_bytes(sc, threads) > (size_t)max_smem) threads -= 128;
+    const size_t smem = trace_smem_bytes(sc, threads);
+    err = cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int per_sm = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel, RL_TRACE_THREADS, smem);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel, threads, smem);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
     // carve out only the shared memory the resident CTAs need (+1 KB each that the system
@@ -149,7 +156,7 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
         if (pct > 100) pct = 100;
         if (pct >= 0) cudaFuncSetAttribute(trace_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     }
-    uint64_t want = (p.n_photons + RL_TRACE_THREADS - 1) / RL_TRACE_THREADS;
+    uint64_t want = (p.n_photons + threads - 1) / threads;
     uint64_t full = (uint64_t)sm_count * per_sm;
     unsigned grid = (unsigned)(want < full ? want : full);
     // the kernel indexes photons of a launch with 32 bits: larger requests take several launches
@@ -165,7 +172,7 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
         a.records = p.records ? p.records + done : nullptr;
         a.accum = p.accum;
         a.ray_counter = p.ray_counter;
-        trace_kernel<<<grid, RL_TRACE_THREADS, smem, st>>>(sc, a);
+        trace_kernel<<<grid, threads, smem, st>>>(sc, a);
         g_launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
