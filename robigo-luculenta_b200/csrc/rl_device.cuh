@@ -50,9 +50,12 @@ struct PrimTables {
     uint32_t scratch;         // per-block scratch behind the blob (see Scratch)
     uint32_t n_spheres, n_clusters, n_planes, n_paraboloids, n_compounds;
     float sphere_cmax2, cluster_rmax;
+    uint32_t class_count[16];  // [parity][class] path counts of the block-wide path sort
 };
 
 #define RL_TABLES_VEC4 ((sizeof(PrimTables) + 15) / 16)
+#define RL_PATH_CLASSES 6      // next actions a path can have (block-wide path sort)
+#define RL_PATH_WORDS 20       // words of path state that move in the sort
 #define RL_CLUSTER_SLOTS 16    // candidate clusters a lane queues privately per round
 #define RL_CAND_SLOTS 8        // queued sphere candidates per lane
 #define RL_COMPOUND_SLOTS 4    // body results per lane, and body tasks per thread of the block list
@@ -62,6 +65,9 @@ struct PrimTables {
 // then the sphere queue (sphere phase), then the body results (body phase); block task list 4 per
 // slot; three counters 12; pair list 2 * RL_PAIR_CAP / 32
 #define RL_SCRATCH_BYTES_PER_THREAD (48 + 32 + 4 * RL_COMPOUND_SLOTS + 12 + 2 * RL_PAIR_CAP / 32)
+// the path sort of the trace kernel adds its own area behind the scratch: staging of the path
+// state and the permutation table
+#define RL_SORT_BYTES_PER_THREAD (4 * RL_PATH_WORDS + 2 * RL_PATH_CLASSES)
 static_assert(2 * RL_CLUSTER_SLOTS <= 32 && 2 * RL_CAND_SLOTS <= 32 && 8 * RL_COMPOUND_SLOTS <= 32, "shared 32-byte area");
 
 __device__ __forceinline__ const PrimTables &tables() {
@@ -108,6 +114,7 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         uint32_t *counters = reinterpret_cast<uint32_t *>(results + RL_COMPOUND_SLOTS * blockDim.x)
                              + RL_COMPOUND_SLOTS * blockDim.x;
         for (uint32_t k = threadIdx.x; k < 3 * blockDim.x; k += blockDim.x) counters[k] = 0u;
+        if (threadIdx.x < 16) const_cast<uint32_t *>(tables().class_count)[threadIdx.x] = 0u;
     }
     __syncthreads();
 }
@@ -216,6 +223,50 @@ __device__ __forceinline__ Ray idle_ray() {
     r.direction = mk(1.0f, 0.0f, 0.0f);
     r.wavelength = 0.0f;
     return r;
+}
+
+// --------------------------------------------------------- path sort by class
+// Optional (RL_SORT_PATHS): per bounce, the paths of a block are re-dealt to its
+// threads in the order of what happens to them next, so that a warp executes
+// one or two of the material code paths instead of all of them.  A path is just
+// its state: 20 words move through shared memory.  One barrier per sort: every
+// warp reserves a run in each class with one shared-memory atomic per class, the
+// threads publish "the path parked by thread tid is number k of class c" in a
+// permutation table; after the barrier thread j works out from the six class
+// totals which (class, k) it serves and fetches that path.  The counters are
+// double-buffered by iteration parity and zeroed one iteration ahead.
+#define RL_CLASS_MISS 0u
+#define RL_CLASS_EMITTER 1u
+#define RL_CLASS_DIFFUSE 2u
+#define RL_CLASS_GLASS 3u
+#define RL_CLASS_SOAP 4u
+#define RL_CLASS_IDLE 5u
+
+__device__ __forceinline__ void path_sort_publish(uint32_t cls, uint32_t parity, uint16_t *perm) {
+    uint32_t *count = const_cast<uint32_t *>(tables().class_count) + 8 * parity;
+    const uint32_t lane = threadIdx.x & 31u, lanes_below = (1u << lane) - 1u;
+    uint32_t rank = 0, run = 0;
+#pragma unroll
+    for (uint32_t c = 0; c < RL_PATH_CLASSES; c++) {
+        const uint32_t mask = __ballot_sync(0xffffffffu, cls == c);
+        if (lane == c && mask) run = atomicAdd(&count[c], (uint32_t)__popc(mask));
+        if (cls == c) rank = __popc(mask & lanes_below);
+    }
+    run = __shfl_sync(0xffffffffu, run, cls);
+    perm[cls * blockDim.x + run + rank] = (uint16_t)threadIdx.x;
+}
+// After the barrier: the thread whose parked path this thread takes over, and that path's class.
+__device__ __forceinline__ uint32_t path_sort_fetch(uint32_t parity, const uint16_t *perm, uint32_t &cls_out) {
+    uint32_t *count = const_cast<uint32_t *>(tables().class_count);
+    uint32_t k = threadIdx.x, cls = 0;
+#pragma unroll
+    for (uint32_t c = 0; c < RL_PATH_CLASSES - 1; c++) {
+        const uint32_t n = count[8 * parity + c];
+        if (cls == c && k >= n) { k -= n; cls = c + 1; }
+    }
+    if (threadIdx.x < RL_PATH_CLASSES) count[8 * (parity ^ 1u) + threadIdx.x] = 0u;   // for the next iteration
+    cls_out = cls;
+    return perm[cls * blockDim.x + k];
 }
 
 // ------------------------------------------------------------------- camera

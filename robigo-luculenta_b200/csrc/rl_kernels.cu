@@ -22,6 +22,9 @@ void kernel_launches_reset() { g_launches.store(0); }
 #ifndef RL_TRACE_THREADS
 #define RL_TRACE_THREADS 768
 #endif
+#ifndef RL_SORT_PATHS
+#define RL_SORT_PATHS 0          // 1: re-deal the paths of a CTA by next action every bounce (see rl_device.cuh)
+#endif
 #ifndef RL_TRACE_MIN_BLOCKS
 #define RL_TRACE_MIN_BLOCKS 1
 #endif
@@ -61,6 +64,13 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
     Rng rng;
     rng.init();
     uint32_t rays = 0;
+#if RL_SORT_PATHS
+    // staging of the path exchange and the permutation table, behind the intersection scratch
+    uint32_t *stage = reinterpret_cast<uint32_t *>(
+        reinterpret_cast<char *>(rl_smem + tables().scratch) + (size_t)RL_SCRATCH_BYTES_PER_THREAD * blockDim.x);
+    uint16_t *perm = reinterpret_cast<uint16_t *>(stage + RL_PATH_WORDS * blockDim.x);
+    uint32_t parity = 0;
+#endif
 
     for (;;) {
         if (!alive && next < n_photons) {
@@ -81,10 +91,49 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
         // every thread of the block takes part in the intersection (block barriers and warp
         // votes inside); idle lanes trace a ray that hits nothing
         if (!__syncthreads_or(alive)) break;
-        const Hit hit = intersect_scene(alive ? ray : idle_ray());
+        Hit hit = intersect_scene(alive ? ray : idle_ray());
+        if (alive) rays++;                                              // Scene::intersect calls (scene.rs:39)
+#if RL_SORT_PATHS
+        {
+            uint32_t cls = RL_CLASS_IDLE;
+            if (alive) {
+                cls = RL_CLASS_MISS;
+                if (hit.obj >= 0) {
+                    const uint32_t kind = __float_as_uint(__ldg(sc.materials + hit.obj).x);
+                    cls = kind == RL_MATERIAL_BLACKBODY ? RL_CLASS_EMITTER
+                          : (kind <= RL_MATERIAL_GLOSSY_MIRROR ? RL_CLASS_DIFFUSE
+                             : (kind == RL_MATERIAL_SF10_GLASS ? RL_CLASS_GLASS : RL_CLASS_SOAP));
+                }
+            }
+            path_sort_publish(cls, parity, perm);
+            const uint32_t T = blockDim.x;
+            uint32_t *p = stage + threadIdx.x;
+            p[0 * T] = __float_as_uint(ray.origin.x); p[1 * T] = __float_as_uint(ray.origin.y);
+            p[2 * T] = __float_as_uint(ray.origin.z); p[3 * T] = __float_as_uint(ray.direction.x);
+            p[4 * T] = __float_as_uint(ray.direction.y); p[5 * T] = __float_as_uint(ray.direction.z);
+            p[6 * T] = __float_as_uint(ray.wavelength); p[7 * T] = __float_as_uint(intensity);
+            p[8 * T] = __float_as_uint(continue_chance); p[9 * T] = __float_as_uint(sx);
+            p[10 * T] = __float_as_uint(sy); p[11 * T] = cur;
+            p[12 * T] = (rng.block << 3) | rng.left;
+            p[13 * T] = rng.b0; p[14 * T] = rng.b1; p[15 * T] = rng.b2;
+            p[16 * T] = __float_as_uint(hit.t); p[17 * T] = (uint32_t)hit.obj; p[18 * T] = hit.code;
+            __syncthreads();
+            p = stage + path_sort_fetch(parity, perm, cls);
+            parity ^= 1u;
+            ray.origin = mk(__uint_as_float(p[0 * T]), __uint_as_float(p[1 * T]), __uint_as_float(p[2 * T]));
+            ray.direction = mk(__uint_as_float(p[3 * T]), __uint_as_float(p[4 * T]), __uint_as_float(p[5 * T]));
+            ray.wavelength = __uint_as_float(p[6 * T]); intensity = __uint_as_float(p[7 * T]);
+            continue_chance = __uint_as_float(p[8 * T]); sx = __uint_as_float(p[9 * T]);
+            sy = __uint_as_float(p[10 * T]); cur = p[11 * T];
+            rng.block = p[12 * T] >> 3; rng.left = p[12 * T] & 7u;
+            rng.b0 = p[13 * T]; rng.b1 = p[14 * T]; rng.b2 = p[15 * T];
+            hit.t = __uint_as_float(p[16 * T]); hit.obj = (int)p[17 * T]; hit.code = p[18 * T];
+            alive = cls != RL_CLASS_IDLE;
+            // the staging area is written again only behind the next loop-top barrier
+        }
+#endif
         if (alive) {
             // trace_unit.rs:91-131
-            rays++;
             bool done = false;
             float result = 0.0f;
             if (hit.obj < 0) {
@@ -129,6 +178,10 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
 }
 
 size_t trace_smem_bytes(const DevScene &sc, int threads) { return tracing_smem_bytes(sc, threads); }
+// the trace kernel proper: plus the path-sort area when enabled
+static size_t trace_kernel_smem_bytes(const DevScene &sc, int threads) {
+    return tracing_smem_bytes(sc, threads) + (RL_SORT_PATHS ? (size_t)RL_SORT_BYTES_PER_THREAD * threads : 0);
+}
 
 cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count, cudaStream_t st) {
     if (p.n_photons == 0) return cudaSuccess;
@@ -139,8 +192,8 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (err != cudaSuccess) return err;
     int threads = RL_TRACE_THREADS;
-    while (threads > 128 && trace_smem_bytes(sc, threads) > (size_t)max_smem) threads -= 128;
-    const size_t smem = trace_smem_bytes(sc, threads);
+    while (threads > 128 && trace_kernel_smem_bytes(sc, threads) > (size_t)max_smem) threads -= 128;
+    const size_t smem = trace_kernel_smem_bytes(sc, threads);
     err = cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int per_sm = 0;
