@@ -334,6 +334,7 @@ def main():
         total = 0.0
         for _ in range(reps):
             flush.fill_(1)
+            flush_sum = flush[: 192 << 20].sum()      # read pass: leaves L2 full of clean lines
             a.record(); fn(); b.record()
             torch.cuda.synchronize()
             total += a.elapsed_time(b)

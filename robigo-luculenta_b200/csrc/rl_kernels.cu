@@ -234,10 +234,13 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
 }
 
 // ------------------------------------------------------------------ K2 splat
+#ifndef RL_SPLAT_LOADS
+#define RL_SPLAT_LOADS 8
+#endif
 __global__ void __launch_bounds__(256)
 splat_kernel(const float4 *__restrict__ records, uint64_t n, float4 *accum, int width, int height,
              float aspect) {
-    // Streaming read of the records with four independent 16-byte loads in flight per thread
+    // Streaming read of the records with RL_SPLAT_LOADS independent 16-byte loads in flight per thread
     // (L1 bypassed: every record is used once).  Only ~8 % of the photons of the built-in scene
     // carry light, so splatting in place would run the splat code for two or three lanes of a
     // warp at a time: contributing records are compacted into a per-warp staging buffer with a
@@ -248,15 +251,15 @@ splat_kernel(const float4 *__restrict__ records, uint64_t n, float4 *accum, int 
     uint32_t count = 0;                                         // warp-uniform
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);  // warp-uniform trip count
-    for (uint64_t base = first; base < n; base += 4 * stride) {
-        float4 ph[4];
+    for (uint64_t base = first; base < n; base += RL_SPLAT_LOADS * stride) {
+        float4 ph[RL_SPLAT_LOADS];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < RL_SPLAT_LOADS; k++) {
             const uint64_t i = base + k * stride + lane;
             ph[k] = i < n ? __ldcs(records + i) : make_float4(0.f, 0.f, 0.f, 0.f);  // {x, y, probability, wavelength}
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < RL_SPLAT_LOADS; k++) {
             const bool lit = ph[k].z != 0.0f;                   // adding cie * 0 changes nothing (plot_unit.rs:80-83)
             const uint32_t mask = __ballot_sync(0xffffffffu, lit);
             if (lit) mine[count + __popc(mask & lanes_below)] = ph[k];
