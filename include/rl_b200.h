@@ -210,6 +210,18 @@ int rl_trace_unit_sync(rl_trace_unit *unit);
 /* Reset the process-wide batch counter used by rl_trace_unit_render. */
 void rl_trace_batch_counter_reset(uint64_t next_batch);
 
+/* Host buffers of the units.  The reference's units own plain `Vec`s
+ * (`mapped_photons`, trace_unit.rs:56,75-77; `tristimulus_buffer`,
+ * plot_unit.rs:34,47 and gather_unit.rs:26,40) that the host passes around as
+ * slices (app.rs:139,146,157).  They are allocated once per unit and never
+ * resized, so the shim page-locks them once after allocation: copies to and
+ * from a registered buffer are true DMA transfers that overlap the kernels of
+ * the other units instead of staged, blocking copies through pageable memory.
+ * Registration is optional (an unregistered buffer works, slower) and
+ * idempotent per address; unregister before the Vec is dropped. */
+int rl_host_register(void *ptr, size_t bytes);
+int rl_host_unregister(void *ptr);
+
 /* ------------------------------------------------------------ PlotUnit   */
 
 /* PlotUnit::new (plot_unit.rs:43-53) */
@@ -259,8 +271,19 @@ int rl_gather_unit_accumulate_plot(rl_gather_unit *unit, rl_plot_unit *plot, int
 int rl_gather_unit_accumulate_device(rl_gather_unit *unit, const void *const *xyzw_buffers,
                                      uint32_t n_buffers);
 /* GatherUnit::save (gather_unit.rs:68-78): accumulator then compensation,
- * 12 raw bytes per pixel each, no header -> 24*w*h bytes. */
+ * 12 raw bytes per pixel each, no header -> 24*w*h bytes.
+ * The host calls this after every gather (app.rs:151).  The call snapshots
+ * the device buffers into page-locked host memory and returns; a writer
+ * thread of the unit puts the snapshot into `path.tmp` and renames it over
+ * `path`, so the file always holds one complete snapshot (the reference
+ * truncates and rewrites in place).  A newer snapshot replaces one that has
+ * not been written yet.  The first save to a path is written before the call
+ * returns, so an unwritable path fails here ("failed to open file",
+ * gather_unit.rs:69); a later write failure is returned by the next save or
+ * flush.  rl_gather_unit_flush waits for the file to be current;
+ * rl_gather_unit_load and rl_gather_unit_destroy flush first. */
 int rl_gather_unit_save(rl_gather_unit *unit, const char *path);
+int rl_gather_unit_flush(rl_gather_unit *unit);
 /* GatherUnit::read (gather_unit.rs:81-92); a short file is not an error
  * (read.rs:20-32), a missing file is RL_ERR_IO here. */
 int rl_gather_unit_load(rl_gather_unit *unit, const char *path);

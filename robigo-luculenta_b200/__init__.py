@@ -115,6 +115,8 @@ SYMBOLS = {
     "rl_trace_unit_ray_count": (_I, [_P, C.POINTER(_U64)]),
     "rl_trace_unit_sync": (_I, [_P]),
     "rl_trace_batch_counter_reset": (None, [_U64]),
+    "rl_host_register": (_I, [_P, C.c_size_t]),
+    "rl_host_unregister": (_I, [_P]),
     "rl_plot_unit_create": (_I, [_U64, _U32, _U32, C.POINTER(_P)]),
     "rl_plot_unit_destroy": (_I, [_P]),
     "rl_plot_unit_set_stream": (_I, [_P, _P]),
@@ -134,6 +136,7 @@ SYMBOLS = {
     "rl_gather_unit_accumulate_plot": (_I, [_P, _P, _I]),
     "rl_gather_unit_accumulate_device": (_I, [_P, C.POINTER(_P), _U32]),
     "rl_gather_unit_save": (_I, [_P, C.c_char_p]),
+    "rl_gather_unit_flush": (_I, [_P]),
     "rl_gather_unit_load": (_I, [_P, C.c_char_p]),
     "rl_gather_unit_download": (_I, [_P, _P, _P]),
     "rl_gather_unit_sync": (_I, [_P]),
@@ -453,8 +456,15 @@ class GatherUnit:
         arr = (_P * len(pointers))(*[_P(p) for p in pointers])
         _check(lib().rl_gather_unit_accumulate_device(self._h, arr, len(pointers)))
 
-    def save(self, path="buffer.raw"):
+    def save(self, path="buffer.raw", wait=True):
+        """GatherUnit::save (gather_unit.rs:68-78).  The file is written by the unit's
+        writer thread; `wait` returns once it is on disk (rl_gather_unit_flush)."""
         _check(lib().rl_gather_unit_save(self._h, os.fsencode(path)))
+        if wait:
+            self.flush()
+
+    def flush(self):
+        _check(lib().rl_gather_unit_flush(self._h))
 
     def load(self, path="buffer.raw"):
         _check(lib().rl_gather_unit_load(self._h, os.fsencode(path)))

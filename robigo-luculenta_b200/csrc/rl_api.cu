@@ -6,9 +6,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rl_b200.h"
@@ -121,6 +124,79 @@ struct rl_plot_unit {
     uint64_t staging_capacity = 0;
 };
 
+// buffer.raw writer of a gather unit (gather_unit.rs:68-78 rewrites the whole file on every
+// gather, app.rs:151; at 1024^2 that is 25 MB of file I/O per gather and was the critical path
+// of the whole pipeline).  save() only snapshots the two device buffers into page-locked host
+// memory (one DMA transfer); a background thread writes the snapshot to `path.tmp` and renames
+// it over `path`, so the file on disk is always one complete snapshot.  A save that arrives
+// while an older snapshot still waits to be written replaces it (every save rewrites the whole
+// file, only the newest state matters).  The first save to a path is written synchronously so
+// that an unwritable path fails in the caller ("failed to open file", gather_unit.rs:69); a
+// later background failure is returned by the next save / flush.
+struct SaveWriter {
+    std::mutex m;
+    std::condition_variable cv;
+    std::thread thread;
+    bool started = false, stop = false;
+    float *buf[2] = {nullptr, nullptr};
+    size_t floats = 0;
+    int pending = -1, writing = -1;
+    std::string pending_path, error;
+    std::vector<std::string> proven;
+
+    static bool write_file(const std::string &path, const float *data, size_t floats, std::string &err) {
+        const std::string tmp = path + ".tmp";
+        FILE *f = fopen(tmp.c_str(), "wb");
+        if (!f) { err = "failed to open file " + path; return false; }
+        const size_t w = fwrite(data, sizeof(float), floats, f);
+        const int c = fclose(f);
+        if (w != floats || c != 0 || rename(tmp.c_str(), path.c_str()) != 0) {
+            remove(tmp.c_str());
+            err = "failed to write raw buffer " + path;
+            return false;
+        }
+        return true;
+    }
+    void run() {
+        std::unique_lock<std::mutex> lock(m);
+        for (;;) {
+            cv.wait(lock, [&] { return pending >= 0 || stop; });
+            if (pending < 0) return;
+            const int idx = pending;
+            const std::string path = pending_path;
+            pending = -1;
+            writing = idx;
+            lock.unlock();
+            std::string err;
+            const bool ok = write_file(path, buf[idx], floats, err);
+            lock.lock();
+            writing = -1;
+            if (!ok && error.empty()) error = err;
+            cv.notify_all();
+        }
+    }
+    // waits until nothing is queued or being written; returns the first background failure
+    std::string flush() {
+        std::unique_lock<std::mutex> lock(m);
+        cv.wait(lock, [&] { return pending < 0 && writing < 0; });
+        std::string e;
+        e.swap(error);
+        return e;
+    }
+    void shutdown() {
+        if (started) {
+            {
+                std::lock_guard<std::mutex> lock(m);
+                stop = true;
+            }
+            cv.notify_all();
+            thread.join();
+            started = false;
+        }
+        for (float *&b : buf) { if (b) cudaFreeHost(b); b = nullptr; }
+    }
+};
+
 struct rl_gather_unit {
     uint32_t width = 0, height = 0;
     Device dev;
@@ -128,6 +204,7 @@ struct rl_gather_unit {
     float *d_acc = nullptr;
     float *d_comp = nullptr;
     float *d_staging = nullptr;
+    SaveWriter writer;
 };
 
 struct rl_tonemap_unit {
@@ -633,6 +710,23 @@ int rl_trace_unit_sync(rl_trace_unit *u) {
 
 void rl_trace_batch_counter_reset(uint64_t next_batch) { g_next_batch.store(next_batch); }
 
+// ------------------------------------------------------- host buffer pinning
+int rl_host_register(void *ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return fail(RL_ERR_INVALID, "rl_host_register: null or empty buffer");
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return RL_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(RL_ERR_CUDA, cudaGetErrorString(e)); }
+    return RL_OK;
+}
+
+int rl_host_unregister(void *ptr) {
+    if (!ptr) return RL_OK;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return RL_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(RL_ERR_CUDA, cudaGetErrorString(e)); }
+    return RL_OK;
+}
+
 // ---------------------------------------------------------------- PlotUnit
 int rl_plot_unit_create(uint64_t id, uint32_t width, uint32_t height, rl_plot_unit **out) {
     if (!out || width == 0 || height == 0) return fail(RL_ERR_INVALID, "rl_plot_unit_create: bad argument");
@@ -795,6 +889,7 @@ int rl_gather_unit_destroy(rl_gather_unit *u) {
     if (!u) return RL_OK;
     cudaSetDevice(u->dev.index);
     if (u->ss.stream) cudaStreamSynchronize(u->ss.stream);
+    u->writer.shutdown();          // writes out a snapshot that is still queued
     cudaFree(u->d_acc); cudaFree(u->d_comp); cudaFree(u->d_staging);
     u->ss.destroy();
     delete u;
@@ -850,22 +945,68 @@ int rl_gather_unit_accumulate_device(rl_gather_unit *u, const void *const *bufs,
 int rl_gather_unit_save(rl_gather_unit *u, const char *path) {
     if (!u || !path) return fail(RL_ERR_INVALID, "rl_gather_unit_save: null argument");
     RL_CUDA(cudaSetDevice(u->dev.index));
+    SaveWriter &wr = u->writer;
     const size_t n = (size_t)u->width * u->height * 3;
-    std::vector<float> host(2 * n);
-    RL_CUDA(cudaMemcpyAsync(host.data(), u->d_acc, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
-    RL_CUDA(cudaMemcpyAsync(host.data() + n, u->d_comp, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
+    if (!wr.buf[0]) {
+        wr.floats = 2 * n;
+        RL_CUDA(cudaMallocHost(&wr.buf[0], 2 * n * sizeof(float)));
+        cudaError_t e = cudaMallocHost(&wr.buf[1], 2 * n * sizeof(float));
+        if (e != cudaSuccess) { cudaFreeHost(wr.buf[0]); wr.buf[0] = nullptr; return fail(RL_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    bool proven = false;
+    for (const std::string &p : wr.proven) proven |= p == path;
+    int idx = 0;
+    if (proven) {
+        std::lock_guard<std::mutex> lock(wr.m);
+        if (!wr.error.empty()) {
+            std::string e;
+            e.swap(wr.error);
+            return fail(RL_ERR_IO, e);
+        }
+        if (wr.pending >= 0) { idx = wr.pending; wr.pending = -1; }   // replace the snapshot not yet written
+        else idx = wr.writing == 0 ? 1 : 0;
+    } else {
+        const std::string e = wr.flush();
+        if (!e.empty()) return fail(RL_ERR_IO, e);
+    }
+    // only this thread fills buffers (a unit is never shared), the writer only reads `writing`
+    float *host = wr.buf[idx];
+    RL_CUDA(cudaMemcpyAsync(host, u->d_acc, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(cudaMemcpyAsync(host + n, u->d_comp, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
-    FILE *f = fopen(path, "wb");
-    if (!f) return fail(RL_ERR_IO, std::string("failed to open file ") + path);
-    size_t w = fwrite(host.data(), sizeof(float), 2 * n, f);
-    int c = fclose(f);
-    if (w != 2 * n || c != 0) return fail(RL_ERR_IO, "failed to write raw buffer");
+    if (!proven) {
+        std::string err;
+        if (!SaveWriter::write_file(path, host, 2 * n, err)) return fail(RL_ERR_IO, err);
+        wr.proven.push_back(path);
+        return RL_OK;
+    }
+    {
+        std::lock_guard<std::mutex> lock(wr.m);
+        if (!wr.started) {
+            wr.thread = std::thread([&wr] { wr.run(); });
+            wr.started = true;
+        }
+        wr.pending = idx;
+        wr.pending_path = path;
+    }
+    wr.cv.notify_all();
+    return RL_OK;
+}
+
+int rl_gather_unit_flush(rl_gather_unit *u) {
+    if (!u) return fail(RL_ERR_INVALID, "null unit");
+    const std::string e = u->writer.flush();
+    if (!e.empty()) return fail(RL_ERR_IO, e);
     return RL_OK;
 }
 
 int rl_gather_unit_load(rl_gather_unit *u, const char *path) {
     if (!u || !path) return fail(RL_ERR_INVALID, "rl_gather_unit_load: null argument");
     RL_CUDA(cudaSetDevice(u->dev.index));
+    {
+        const std::string e = u->writer.flush();     // a queued save of the same file lands first
+        if (!e.empty()) return fail(RL_ERR_IO, e);
+    }
     const size_t n = (size_t)u->width * u->height * 3;
     FILE *f = fopen(path, "rb");
     if (!f) return fail(RL_ERR_IO, std::string("failed to open file ") + path);

@@ -119,6 +119,17 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
     __syncthreads();
 }
 
+// The block's photon pool counter (trace_kernel): the second word of the third
+// scratch counter array, whose first word is the task-list length and whose
+// other words are unused (blocks have at least 128 threads).
+__device__ __forceinline__ uint32_t *photon_pool() {
+    float4 *ray_tab = rl_smem + tables().scratch;
+    float2 *results = reinterpret_cast<float2 *>(ray_tab + 3 * blockDim.x);
+    uint32_t *counters = reinterpret_cast<uint32_t *>(results + RL_COMPOUND_SLOTS * blockDim.x)
+                         + RL_COMPOUND_SLOTS * blockDim.x;
+    return counters + 2 * blockDim.x + 1;
+}
+
 // Shared memory a tracing kernel needs with `threads` threads per block.
 inline size_t tracing_smem_bytes(const DevScene &sc, int threads) {
     return (RL_TABLES_VEC4 + (size_t)sc.smem_vec4) * sizeof(float4)
@@ -545,8 +556,11 @@ __device__ __forceinline__ Hit intersect_scene_brute(const Ray &ray) {
 // the bounding test.
 //
 // Must be called by every thread of the block together (block barriers and
-// warp votes inside); threads without a live path pass idle_ray().
-__device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
+// warp votes inside); threads without a live path pass idle_ray() and
+// live = false.  A warp none of whose lanes is live skips the scans (its rays
+// hit nothing anyway) and only serves the block's task list: in the tail of a
+// small batch most warps of a block are in that state.
+__device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true) {
     const PrimTables &tb = tables();
     Hit best;
     best.t = 1.0e12f; best.obj = -1; best.code = RL_HIT_NONE;
@@ -601,8 +615,9 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
     const float bthr_c = bthr - sqrtf(dd) * tb.cluster_rmax;
     const uint32_t lanes_below = (1u << lane) - 1u;
     uint16_t *myq = lq_base + tid;                              // private cluster queue, slot k at myq[k * nthreads]
-    uint32_t i = 0;
-    do {
+    const bool warp_live = __any_sync(0xffffffffu, live);       // warp-uniform
+    uint32_t i = warp_live ? 0u : n_clusters;
+    if (warp_live) do {
         // each lane queues its candidate clusters privately (three predicated instructions per
         // cluster), until any queue could overflow
         uint32_t mine = 0;
@@ -680,7 +695,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
         __syncwarp();
     } while (__any_sync(0xffffffffu, i < n_clusters));
 
-    intersect_flat_surfaces(tb, ray, best);
+    if (warp_live) intersect_flat_surfaces(tb, ray, best);
 
     // Compound bodies (block-wide; every thread of the block calls intersect_scene together).
     //  1. bounding-sphere test in a uniform loop, kept (lane, body) pairs compacted with a ballot;
@@ -701,7 +716,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray) {
         const uint32_t round_end = min(round + RL_BODIES_PER_ROUND, n_compounds);
         uint32_t npairs = 0;                                    // warp-uniform
 #pragma unroll 1
-        for (uint32_t i = round; i < round_end; i++) {
+        for (uint32_t i = warp_live ? round : round_end; i < round_end; i++) {
             const float4 b4 = compounds[2 * i + 1];             // bounding sphere {c, r^2}
             bool keep = true;
             if (b4.w >= 0.0f) {

@@ -9,6 +9,8 @@
 // Compile with -fmad=false: see rl_math.cuh.
 #include <atomic>
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 #include "rl_kernels.h"
 #include "rl_device.cuh"
@@ -28,6 +30,14 @@ void kernel_launches_reset() { g_launches.store(0); }
 #ifndef RL_TRACE_MIN_BLOCKS
 #define RL_TRACE_MIN_BLOCKS 1
 #endif
+// launches with fewer than RL_TRACE_SMALL_PATHS photons per thread of a full grid use CTAs of
+// RL_TRACE_SMALL_CTA threads (0 paths: never); both can be overridden from the environment
+#ifndef RL_TRACE_SMALL_CTA
+#define RL_TRACE_SMALL_CTA 256
+#endif
+#ifndef RL_TRACE_SMALL_PATHS
+#define RL_TRACE_SMALL_PATHS 64
+#endif
 
 // ------------------------------------------------------------------ K1 trace
 struct TraceArgs {
@@ -41,19 +51,27 @@ struct TraceArgs {
     unsigned long long *ray_counter;
 };
 
-// Persistent threads with path regeneration: every lane owns the photons
-// tid, tid + T, tid + 2T, ... of the launch and starts its next photon as soon
-// as its current path ends, so a warp never idles on its longest path.  The
-// primitive tables live in shared memory; each loop iteration is one
-// Scene::intersect plus one material interaction for every live lane.
+// Persistent threads with path regeneration: a block owns a contiguous range
+// of the launch's photons and hands them out from a counter in shared memory
+// (one warp-aggregated atomic per warp and iteration); a lane takes its next
+// photon the moment its current path ends, so a warp never idles on its longest
+// path and no lane idles while the block's pool is not empty -- with the
+// reference's 524 288-photon batches a thread sees only a handful of paths and
+// a static deal would leave most lanes waiting for the unluckiest one.  The
+// result of a photon depends on its id alone, so the deal changes nothing but
+// the order of the accumulator atomics.  The primitive tables live in shared
+// memory; each loop iteration is one Scene::intersect plus one material
+// interaction for every live lane.
 __global__ void __launch_bounds__(RL_TRACE_THREADS, RL_TRACE_MIN_BLOCKS)
 trace_kernel(const DevScene sc, const TraceArgs a) {
     setup_tables(sc);
 
     // photon indices within the launch fit 32 bits (launch_trace splits larger requests)
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t n_photons = (uint32_t)a.n_photons;
-    uint32_t next = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pool_end = (uint32_t)(a.n_photons * (blockIdx.x + 1ull) / gridDim.x);
+    uint32_t *pool = photon_pool();
+    if (threadIdx.x == 0) *pool = (uint32_t)(a.n_photons * (uint64_t)blockIdx.x / gridDim.x);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
 
     bool alive = false;
     uint32_t cur = 0;
@@ -73,10 +91,22 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
 #endif
 
     for (;;) {
-        if (!alive && next < n_photons) {
+        // lanes without a path draw the next photon ids of the block's pool; the counter stops
+        // being advanced once it has passed the end (it is read first), so it cannot wrap
+        uint32_t mine = 0xffffffffu;
+        {
+            const uint32_t want = __ballot_sync(0xffffffffu, !alive);
+            if (want != 0u && *reinterpret_cast<volatile uint32_t *>(pool) < pool_end) {
+                const uint32_t leader = __ffs(want) - 1u;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(pool, (uint32_t)__popc(want));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!alive) mine = base + __popc(want & ((1u << lane) - 1u));
+            }
+        }
+        if (mine < pool_end) {
             // trace_unit.rs:151-158 and :136-145
-            cur = next;
-            next = next + stride < next ? 0xffffffffu : next + stride;   // saturate: 2^32 - 1 is never a valid index
+            cur = mine;
             const RngKey key = {a.seed, a.first_photon + cur};
             rng.init();
             const float wavelength = rng.wavelength(key);
@@ -91,7 +121,7 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
         // every thread of the block takes part in the intersection (block barriers and warp
         // votes inside); idle lanes trace a ray that hits nothing
         if (!__syncthreads_or(alive)) break;
-        Hit hit = intersect_scene(alive ? ray : idle_ray());
+        Hit hit = intersect_scene(alive ? ray : idle_ray(), alive);
         if (alive) rays++;                                              // Scene::intersect calls (scene.rs:39)
 #if RL_SORT_PATHS
         {
@@ -183,8 +213,62 @@ static size_t trace_kernel_smem_bytes(const DevScene &sc, int threads) {
     return tracing_smem_bytes(sc, threads) + (RL_SORT_PATHS ? (size_t)RL_SORT_BYTES_PER_THREAD * threads : 0);
 }
 
+// Small launches in flight, one entry per launch: an event recorded behind the kernel on the
+// unit's stream.  launch_trace (under its lock) drops the completed ones and counts the other
+// streams that still have a small launch queued or running -- the concurrency the host's worker
+// threads are producing right now (app.rs:95-111 runs C of them over 3C trace units).
+struct SmallLaunch { cudaEvent_t done; cudaStream_t stream; int device; };
+static std::vector<SmallLaunch> g_small_inflight;
+static std::vector<SmallLaunch> g_small_events;   // recycled events (stream unused)
+
+static int other_streams_in_flight(int device, cudaStream_t mine) {
+    std::vector<cudaStream_t> seen;
+    size_t keep = 0;
+    for (size_t i = 0; i < g_small_inflight.size(); i++) {
+        const SmallLaunch l = g_small_inflight[i];
+        if (cudaEventQuery(l.done) == cudaErrorNotReady) {
+            g_small_inflight[keep++] = l;
+            if (l.device == device && l.stream != mine) {
+                bool dup = false;
+                for (cudaStream_t s : seen) dup |= s == l.stream;
+                if (!dup) seen.push_back(l.stream);
+            }
+        } else {
+            g_small_events.push_back(l);
+        }
+    }
+    g_small_inflight.resize(keep);
+    cudaGetLastError();   // cudaErrorNotReady is not an error
+    return (int)seen.size();
+}
+
+static void note_small_launch(int device, cudaStream_t st) {
+    SmallLaunch l{nullptr, st, device};
+    for (size_t i = 0; i < g_small_events.size(); i++)
+        if (g_small_events[i].device == device) {
+            l.done = g_small_events[i].done;
+            g_small_events.erase(g_small_events.begin() + i);
+            break;
+        }
+    if (!l.done && cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    if (cudaEventRecord(l.done, st) == cudaSuccess) g_small_inflight.push_back(l);
+    else { cudaGetLastError(); g_small_events.push_back(l); }
+}
+
+static int env_int(const char *name, int fallback) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : fallback;
+}
+
 cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count, cudaStream_t st) {
     if (p.n_photons == 0) return cudaSuccess;
+    // the function attributes below are process-wide: launches from the threads of different
+    // units (each on its own stream) take turns setting them and launching
+    static std::mutex launch_lock;
+    std::lock_guard<std::mutex> guard(launch_lock);
     // the largest CTA (up to RL_TRACE_THREADS) whose tables + scratch fit the shared memory of an SM:
     // big CTAs fill the per-CTA task list of the body evaluation best
     int dev = 0, max_smem = 0;
@@ -193,8 +277,23 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     if (err != cudaSuccess) return err;
     int threads = RL_TRACE_THREADS;
     while (threads > 128 && trace_kernel_smem_bytes(sc, threads) > (size_t)max_smem) threads -= 128;
+    // Small batches (the reference's 524 288 photons are 4.6 per thread of a full grid) spend most
+    // of their time in the tail, where a block waits for its last paths.  They are launched as
+    // small CTAs, several per SM, so that the blocks of a launch retire one by one and the blocks
+    // of the next unit's launch (another stream) move in beside the ones still in their tail.
+    // Each such launch also takes only its share of the SM's block slots: with k other units'
+    // small launches in flight it asks for ceil(per_sm / (k + 1)) blocks per SM, so k + 1 launches
+    // run side by side with three times the paths per thread (fewer table copies and tails per
+    // photon) instead of one after the other with every block spending most of its life in its
+    // tail.  Measured on the reference's batch, built-in scene, 8 units (tools/strict_rates.py):
+    // 768 x 1: 2200 Mrays/s, 256 x 3 full grid: 2310, 256 x 1-of-3: 2600 (large batches: 2750).
+    const int small_cta = env_int("RL_TRACE_SMALL_CTA", RL_TRACE_SMALL_CTA);
+    const uint64_t small_paths = (uint64_t)env_int("RL_TRACE_SMALL_PATHS", RL_TRACE_SMALL_PATHS);
+    const bool small = small_cta >= 128 && small_cta < threads && small_cta % 32 == 0
+                       && p.n_photons < small_paths * (uint64_t)sm_count * (uint64_t)threads;
+    if (small) threads = small_cta;
     const size_t smem = trace_kernel_smem_bytes(sc, threads);
-    err = cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    err = cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (err != cudaSuccess) return err;
     int per_sm = 0;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel, threads, smem);
@@ -211,6 +310,15 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     }
     uint64_t want = (p.n_photons + threads - 1) / threads;
     uint64_t full = (uint64_t)sm_count * per_sm;
+    if (small) {
+        // RL_TRACE_BLOCKS_PER_SM > 0 fixes the share (experiments); default: by the concurrency seen
+        int share = env_int("RL_TRACE_BLOCKS_PER_SM", 0);
+        if (share <= 0) {
+            const int others = other_streams_in_flight(dev, st);
+            share = (per_sm + others) / (others + 1);
+        }
+        if (share < per_sm) full = (uint64_t)sm_count * (share < 1 ? 1 : share);
+    }
     unsigned grid = (unsigned)(want < full ? want : full);
     // the kernel indexes photons of a launch with 32 bits: larger requests take several launches
     const uint64_t chunk = 1ull << 31;
@@ -230,6 +338,7 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
+    if (small) note_small_launch(dev, st);
     return cudaSuccess;
 }
 

@@ -10,7 +10,7 @@
 // one handle never shared -- is exercised exactly as the Rust host would.
 //
 //   rl_replay --width W --height H --threads C --batches B [--batch N] [--seed S]
-//             [--mode strict|device] [--scene 1..4] [--out PREFIX]
+//             [--mode strict|device] [--scene 1..4] [--out PREFIX] [--pin 0|1] [--lazy 0|1]
 //
 // strict: every call goes through host buffers exactly as app.rs:132-164 does
 //         (mapped_photons Vec -> plot(&[MappedPhoton]) -> tristimulus_buffer Vec
@@ -18,6 +18,7 @@
 // device: the same schedule with the device-resident overloads (no host trips).
 // Stops after B trace batches, gathers what is left, tonemaps once, writes
 // PREFIX.raw (buffer.raw format) and PREFIX.ppm, prints one JSON line.
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -153,8 +154,22 @@ private:
     std::string raw_path_;
 };
 
+// wall time the workers spent in each kind of task (summed over threads), for the report
+struct KindStats { std::atomic<uint64_t> ns{0}, calls{0}; };
+KindStats g_stats[5];
+
+void execute_kind(Task &t, const Scene &scene, bool device);
+
 // app.rs:113-164
 void execute(Task &t, const Scene &scene, bool device) {
+    const auto t0 = std::chrono::steady_clock::now();
+    execute_kind(t, scene, device);
+    const auto dt = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0);
+    g_stats[(int)t.kind].ns += (uint64_t)dt.count();
+    g_stats[(int)t.kind].calls++;
+}
+
+void execute_kind(Task &t, const Scene &scene, bool device) {
     switch (t.kind) {
     case Kind::Sleep: std::this_thread::sleep_for(std::chrono::milliseconds(1)); break;   // app.rs:128-130 (100 ms there)
     case Kind::Trace: t.trace->render(scene); break;                                      // app.rs:132-134
@@ -194,6 +209,8 @@ int main(int argc, char **argv) {
     const int which = atoi(arg(argc, argv, "--scene", "2"));
     const bool device = !strcmp(arg(argc, argv, "--mode", "strict"), "device");
     const std::string out = arg(argc, argv, "--out", "replay");
+    pin_host_buffers() = atoi(arg(argc, argv, "--pin", "1")) != 0;
+    lazy_host_mirrors() = atoi(arg(argc, argv, "--lazy", "1")) != 0;
 
     try {
         rl_scene_builder *builder = nullptr;
@@ -235,11 +252,17 @@ int main(int argc, char **argv) {
             fclose(f);
         }
         const uint64_t rays = scheduler.rays();
-        printf("{\"mode\": \"%s\", \"threads\": %zu, \"batches\": %llu, \"batch\": %llu, \"seconds\": %.6f, "
-               "\"batches_per_s\": %.3f, \"rays\": %llu, \"mrays_per_s\": %.3f}\n",
-               device ? "device" : "strict", threads, (unsigned long long)scheduler.traces_completed(),
+        printf("{\"mode\": \"%s\", \"pinned\": %s, \"lazy\": %s, \"width\": %u, \"height\": %u, \"threads\": %zu, \"batches\": %llu, \"batch\": %llu, \"seconds\": %.6f, "
+               "\"batches_per_s\": %.3f, \"rays\": %llu, \"mrays_per_s\": %.3f, \"worker_seconds\": {\"sleep\": [%llu, %.3f], "
+               "\"trace\": [%llu, %.3f], \"plot\": [%llu, %.3f], \"gather\": [%llu, %.3f], \"tonemap\": [%llu, %.3f]}}\n",
+               device ? "device" : "strict", pin_host_buffers() ? "true" : "false",
+               lazy_host_mirrors() ? "true" : "false", w, h, threads, (unsigned long long)scheduler.traces_completed(),
                (unsigned long long)batch, seconds, scheduler.traces_completed() / seconds,
-               (unsigned long long)rays, rays / seconds / 1e6);
+               (unsigned long long)rays, rays / seconds / 1e6,
+               (unsigned long long)g_stats[0].calls, g_stats[0].ns * 1e-9, (unsigned long long)g_stats[1].calls,
+               g_stats[1].ns * 1e-9, (unsigned long long)g_stats[2].calls, g_stats[2].ns * 1e-9,
+               (unsigned long long)g_stats[3].calls, g_stats[3].ns * 1e-9, (unsigned long long)g_stats[4].calls,
+               g_stats[4].ns * 1e-9);
         rl_scene_builder_destroy(builder);
     } catch (const std::exception &e) {
         fprintf(stderr, "rl_replay: %s\n", e.what());

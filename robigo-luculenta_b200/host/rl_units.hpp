@@ -9,6 +9,7 @@
 #pragma once
 
 #include <cstdint>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -23,6 +24,67 @@ using MappedPhoton = rl_mapped_photon;                 // trace_unit.rs:23-37
 inline void expect(int status, const char *what) {
     if (status != RL_OK) throw std::runtime_error(std::string(what) + ": " + rl_last_error());
 }
+
+// The units' host buffers are allocated once and never resized (trace_unit.rs:75-77,
+// plot_unit.rs:47, gather_unit.rs:40, tonemap_unit.rs:47): page-lock them once so that the
+// copies behind render()/plot()/accumulate() are DMA transfers (rl_host_register).
+// `pin_host_buffers() = false` keeps them pageable (A/B measurements).
+inline bool &pin_host_buffers() { static bool on = true; return on; }
+template <typename T> inline void pin(std::vector<T> &v) {
+    if (pin_host_buffers() && !v.empty()) expect(rl_host_register(v.data(), v.size() * sizeof(T)), "rl_host_register");
+}
+template <typename T> inline void unpin(std::vector<T> &v) {
+    if (pin_host_buffers() && !v.empty()) rl_host_unregister(v.data());
+}
+
+// A unit's read-only host buffer whose truth lives on the device: `tristimulus_buffer` of
+// PlotUnit (plot_unit.rs:34) and GatherUnit (gather_unit.rs:26).  The host only ever reads
+// these fields, as slices handed to the next unit (app.rs:146,157), so the copy back from the
+// device is made when the field is read, not after every plot()/accumulate() that changes it:
+// a plot task plots a dozen trace units into one plot unit (task_scheduler.rs:192-207) before
+// anybody looks at the result.  Reads go through the conversions below, which is where a Rust
+// shim puts `impl Deref<Target = [Vector3]>` -- `&unit.tristimulus_buffer` at the call sites
+// of app.rs coerces to `&[Vector3]` unchanged.  `lazy_host_mirrors() = false` copies back
+// eagerly after every change instead (A/B measurements).
+inline bool &lazy_host_mirrors() { static bool on = true; return on; }
+template <typename T> class HostMirror {
+public:
+    using Download = std::function<void(T *)>;
+    HostMirror() = default;
+    ~HostMirror() { unpin(storage_); }
+    HostMirror(const HostMirror &) = delete;
+    HostMirror &operator=(const HostMirror &) = delete;
+    void init(size_t n, Download download) {
+        storage_.assign(n, T{});
+        pin(storage_);
+        download_ = std::move(download);
+    }
+    // the device copy changed
+    void invalidate() {
+        if (!download_) return;
+        stale_ = true;
+        if (!lazy_host_mirrors()) sync();
+    }
+    const std::vector<T> &get() const { sync(); return storage_; }
+    operator const std::vector<T> &() const { return get(); }
+    const T *data() const { return get().data(); }
+    size_t size() const { return storage_.size(); }
+    bool empty() const { return storage_.empty(); }
+    const T &operator[](size_t i) const { return get()[i]; }
+    typename std::vector<T>::const_iterator begin() const { return get().begin(); }
+    typename std::vector<T>::const_iterator end() const { return get().end(); }
+
+private:
+    void sync() const {
+        if (stale_) {
+            download_(storage_.data());
+            stale_ = false;
+        }
+    }
+    mutable std::vector<T> storage_;
+    mutable bool stale_ = false;
+    Download download_;
+};
 
 // Stands in for Arc<Scene> (app.rs:63): the flattened scene on the device.
 class Scene {
@@ -47,8 +109,9 @@ public:
         expect(rl_trace_unit_create(id_, width, height, seed, &handle_), "rl_trace_unit_create");
         expect(rl_trace_unit_set_batch_size(handle_, batch), "rl_trace_unit_set_batch_size");
         if (!keep_on_device) mapped_photons.assign(batch, MappedPhoton{0.f, 0.f, 0.f, 0.f});
+        pin(mapped_photons);
     }
-    ~TraceUnit() { rl_trace_unit_destroy(handle_); }
+    ~TraceUnit() { rl_trace_unit_destroy(handle_); unpin(mapped_photons); }
     TraceUnit(const TraceUnit &) = delete;
     TraceUnit &operator=(const TraceUnit &) = delete;
 
@@ -74,12 +137,14 @@ private:
 
 class PlotUnit {
 public:
-    // plot_unit.rs:43-53.  `mirror_on_host`: refresh `tristimulus_buffer` after
-    // every plot()/clear(), as the unchanged app.rs:146 reads the field.
-    PlotUnit(size_t id_, uint32_t width, uint32_t height, bool mirror_on_host = true)
-        : id(id_), mirror_(mirror_on_host) {
+    // plot_unit.rs:43-53.  `mirror_on_host`: keep `tristimulus_buffer` readable on the host,
+    // as the unchanged app.rs:146 reads the field.
+    PlotUnit(size_t id_, uint32_t width, uint32_t height, bool mirror_on_host = true) : id(id_) {
         expect(rl_plot_unit_create(id_, width, height, &handle_), "rl_plot_unit_create");
-        if (mirror_) tristimulus_buffer.assign((size_t)width * height, Vector3{0.f, 0.f, 0.f});
+        if (mirror_on_host)
+            tristimulus_buffer.init((size_t)width * height, [this](Vector3 *dst) {
+                expect(rl_plot_unit_download(handle_, reinterpret_cast<float *>(dst)), "rl_plot_unit_download");
+            });
     }
     ~PlotUnit() { rl_plot_unit_destroy(handle_); }
     PlotUnit(const PlotUnit &) = delete;
@@ -88,42 +153,39 @@ public:
     // plot_unit.rs:87-95
     void plot(const std::vector<MappedPhoton> &photons) {
         expect(rl_plot_unit_plot(handle_, photons.data(), photons.size()), "rl_plot_unit_plot");
-        refresh();
+        tristimulus_buffer.invalidate();
     }
     // the same on records a trace unit left on the device
     void plot(TraceUnit &unit) {
         expect(rl_plot_unit_plot_device(handle_, unit.handle()), "rl_plot_unit_plot_device");
-        refresh();
+        tristimulus_buffer.invalidate();
     }
     // plot_unit.rs:98-102
     void clear() {
         expect(rl_plot_unit_clear(handle_), "rl_plot_unit_clear");
-        if (mirror_) tristimulus_buffer.assign(tristimulus_buffer.size(), Vector3{0.f, 0.f, 0.f});
+        tristimulus_buffer.invalidate();
     }
     rl_plot_unit *handle() { return handle_; }
 
-    std::vector<Vector3> tristimulus_buffer;           // plot_unit.rs:34
+    HostMirror<Vector3> tristimulus_buffer;            // plot_unit.rs:34
     size_t id;                                         // plot_unit.rs:37
 
 private:
-    void refresh() {
-        if (mirror_)
-            expect(rl_plot_unit_download(handle_, reinterpret_cast<float *>(tristimulus_buffer.data())),
-                   "rl_plot_unit_download");
-    }
     rl_plot_unit *handle_ = nullptr;
-    bool mirror_;
 };
 
 class GatherUnit {
 public:
     // gather_unit.rs:35-46: resumes from "buffer.raw" if it exists
     GatherUnit(uint32_t width, uint32_t height, const char *resume_path = "buffer.raw", bool mirror_on_host = true)
-        : path_(resume_path ? resume_path : ""), mirror_(mirror_on_host) {
+        : path_(resume_path ? resume_path : "") {
         expect(rl_gather_unit_create(width, height, resume_path, &handle_), "rl_gather_unit_create");
-        if (mirror_) {
-            tristimulus_buffer.assign((size_t)width * height, Vector3{0.f, 0.f, 0.f});
-            refresh();
+        if (mirror_on_host) {
+            tristimulus_buffer.init((size_t)width * height, [this](Vector3 *dst) {
+                expect(rl_gather_unit_download(handle_, reinterpret_cast<float *>(dst), nullptr),
+                       "rl_gather_unit_download");
+            });
+            tristimulus_buffer.invalidate();           // the resumed state
         }
     }
     ~GatherUnit() { rl_gather_unit_destroy(handle_); }
@@ -134,31 +196,27 @@ public:
     void accumulate(const std::vector<Vector3> &tristimuli) {
         expect(rl_gather_unit_accumulate(handle_, reinterpret_cast<const float *>(tristimuli.data())),
                "rl_gather_unit_accumulate");
-        refresh();
+        tristimulus_buffer.invalidate();
     }
     // accumulate(&plot.tristimulus_buffer) + plot.clear() without the host trip (app.rs:145-148)
     void accumulate(PlotUnit &plot, bool clear_plot) {
         expect(rl_gather_unit_accumulate_plot(handle_, plot.handle(), clear_plot ? 1 : 0),
                "rl_gather_unit_accumulate_plot");
-        refresh();
+        tristimulus_buffer.invalidate();
+        if (clear_plot) plot.tristimulus_buffer.invalidate();
     }
-    // gather_unit.rs:68-78
+    // gather_unit.rs:68-78; the file is written behind the call (rl_gather_unit_save), the
+    // destructor waits for it
     void save() {
         if (!path_.empty()) expect(rl_gather_unit_save(handle_, path_.c_str()), "failed to open file");
     }
     rl_gather_unit *handle() { return handle_; }
 
-    std::vector<Vector3> tristimulus_buffer;           // gather_unit.rs:26
+    HostMirror<Vector3> tristimulus_buffer;            // gather_unit.rs:26
 
 private:
-    void refresh() {
-        if (mirror_)
-            expect(rl_gather_unit_download(handle_, reinterpret_cast<float *>(tristimulus_buffer.data()), nullptr),
-                   "rl_gather_unit_download");
-    }
     rl_gather_unit *handle_ = nullptr;
     std::string path_;
-    bool mirror_;
 };
 
 class TonemapUnit {
@@ -166,8 +224,9 @@ public:
     // tonemap_unit.rs:43-51
     TonemapUnit(uint32_t width, uint32_t height) : rgb_buffer((size_t)width * height * 3, 0) {
         expect(rl_tonemap_unit_create(width, height, &handle_), "rl_tonemap_unit_create");
+        pin(rgb_buffer);
     }
-    ~TonemapUnit() { rl_tonemap_unit_destroy(handle_); }
+    ~TonemapUnit() { rl_tonemap_unit_destroy(handle_); unpin(rgb_buffer); }
     TonemapUnit(const TonemapUnit &) = delete;
     TonemapUnit &operator=(const TonemapUnit &) = delete;
 

@@ -327,6 +327,46 @@ def test_buffer_raw_checkpoint_format(gpu, tmp_path):
     assert e.value.code == gpu.RL_ERR_IO
 
 
+def test_buffer_raw_background_writer(gpu, tmp_path):
+    # app.rs:151 saves after every gather: only the first save to a path writes in the caller,
+    # later ones hand a snapshot to the unit's writer thread (newest wins); the file on disk is
+    # always one complete snapshot and flush / load / destroy make it current
+    w, h = 256, 256
+    rng = np.random.default_rng(11)
+    path = str(tmp_path / "buffer.raw")
+    other = gpu.GatherUnit(w, h)
+    with pytest.raises(gpu.RlError) as e:
+        other.save(str(tmp_path / "no_such_dir" / "buffer.raw"))    # "failed to open file" in the caller
+    assert e.value.code == gpu.RL_ERR_IO
+    g = gpu.GatherUnit(w, h)
+    states = []
+    for i in range(12):
+        g.accumulate(rng.uniform(0, 5, (h, w, 3)).astype(np.float32))
+        acc, comp = g.download(with_compensation=True)
+        states.append(np.concatenate([acc.reshape(-1), comp.reshape(-1)]))
+        g.save(path, wait=False)
+        # whatever the writer is doing, a reader sees a whole snapshot of some earlier or the current state
+        raw = np.fromfile(path, dtype="<f4")
+        assert raw.size == 6 * w * h
+        assert any(np.array_equal(raw, st) for st in states)
+    g.flush()
+    assert np.array_equal(np.fromfile(path, dtype="<f4"), states[-1])
+    # load waits for a queued save of the same file; destroy writes out what is still queued
+    g.accumulate(rng.uniform(0, 5, (h, w, 3)).astype(np.float32))
+    acc, comp = g.download(with_compensation=True)
+    g.save(path, wait=False)
+    g.load(path)
+    acc2, comp2 = g.download(with_compensation=True)
+    assert np.array_equal(acc2, acc) and np.array_equal(comp2, comp)
+    g.accumulate(rng.uniform(0, 5, (h, w, 3)).astype(np.float32))
+    acc, comp = g.download(with_compensation=True)
+    g.save(path, wait=False)
+    del g
+    raw = np.fromfile(path, dtype="<f4")
+    assert np.array_equal(raw[: 3 * w * h], acc.reshape(-1)) and np.array_equal(raw[3 * w * h:], comp.reshape(-1))
+    assert not os.path.exists(path + ".tmp")
+
+
 # ----------------------------------------------------------------- tonemap
 def test_tonemap_matches_oracle(gpu, orc):
     w, h, n = 96, 64, 300000
