@@ -13,6 +13,12 @@ Scene::intersect call (scene.rs:39), counted on the device.
 Under torchrun (N > 1) every rank traces its own 2^28-photon id range (weak
 scaling: the job renders N x 256 spp), the XYZ framebuffers are summed onto
 rank 0 with one NCCL reduce and gathered there (gather_unit.rs:49-64).
+
+`value` is the device-resident rate (one fused launch per step).  `e2e` is the
+same workload pushed through the reference host's own call pattern with host
+buffers (strict mode: host/rl_replay.cpp, 524 288-photon batches, every
+MappedPhoton and tristimulus buffer crossing PCIe, buffer.raw written after
+every gather); `e2e_device` is the device-mode API with the frame copied back.
 """
 from __future__ import annotations
 
@@ -286,12 +292,10 @@ def main():
     total_rays = int(r[0])
     value = total_rays / (step_ms * 1e-3) / 1e6
 
-    # ---- end to end through the C ABI with host buffers -------------------------------------
+    # ---- end to end, device mode: the C ABI with the records left on the GPU ------------------
     # every step: scene descriptor (host) -> rl_scene_create, fused trace+splat, gather, and the
-    # XYZ framebuffer copied back into pinned host memory
+    # XYZ framebuffer copied back into pinned host memory (the four-line edit of app.rs)
     host_xyz = torch.empty((HEIGHT, WIDTH, 3), dtype=torch.float32).pin_memory().numpy()
-    h2d = desc.n_surfaces * 52 + desc.n_objects * 20 + 84
-    d2h = WIDTH * HEIGHT * 12
 
     def e2e_step():
         sc = pkg.Scene(desc)
@@ -304,19 +308,78 @@ def main():
     e2e_step()
     barrier()
     rays1 = trace.ray_count()
+    pkg.reset_transfer_counters()
     e2e_steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+    dev_h2d, dev_d2h = pkg.transfer_counters()
     e2e_rays = trace.ray_count() - rays1
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     r = torch.tensor([e2e_rays], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
-    e2e_value = int(r[0]) / float(t[0]) / 1e6
+    e2e_device = {"value": int(r[0]) / float(t[0]) / 1e6, "unit": "Mrays/s",
+                  "h2d_bytes_per_step": dev_h2d // e2e_steps, "d2h_bytes_per_step": dev_d2h // e2e_steps,
+                  "steps": e2e_steps,
+                  "path": "rl_scene_create(host descriptor) + rl_trace_unit_render_fused + gather + XYZ frame to "
+                          "pinned host memory, one 2^28-photon call per step (device mode, DESIGN.md 1)"}
+
+    # ---- end to end, strict mode: the reference host's own call pattern with host buffers ------
+    # host/rl_replay.cpp drives the C ABI exactly as app.rs:95-164 / task_scheduler.rs:91-182 do:
+    # C worker threads, 3C trace units rendering 524 288-photon batches into host Vecs
+    # (TraceUnit::render), PlotUnit::plot(&[MappedPhoton]) from host memory, GatherUnit::accumulate
+    # (&[Vector3]) from host memory, buffer.raw saved after every gather, one tonemap at the end.
+    # One process per GPU; rank r renders the batches [r * B, (r + 1) * B); with N > 1 the ranks'
+    # gathered frames are then summed onto rank 0 (host -> device -> NCCL reduce -> host).
+    e2e_steps = max(1, min(args.steps, 8))
+    replay_batches = e2e_steps * (n // 524288)
+    workers = max(2, min(16, (os.cpu_count() or 8) // world))
+    exe = entry.build_replay()
+    out_prefix = f"/tmp/rl_bench_replay_{os.getpid()}"
+    cmd = [exe, "--width", str(WIDTH), "--height", str(HEIGHT), "--threads", str(workers), "--batches",
+           str(replay_batches), "--batch", "524288", "--seed", str(SEED), "--mode", "strict", "--scene", "2",
+           "--out", out_prefix, "--first-batch", str(rank * replay_batches)]
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=visible.split(",")[local_rank] if visible else str(local_rank))
+    barrier()
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1200)
+    if res.returncode != 0:
+        raise RuntimeError("rl_replay failed: " + res.stderr[-500:])
+    replay = json.loads(res.stdout.strip().splitlines()[-1])
+    combine_s = 0.0
+    if world > 1:
+        t0 = time.perf_counter()
+        frame = np.fromfile(out_prefix + ".raw", dtype="<f4", count=WIDTH * HEIGHT * 3)
+        dev_frame = torch.from_numpy(frame).cuda()
+        dist.reduce(dev_frame, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            host_xyz[...] = dev_frame.cpu().numpy().reshape(HEIGHT, WIDTH, 3)
+        barrier()
+        combine_s = time.perf_counter() - t0
+    for suffix in (".raw", ".ppm"):
+        try:
+            os.remove(out_prefix + suffix)
+        except OSError:
+            pass
+    t = torch.tensor([replay["seconds"] + combine_s], dtype=torch.float64, device="cuda")
+    r = torch.tensor([replay["rays"], replay["h2d_bytes"], replay["d2h_bytes"]], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    frame_bytes = WIDTH * HEIGHT * 12 if world > 1 else 0
+    e2e = {"value": int(r[0]) / float(t[0]) / 1e6, "unit": "Mrays/s",
+           "h2d_bytes_per_step": (int(r[1]) + frame_bytes * world) // e2e_steps,
+           "d2h_bytes_per_step": (int(r[2]) + frame_bytes) // e2e_steps,
+           "steps": e2e_steps, "batches_per_step_per_gpu": n // 524288, "worker_threads_per_gpu": workers,
+           "seconds": float(t[0]),
+           "path": "strict mode: the reference host's call pattern replayed against the C ABI with host buffers "
+                   "(host/rl_replay.cpp; app.rs:95-164, task_scheduler.rs:91-182): 524 288-photon TraceUnit::render "
+                   "into host memory, PlotUnit::plot / GatherUnit::accumulate from host memory, buffer.raw saved "
+                   "after every gather, tonemap at the end" + ("; ranks' frames summed onto rank 0" if world > 1 else "")}
 
     if rank != 0:
         if world > 1:
@@ -385,6 +448,27 @@ def main():
         ],
     }
 
+    # The trace kernel's own bound is FP32 issue.  Algorithmic flops of one Scene::intersect call =
+    # the reference's linear scan (scene.rs:39-60) over the built-in scene with SURVEY 8d's per-
+    # primitive costs: 311 spheres x 19 + 3 paraboloids x 45 + 3 planes/circles x 15 + 22 prisms x
+    # 8 half-space tests x 15 (their containment tests, which depend on the ray, are left out: a
+    # lower bound).  The kernel reaches the same hits with fewer executed operations (culling), so
+    # this is reference-equivalent work per second, next to the executed issue-slot utilisation of
+    # the committed ncu capture.
+    flops_per_ray = 311 * 19 + 3 * 45 + 3 * 15 + 22 * 8 * 15
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    fp32_peak = torch.cuda.get_device_properties(local_rank).multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
+    rays_per_launch = total_rays / (world * args.steps)
+    roofline["compute"] = {
+        "bound": "fp32 issue (no tensor-core work on this path)",
+        "achieved": rays_per_launch * flops_per_ray / kernel_s / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": rays_per_launch * flops_per_ray / kernel_s / 1e12 / fp32_peak,
+        "algorithmic_flops_per_ray": flops_per_ray,
+        "peak_source": f"SMs x 128 FP32 lanes x 2 x {sm_mhz:.0f} MHz (sampled SM clock)",
+        "note": "algorithmic = the reference's brute-force scan per Scene::intersect call, containment tests of "
+                "the prisms excluded (lower bound); executed issue-slot utilisation is in profiles/",
+    }
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         entry.build_oracle()
@@ -411,8 +495,8 @@ def main():
         "mphotons_per_s": n * world * args.steps / (step_ms * 1e-3) / 1e6,
         "batches_per_s": n * world * args.steps / (step_ms * 1e-3) / 524288,
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps},
+        "e2e": e2e,
+        "e2e_device": e2e_device,
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

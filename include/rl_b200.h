@@ -210,6 +210,13 @@ int rl_trace_unit_sync(rl_trace_unit *unit);
 /* Reset the process-wide batch counter used by rl_trace_unit_render. */
 void rl_trace_batch_counter_reset(uint64_t next_batch);
 
+/* Bytes copied host -> device and device -> host by the entry points of this
+ * ABI since the last reset (process-wide): scene tables, MappedPhoton batches,
+ * tristimulus buffers, buffer.raw snapshots, RGB images.  What bench.py reports
+ * as h2d/d2h bytes per step. */
+void rl_transfer_counters(uint64_t *h2d_bytes, uint64_t *d2h_bytes);
+void rl_transfer_counters_reset(void);
+
 /* Host buffers of the units.  The reference's units own plain `Vec`s
  * (`mapped_photons`, trace_unit.rs:56,75-77; `tristimulus_buffer`,
  * plot_unit.rs:34,47 and gather_unit.rs:26,40) that the host passes around as

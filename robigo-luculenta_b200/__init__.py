@@ -115,6 +115,8 @@ SYMBOLS = {
     "rl_trace_unit_ray_count": (_I, [_P, C.POINTER(_U64)]),
     "rl_trace_unit_sync": (_I, [_P]),
     "rl_trace_batch_counter_reset": (None, [_U64]),
+    "rl_transfer_counters": (None, [C.POINTER(_U64), C.POINTER(_U64)]),
+    "rl_transfer_counters_reset": (None, []),
     "rl_host_register": (_I, [_P, C.c_size_t]),
     "rl_host_unregister": (_I, [_P]),
     "rl_plot_unit_create": (_I, [_U64, _U32, _U32, C.POINTER(_P)]),
@@ -205,6 +207,17 @@ def kernel_launch_count():
 
 def reset_kernel_launch_count():
     lib().rl_kernel_launch_count_reset()
+
+
+def transfer_counters():
+    """(host->device, device->host) bytes copied through the C ABI since the last reset."""
+    a, b = _U64(0), _U64(0)
+    lib().rl_transfer_counters(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
+
+
+def reset_transfer_counters():
+    lib().rl_transfer_counters_reset()
 
 
 def reset_batch_counter(next_batch=0):

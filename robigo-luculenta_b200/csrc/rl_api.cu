@@ -28,6 +28,15 @@ int fail(int code, const std::string &msg) {
     return code;
 }
 
+// bytes that crossed the host/device boundary through this ABI (rl_transfer_counters)
+std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0};
+
+cudaError_t copy_async(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream) {
+    if (kind == cudaMemcpyHostToDevice) g_h2d_bytes += bytes;
+    else if (kind == cudaMemcpyDeviceToHost) g_d2h_bytes += bytes;
+    return cudaMemcpyAsync(dst, src, bytes, kind, stream);
+}
+
 #define RL_CUDA(expr)                                                                          \
     do {                                                                                       \
         cudaError_t e_ = (expr);                                                               \
@@ -571,6 +580,7 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     if (e == cudaSuccess) e = cudaMalloc(&sc->d_materials, materials.size() * sizeof(float4));
     if (e == cudaSuccess)
         e = cudaMemcpy(sc->d_blob, blob.data(), blob.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    g_h2d_bytes += blob.size() * sizeof(float4) + materials.size() * sizeof(float4);
     if (e == cudaSuccess)
         e = cudaMemcpy(sc->d_materials, materials.data(), materials.size() * sizeof(float4),
                        cudaMemcpyHostToDevice);
@@ -659,7 +669,7 @@ int rl_trace_unit_render_range(rl_trace_unit *u, const rl_scene *scene, uint64_t
     RL_CUDA(launch_trace(scene->ds, p, u->dev.sm_count, u->ss.stream));
     u->n_valid = n_photons;
     if (out) {
-        RL_CUDA(cudaMemcpyAsync(out, u->d_records, n_photons * sizeof(rl_mapped_photon),
+        RL_CUDA(copy_async(out, u->d_records, n_photons * sizeof(rl_mapped_photon),
                                 cudaMemcpyDeviceToHost, u->ss.stream));
         RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     }
@@ -695,7 +705,7 @@ int rl_trace_unit_ray_count(rl_trace_unit *u, uint64_t *out_rays) {
     if (!u || !out_rays) return fail(RL_ERR_INVALID, "null argument");
     RL_CUDA(cudaSetDevice(u->dev.index));
     unsigned long long v = 0;
-    RL_CUDA(cudaMemcpyAsync(&v, u->d_rays, sizeof(v), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(copy_async(&v, u->d_rays, sizeof(v), cudaMemcpyDeviceToHost, u->ss.stream));
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     *out_rays = v;
     return RL_OK;
@@ -709,6 +719,12 @@ int rl_trace_unit_sync(rl_trace_unit *u) {
 }
 
 void rl_trace_batch_counter_reset(uint64_t next_batch) { g_next_batch.store(next_batch); }
+
+void rl_transfer_counters(uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
+    if (h2d_bytes) *h2d_bytes = g_h2d_bytes.load();
+    if (d2h_bytes) *d2h_bytes = g_d2h_bytes.load();
+}
+void rl_transfer_counters_reset(void) { g_h2d_bytes.store(0); g_d2h_bytes.store(0); }
 
 // ------------------------------------------------------- host buffer pinning
 int rl_host_register(void *ptr, size_t bytes) {
@@ -776,7 +792,7 @@ int rl_plot_unit_plot(rl_plot_unit *u, const rl_mapped_photon *photons, uint64_t
         RL_CUDA(cudaMalloc(&u->d_staging, n * sizeof(rl_mapped_photon)));
         u->staging_capacity = n;
     }
-    RL_CUDA(cudaMemcpyAsync(u->d_staging, photons, n * sizeof(rl_mapped_photon),
+    RL_CUDA(copy_async(u->d_staging, photons, n * sizeof(rl_mapped_photon),
                             cudaMemcpyHostToDevice, u->ss.stream));
     RL_CUDA(launch_splat(u->d_staging, n, u->d_accum, u->width, u->height, u->dev.sm_count,
                          u->ss.stream));
@@ -809,7 +825,7 @@ int rl_plot_unit_download(rl_plot_unit *u, float *xyz) {
     RL_CUDA(cudaSetDevice(u->dev.index));
     const uint64_t n = (uint64_t)u->width * u->height;
     RL_CUDA(launch_pack_xyz(u->d_accum, u->d_packed, n, u->ss.stream));
-    RL_CUDA(cudaMemcpyAsync(xyz, u->d_packed, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(copy_async(xyz, u->d_packed, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     return RL_OK;
 }
@@ -907,7 +923,7 @@ int rl_gather_unit_accumulate(rl_gather_unit *u, const float *xyz) {
     if (!u || !xyz) return fail(RL_ERR_INVALID, "rl_gather_unit_accumulate: null argument");
     RL_CUDA(cudaSetDevice(u->dev.index));
     const uint64_t n = (uint64_t)u->width * u->height;
-    RL_CUDA(cudaMemcpyAsync(u->d_staging, xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, u->ss.stream));
+    RL_CUDA(copy_async(u->d_staging, xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, u->ss.stream));
     RL_CUDA(launch_gather(u->d_acc, u->d_comp, nullptr, 0, u->d_staging, nullptr, n, u->dev.sm_count,
                           u->ss.stream));
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
@@ -971,8 +987,8 @@ int rl_gather_unit_save(rl_gather_unit *u, const char *path) {
     }
     // only this thread fills buffers (a unit is never shared), the writer only reads `writing`
     float *host = wr.buf[idx];
-    RL_CUDA(cudaMemcpyAsync(host, u->d_acc, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
-    RL_CUDA(cudaMemcpyAsync(host + n, u->d_comp, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(copy_async(host, u->d_acc, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(copy_async(host + n, u->d_comp, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     if (!proven) {
         std::string err;
@@ -1013,14 +1029,14 @@ int rl_gather_unit_load(rl_gather_unit *u, const char *path) {
     // read.rs:20-32: a short file is not an error; what was not read keeps
     // its current value.
     std::vector<float> host(2 * n);
-    RL_CUDA(cudaMemcpyAsync(host.data(), u->d_acc, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
-    RL_CUDA(cudaMemcpyAsync(host.data() + n, u->d_comp, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(copy_async(host.data(), u->d_acc, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(copy_async(host.data() + n, u->d_comp, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     size_t got = fread(host.data(), 1, 2 * n * sizeof(float), f);
     (void)got;
     fclose(f);
-    RL_CUDA(cudaMemcpyAsync(u->d_acc, host.data(), n * sizeof(float), cudaMemcpyHostToDevice, u->ss.stream));
-    RL_CUDA(cudaMemcpyAsync(u->d_comp, host.data() + n, n * sizeof(float), cudaMemcpyHostToDevice, u->ss.stream));
+    RL_CUDA(copy_async(u->d_acc, host.data(), n * sizeof(float), cudaMemcpyHostToDevice, u->ss.stream));
+    RL_CUDA(copy_async(u->d_comp, host.data() + n, n * sizeof(float), cudaMemcpyHostToDevice, u->ss.stream));
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     return RL_OK;
 }
@@ -1029,8 +1045,8 @@ int rl_gather_unit_download(rl_gather_unit *u, float *xyz, float *comp) {
     if (!u || !xyz) return fail(RL_ERR_INVALID, "rl_gather_unit_download: null argument");
     RL_CUDA(cudaSetDevice(u->dev.index));
     const size_t bytes = (size_t)u->width * u->height * 3 * sizeof(float);
-    RL_CUDA(cudaMemcpyAsync(xyz, u->d_acc, bytes, cudaMemcpyDeviceToHost, u->ss.stream));
-    if (comp) RL_CUDA(cudaMemcpyAsync(comp, u->d_comp, bytes, cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(copy_async(xyz, u->d_acc, bytes, cudaMemcpyDeviceToHost, u->ss.stream));
+    if (comp) RL_CUDA(copy_async(comp, u->d_comp, bytes, cudaMemcpyDeviceToHost, u->ss.stream));
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     return RL_OK;
 }
@@ -1085,10 +1101,10 @@ int rl_tonemap_unit_set_stream(rl_tonemap_unit *u, void *s) {
 static int tonemap_device(rl_tonemap_unit *u, const float *d_xyz, uint8_t *rgb) {
     RL_CUDA(launch_tonemap(d_xyz, u->width, u->height, u->d_moments, u->d_exposure, u->d_rgb,
                            u->dev.sm_count, u->ss.stream));
-    RL_CUDA(cudaMemcpyAsync(&u->last_exposure, u->d_exposure, sizeof(float), cudaMemcpyDeviceToHost,
+    RL_CUDA(copy_async(&u->last_exposure, u->d_exposure, sizeof(float), cudaMemcpyDeviceToHost,
                             u->ss.stream));
     if (rgb)
-        RL_CUDA(cudaMemcpyAsync(rgb, u->d_rgb, (size_t)u->width * u->height * 3, cudaMemcpyDeviceToHost,
+        RL_CUDA(copy_async(rgb, u->d_rgb, (size_t)u->width * u->height * 3, cudaMemcpyDeviceToHost,
                                 u->ss.stream));
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     return RL_OK;
@@ -1097,7 +1113,7 @@ static int tonemap_device(rl_tonemap_unit *u, const float *d_xyz, uint8_t *rgb) 
 int rl_tonemap_unit_tonemap(rl_tonemap_unit *u, const float *xyz, uint8_t *rgb) {
     if (!u || !xyz || !rgb) return fail(RL_ERR_INVALID, "rl_tonemap_unit_tonemap: null argument");
     RL_CUDA(cudaSetDevice(u->dev.index));
-    RL_CUDA(cudaMemcpyAsync(u->d_xyz, xyz, (size_t)u->width * u->height * 3 * sizeof(float),
+    RL_CUDA(copy_async(u->d_xyz, xyz, (size_t)u->width * u->height * 3 * sizeof(float),
                             cudaMemcpyHostToDevice, u->ss.stream));
     return tonemap_device(u, u->d_xyz, rgb);
 }

@@ -11,6 +11,9 @@
 //
 //   rl_replay --width W --height H --threads C --batches B [--batch N] [--seed S]
 //             [--mode strict|device] [--scene 1..4] [--out PREFIX] [--pin 0|1] [--lazy 0|1]
+//             [--first-batch K]
+// --first-batch: photon ids start at K * batch (a second process -- another GPU -- continues
+// the id range of the first).
 //
 // strict: every call goes through host buffers exactly as app.rs:132-164 does
 //         (mapped_photons Vec -> plot(&[MappedPhoton]) -> tristimulus_buffer Vec
@@ -219,12 +222,24 @@ int main(int argc, char **argv) {
         rl_scene_desc desc;
         expect(rl_scene_builder_desc(builder, &desc), "rl_scene_builder_desc");
         Scene scene(desc);
-        rl_trace_batch_counter_reset(0);
+        {
+            // untimed warm-up: loads the kernels (one small batch through every unit type)
+            TraceUnit tu(0, 64, 64, seed, 4096, false);
+            PlotUnit pu(0, 64, 64);
+            GatherUnit gu(64, 64, nullptr);
+            TonemapUnit mu(64, 64);
+            tu.render(scene);
+            pu.plot(tu.mapped_photons);
+            gu.accumulate(pu.tristimulus_buffer);
+            mu.tonemap(gu.tristimulus_buffer);
+        }
+        rl_trace_batch_counter_reset(strtoull(arg(argc, argv, "--first-batch", "0"), nullptr, 10));
         const std::string raw = out + ".raw";
         remove(raw.c_str());   // start from black: GatherUnit::new resumes from the file if present
 
         Scheduler scheduler(threads, w, h, seed, batch, device, batches, raw);
         std::mutex lock;
+        rl_transfer_counters_reset();
         const auto t0 = std::chrono::steady_clock::now();
         std::vector<std::thread> workers;
         for (size_t i = 0; i < threads; i++) {
@@ -242,7 +257,11 @@ int main(int argc, char **argv) {
             });
         }
         for (auto &t : workers) t.join();
+        // the run ends when buffer.raw is on disk (the writer thread of the gather unit)
+        expect(rl_gather_unit_flush(scheduler.gather_unit()->handle()), "rl_gather_unit_flush");
         const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        uint64_t h2d = 0, d2h = 0;
+        rl_transfer_counters(&h2d, &d2h);
 
         const auto &rgb = scheduler.tonemap_unit()->rgb_buffer;
         FILE *f = fopen((out + ".ppm").c_str(), "wb");
@@ -253,12 +272,12 @@ int main(int argc, char **argv) {
         }
         const uint64_t rays = scheduler.rays();
         printf("{\"mode\": \"%s\", \"pinned\": %s, \"lazy\": %s, \"width\": %u, \"height\": %u, \"threads\": %zu, \"batches\": %llu, \"batch\": %llu, \"seconds\": %.6f, "
-               "\"batches_per_s\": %.3f, \"rays\": %llu, \"mrays_per_s\": %.3f, \"worker_seconds\": {\"sleep\": [%llu, %.3f], "
+               "\"batches_per_s\": %.3f, \"rays\": %llu, \"mrays_per_s\": %.3f, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"worker_seconds\": {\"sleep\": [%llu, %.3f], "
                "\"trace\": [%llu, %.3f], \"plot\": [%llu, %.3f], \"gather\": [%llu, %.3f], \"tonemap\": [%llu, %.3f]}}\n",
                device ? "device" : "strict", pin_host_buffers() ? "true" : "false",
                lazy_host_mirrors() ? "true" : "false", w, h, threads, (unsigned long long)scheduler.traces_completed(),
                (unsigned long long)batch, seconds, scheduler.traces_completed() / seconds,
-               (unsigned long long)rays, rays / seconds / 1e6,
+               (unsigned long long)rays, rays / seconds / 1e6, (unsigned long long)h2d, (unsigned long long)d2h,
                (unsigned long long)g_stats[0].calls, g_stats[0].ns * 1e-9, (unsigned long long)g_stats[1].calls,
                g_stats[1].ns * 1e-9, (unsigned long long)g_stats[2].calls, g_stats[2].ns * 1e-9,
                (unsigned long long)g_stats[3].calls, g_stats[3].ns * 1e-9, (unsigned long long)g_stats[4].calls,

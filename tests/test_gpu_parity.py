@@ -198,6 +198,51 @@ def test_empty_and_ragged_batches(gpu, orc):
         assert_records_equal(got, want, f"ragged n={n}")
 
 
+def test_launch_geometry_does_not_change_results(gpu, monkeypatch):
+    # block size, share of the SMs' block slots and the order in which a block's pool hands
+    # out photon ids are scheduling only: records and ray counts are bit-equal under every policy
+    sc = gpu.Scene(gpu.SceneBuilder(2))
+    n, first = 150000, (1 << 33) + 99
+    want = None
+    for knobs in ({}, {"RL_TRACE_SMALL_PATHS": "0"}, {"RL_TRACE_SMALL_CTA": "128"},
+                  {"RL_TRACE_SMALL_CTA": "384", "RL_TRACE_BLOCKS_PER_SM": "1"}, {"RL_TRACE_BLOCKS_PER_SM": "2"}):
+        for k in ("RL_TRACE_SMALL_PATHS", "RL_TRACE_SMALL_CTA", "RL_TRACE_BLOCKS_PER_SM"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in knobs.items():
+            monkeypatch.setenv(k, v)
+        tu = gpu.TraceUnit(0, 640, 360, seed=SEED, batch=n)
+        got = (tu.render_range(sc, first, n).copy(), tu.ray_count())
+        if want is None:
+            want = got
+        assert_records_equal(got[0], want[0], f"policy {knobs}")
+        assert got[1] == want[1]
+
+
+def test_units_driven_from_concurrent_threads(gpu, orc):
+    # app.rs:95-111: C worker threads, each with its own trace unit, render at the same time
+    # (the small launches then share the SMs); every unit still returns exactly its batch
+    import threading
+    b = gpu.SceneBuilder(2)
+    sc = gpu.Scene(b)
+    n, rounds, workers = 20000, 3, 6
+    units = [gpu.TraceUnit(i, 320, 200, seed=SEED, batch=n) for i in range(workers)]
+    got = {}
+
+    def work(i):
+        for r in range(rounds):
+            got[(i, r)] = units[i].render_range(sc, (r * workers + i) * n, n).copy()
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(workers)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    want = orc.trace(b.desc(), SEED, 320, 200, 0, rounds * workers * n)
+    for (i, r), rec in got.items():
+        k = r * workers + i
+        assert_records_equal(rec, want[k * n:(k + 1) * n], f"unit {i} round {r}")
+
+
 # ------------------------------------------------------------------- splat
 def image_tolerance(ref):
     return 1e-5 * float(np.abs(ref).max()) + 1e-12

@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""The launches the committed ncu captures are taken from (run under ncu, see profiles/):
+  0  warm-up
+  1  fused trace+splat, built-in scene, 1024^2, 2^24 photons: the bench configuration (768 x 1)
+  2  one reference batch (524 288 photons) into records: the small-launch configuration (256 x 3)
+  3  splat of those records
+"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as entry
+
+pkg = entry.load_package()
+W = H = 1024
+scene = pkg.Scene(pkg.SceneBuilder(pkg.SCENE_C2))
+tu = pkg.TraceUnit(0, W, H, seed=0x5EED, batch=1 << 24)
+pl = pkg.PlotUnit(0, W, H)
+tu.render_fused(scene, pl, 0, 1 << 22)
+tu.sync()
+tu.render_fused(scene, pl, 1 << 24, 1 << 24)
+tu.sync()
+tu.render_range(scene, 1 << 26, 524288, download=False)
+tu.sync()
+pl.plot(tu)
+pl.sync()
+print("rays", tu.ray_count())
