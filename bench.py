@@ -335,7 +335,9 @@ def main():
     # (&[Vector3]) from host memory, buffer.raw saved after every gather, one tonemap at the end.
     # One process per GPU; rank r renders the batches [r * B, (r + 1) * B); with N > 1 the ranks'
     # gathered frames are then summed onto rank 0 (host -> device -> NCCL reduce -> host).
-    e2e_steps = max(1, min(args.steps, 8))
+    # at least four steps' worth, so that the replay's ramp-up and drain (last gathers, tonemap,
+    # buffer.raw flush) weigh as they do in a long render
+    e2e_steps = min(max(args.steps, 4), 16)
     replay_batches = e2e_steps * (n // 524288)
     workers = max(2, min(16, (os.cpu_count() or 8) // world))
     exe = entry.build_replay()

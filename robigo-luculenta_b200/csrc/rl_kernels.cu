@@ -72,6 +72,7 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
     if (threadIdx.x == 0) *pool = (uint32_t)(a.n_photons * (uint64_t)blockIdx.x / gridDim.x);
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
+    bool pool_empty = false;
 
     bool alive = false;
     uint32_t cur = 0;
@@ -91,17 +92,19 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
 #endif
 
     for (;;) {
-        // lanes without a path draw the next photon ids of the block's pool; the counter stops
-        // being advanced once it has passed the end (it is read first), so it cannot wrap
+        // lanes without a path draw the next photon ids of the block's pool; a warp that has seen
+        // the pool empty never touches the counter again, so it overshoots the end by at most
+        // 32 per warp and cannot wrap
         uint32_t mine = 0xffffffffu;
-        {
+        if (!pool_empty) {
             const uint32_t want = __ballot_sync(0xffffffffu, !alive);
-            if (want != 0u && *reinterpret_cast<volatile uint32_t *>(pool) < pool_end) {
+            if (want != 0u) {
                 const uint32_t leader = __ffs(want) - 1u;
                 uint32_t base = 0;
                 if (lane == leader) base = atomicAdd(pool, (uint32_t)__popc(want));
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (!alive) mine = base + __popc(want & ((1u << lane) - 1u));
+                pool_empty = base + (uint32_t)__popc(want) >= pool_end;      // warp-uniform
             }
         }
         if (mine < pool_end) {

@@ -487,6 +487,40 @@ def test_full_resolution_properties(gpu, orc):
     assert np.all(img >= 0.0) and np.isfinite(img).all()
 
 
+def test_c5_canvas_properties(gpu, orc):
+    # BASELINE configs[4] canvas (4096x4096, built-in scene): 201 MB frames, far more pixels than
+    # photons here -- the laws that do not depend on size, plus gather + clear + tonemap at that size
+    w = h = 4096
+    n = 1 << 21
+    b = gpu.SceneBuilder(2)
+    sc = gpu.Scene(b)
+    tu = gpu.TraceUnit(0, w, h, seed=SEED, batch=n)
+    fused = gpu.PlotUnit(0, w, h)
+    tu.render_fused(sc, fused, 5 * n, n)
+    photons = tu.render_range(sc, 5 * n, n)
+    img = fused.tristimulus_buffer
+    cie = orc.tristimulus(photons["wavelength"]).astype(np.float64)
+    total = (cie * photons["probability"].astype(np.float64)[:, None]).sum(axis=0)
+    assert np.allclose(img.astype(np.float64).sum(axis=(0, 1)), total, rtol=2e-4)
+    want = orc.trace(b.desc(), SEED, w, h, 5 * n + 777, 2048)
+    assert_records_equal(photons[777:777 + 2048], want, "sample at 4096^2")
+    # the oracle's splat of the same records, compared where it matters: every touched pixel
+    ref = orc.plot(w, h, photons)
+    assert float(np.abs(img - ref).max()) <= image_tolerance(ref)
+    # gather the frame twice (Kahan), clearing the plot unit the second time
+    g = gpu.GatherUnit(w, h)
+    g.accumulate(fused)
+    g.accumulate(fused, clear=True)
+    acc = np.zeros_like(ref)
+    comp = np.zeros_like(ref)
+    orc.gather_accumulate(acc, comp, img)
+    orc.gather_accumulate(acc, comp, img)
+    assert_bit_equal(g.download().reshape(-1), acc.reshape(-1), "gather at 4096^2")
+    assert not fused.tristimulus_buffer.any()
+    rgb = gpu.TonemapUnit(w, h).tonemap(g)
+    assert rgb.shape == (h, w, 3) and rgb.any()
+
+
 def test_scheduler_call_pattern(gpu, orc):
     # The smoke sequence of the reference's only integration test (main.rs:69-74, app.rs:75-90,
     # task_scheduler.rs:127-182 with concurrency 1): Trace(0), Trace(1), Plot(plot0, [0, 1]),
