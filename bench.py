@@ -443,7 +443,9 @@ def main():
             {"kernel": "splat_kernel (PlotUnit::plot, 2^25 records)", "bound": "hbm",
              "achieved": splat_bytes / (splat_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
              "frac": splat_bytes / (splat_ms * 1e-3) / 1e9 / peak, "ms": splat_ms,
-             "bytes": f"16 B x {n_splat} records + 48 B x {n_lit} contributing photons"},
+             "bytes": f"16 B x {n_splat} records + 48 B x {n_lit} contributing photons",
+             "traffic": 562370560.0,
+             "traffic_source": "profiles/r1_s2_splat_kernel_ncu.txt: dram read + write of one 2^25-record launch"},
             {"kernel": "gather_kernel (GatherUnit::accumulate + clear, 4096^2)", "bound": "hbm",
              "achieved": gw * gw * GATHER_BYTES_PER_PIXEL / (gather_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
              "frac": gw * gw * GATHER_BYTES_PER_PIXEL / (gather_ms * 1e-3) / 1e9 / peak, "ms": gather_ms},

@@ -940,33 +940,58 @@ __constant__ float c_cie[81][3] = {
 #include "rl_cie1931_data.inc"
 };
 
+// Where the CIE table is read from.  The constant bank serves one address per instruction: right
+// for the trace kernel, where one or two lanes of a warp end a lit path at a time, wrong for the
+// splat kernel, where 32 lit photons with 32 different wavelengths look the table up together
+// (each of the six loads would be replayed once per distinct address).  The splat kernel keeps a
+// float4 copy of the table in shared memory.
+struct CieConstant {
+    __device__ __forceinline__ V3 operator()(int i) const { return mk(c_cie[i][0], c_cie[i][1], c_cie[i][2]); }
+};
+struct CieShared {
+    const float4 *tab;                                          // [81] {X, Y, Z, 0}
+    __device__ __forceinline__ V3 operator()(int i) const { const float4 v = tab[i]; return mk(v.x, v.y, v.z); }
+};
+// fills a CieShared table; call with every thread of the block, then __syncthreads()
+__device__ __forceinline__ void fill_cie_shared(float4 *tab) {
+    for (uint32_t i = threadIdx.x; i < 81; i += blockDim.x) tab[i] = make_float4(c_cie[i][0], c_cie[i][1], c_cie[i][2], 0.0f);
+}
+
 // cie1931.rs:20-48
-__device__ __forceinline__ V3 tristimulus(float wavelength) {
+template <typename Table>
+__device__ __forceinline__ V3 tristimulus_from(const Table &cie, float wavelength) {
     const float indexf = (wavelength - 380.0f) / 5.0f;
     const int index = (int)floorf(indexf);
     const float remainder = indexf - (float)index;
     if (index < -1 || index > 80) return mk(0.0f, 0.0f, 0.0f);
-    if (index == -1) return mk(c_cie[0][0] * remainder, c_cie[0][1] * remainder, c_cie[0][2] * remainder);
+    if (index == -1) { const V3 a = cie(0); return mk(a.x * remainder, a.y * remainder, a.z * remainder); }
     if (index == 80) {
         const float w = 1.0f - remainder;
-        return mk(c_cie[80][0] * w, c_cie[80][1] * w, c_cie[80][2] * w);
+        const V3 a = cie(80);
+        return mk(a.x * w, a.y * w, a.z * w);
     }
     const float w = 1.0f - remainder;
-    return mk(c_cie[index][0] * w + c_cie[index + 1][0] * remainder,
-              c_cie[index][1] * w + c_cie[index + 1][1] * remainder,
-              c_cie[index][2] * w + c_cie[index + 1][2] * remainder);
+    const V3 a = cie(index), b = cie(index + 1);
+    return mk(a.x * w + b.x * remainder, a.y * w + b.y * remainder, a.z * w + b.z * remainder);
 }
+__device__ __forceinline__ V3 tristimulus(float wavelength) { return tristimulus_from(CieConstant(), wavelength); }
 
 __device__ __forceinline__ void red_add_v4(float4 *addr, float x, float y, float z) {
+#ifdef RL_PROBE_NO_RED
+    // experiments only (tools/splat_probe.py --no-red): everything but the reduction itself
+    asm volatile("" :: "l"(addr), "f"(x), "f"(y), "f"(z) : "memory");
+#else
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                  :: "l"(addr), "f"(x), "f"(y), "f"(z), "f"(0.0f) : "memory");
+#endif
 }
 
 // PlotUnit::plot for one photon (plot_unit.rs:56-95) into the padded
 // accumulator (one float4 {X, Y, Z, 0} per pixel): four vector reductions.
-__device__ __forceinline__ void splat_photon(float4 *accum, int w, int h, float aspect, float x,
-                                             float y, float wavelength, float probability) {
-    const V3 cie = tristimulus(wavelength) * probability;
+template <typename Table>
+__device__ __forceinline__ void splat_photon_from(const Table &table, float4 *accum, int w, int h, float aspect,
+                                                  float x, float y, float wavelength, float probability) {
+    const V3 cie = tristimulus_from(table, wavelength) * probability;
     const float px = (x * 0.5f + 0.5f) * ((float)w - 1.0f);
     const float py = (y * aspect * 0.5f + 0.5f) * ((float)h - 1.0f);
     const int px1 = max(0, min(w - 1, (int)floorf(px)));
@@ -983,6 +1008,10 @@ __device__ __forceinline__ void splat_photon(float4 *accum, int w, int h, float 
     red_add_v4(accum + ((size_t)py1 * w + px2), cie.x * c21, cie.y * c21, cie.z * c21);
     red_add_v4(accum + ((size_t)py2 * w + px1), cie.x * c12, cie.y * c12, cie.z * c12);
     red_add_v4(accum + ((size_t)py2 * w + px2), cie.x * c22, cie.y * c22, cie.z * c22);
+}
+__device__ __forceinline__ void splat_photon(float4 *accum, int w, int h, float aspect, float x,
+                                             float y, float wavelength, float probability) {
+    splat_photon_from(CieConstant(), accum, w, h, aspect, x, y, wavelength, probability);
 }
 
 }  // namespace rl

@@ -346,60 +346,161 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
 }
 
 // ------------------------------------------------------------------ K2 splat
-#ifndef RL_SPLAT_LOADS
-#define RL_SPLAT_LOADS 8
+// Record stream through shared memory by bulk async copies (TMA, 1-D), warp-specialised: a
+// producer warp keeps RL_SPLAT_STAGES copies of 1024 records (16 KB) in flight into a ring
+// (full/empty mbarrier per stage); eight consumer warps each lift their 128-record slice of a
+// stage into registers, hand the stage back at once and then compact and splat at their own pace.
+// The bytes in flight therefore do not depend on how far the warps have got with the records they
+// hold (with plain loads in registers the ballot chain and the occasional splat of one batch
+// delayed the loads of the next: 59 % of the HBM peak on the record stream), and no warp waits
+// for another warp's splat.
+#ifndef RL_SPLAT_STAGES
+#define RL_SPLAT_STAGES 4
 #endif
-__global__ void __launch_bounds__(256)
+#define RL_SPLAT_CHUNK 1024            // records per stage: 8 consumer warps x 4 rows x 32 lanes
+#define RL_SPLAT_CONSUMERS 8           // warps
+#define RL_SPLAT_THREADS (32 * (RL_SPLAT_CONSUMERS + 1))
+#define RL_SPLAT_LIT_SLOTS 160         // per warp: up to 31 left over + 4 x 32 new
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "RL_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra RL_MBAR_DONE;\n\t"
+        "bra RL_MBAR_WAIT;\n\t"
+        "RL_MBAR_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy, bytes a multiple of 16, both addresses 16-byte aligned; streamed
+// data: evict-first in L2 so the record stream does not push the accumulator out
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(RL_SPLAT_THREADS)
 splat_kernel(const float4 *__restrict__ records, uint64_t n, float4 *accum, int width, int height,
-             float aspect) {
-    // Streaming read of the records with RL_SPLAT_LOADS independent 16-byte loads in flight per thread
-    // (L1 bypassed: every record is used once).  Only ~8 % of the photons of the built-in scene
-    // carry light, so splatting in place would run the splat code for two or three lanes of a
-    // warp at a time: contributing records are compacted into a per-warp staging buffer with a
-    // ballot and splatted 32 at a time with every lane busy.
-    __shared__ float4 stage[8][64];
-    float4 *mine = stage[threadIdx.x >> 5];
-    const uint32_t lane = threadIdx.x & 31u, lanes_below = (1u << lane) - 1u;
-    uint32_t count = 0;                                         // warp-uniform
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);  // warp-uniform trip count
-    for (uint64_t base = first; base < n; base += RL_SPLAT_LOADS * stride) {
-        float4 ph[RL_SPLAT_LOADS];
-#pragma unroll
-        for (int k = 0; k < RL_SPLAT_LOADS; k++) {
-            const uint64_t i = base + k * stride + lane;
-            ph[k] = i < n ? __ldcs(records + i) : make_float4(0.f, 0.f, 0.f, 0.f);  // {x, y, probability, wavelength}
+             float aspect, uint32_t stages) {
+    // Only ~8 % of the photons of the built-in scene carry light, so splatting in place would run
+    // the splat code for two or three lanes of a warp at a time: contributing records are
+    // compacted into a per-warp staging buffer with ballots and splatted 32 at a time with every
+    // lane busy.  The four ballots of a round are independent of each other.
+    extern __shared__ __align__(128) unsigned char splat_smem[];
+    float4 *ring = reinterpret_cast<float4 *>(splat_smem);                       // [stages][RL_SPLAT_CHUNK]
+    float4 *lit_all = ring + (size_t)stages * RL_SPLAT_CHUNK;                    // [consumers][RL_SPLAT_LIT_SLOTS]
+    float4 *cie_tab = lit_all + RL_SPLAT_CONSUMERS * RL_SPLAT_LIT_SLOTS;         // [81 (+3 pad)] CIE table
+    uint64_t *full = reinterpret_cast<uint64_t *>(cie_tab + 84);
+    uint64_t *empty = full + stages;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, lanes_below = (1u << lane) - 1u;
+    const uint64_t n_chunks = (n + RL_SPLAT_CHUNK - 1) / RL_SPLAT_CHUNK;
+    if (tid == 0) {
+        for (uint32_t s = 0; s < stages; s++) {
+            mbar_init(full + s, 1);                       // the producer's arrive + the copy's bytes
+            mbar_init(empty + s, RL_SPLAT_CONSUMERS);     // one arrive per consumer warp
         }
-#pragma unroll
-        for (int k = 0; k < RL_SPLAT_LOADS; k++) {
-            const bool lit = ph[k].z != 0.0f;                   // adding cie * 0 changes nothing (plot_unit.rs:80-83)
-            const uint32_t mask = __ballot_sync(0xffffffffu, lit);
-            if (lit) mine[count + __popc(mask & lanes_below)] = ph[k];
-            count += __popc(mask);
-            if (count >= 32) {
-                __syncwarp();
-                const float4 r = mine[count - 32 + lane];
-                __syncwarp();
-                count -= 32;
-                splat_photon(accum, width, height, aspect, r.x, r.y, r.w, r.z);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fill_cie_shared(cie_tab);
+    const CieShared cie{cie_tab};
+    __syncthreads();
+
+    if (warp == RL_SPLAT_CONSUMERS) {
+        // producer: one lane refills a stage as soon as every consumer warp has lifted its slice
+        if (lane == 0) {
+            uint64_t policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            uint32_t s = 0, parity = 0;
+            for (uint64_t c = blockIdx.x, it = 0; c < n_chunks; c += gridDim.x, it++) {
+                if (it >= stages) mbar_wait(empty + s, parity ^ 1u);     // the stage's previous use
+                const uint64_t first = c * RL_SPLAT_CHUNK;
+                const uint32_t count = (uint32_t)(n - first < RL_SPLAT_CHUNK ? n - first : RL_SPLAT_CHUNK);
+                mbar_expect_tx(full + s, count * 16u);
+                bulk_load(ring + (size_t)s * RL_SPLAT_CHUNK, records + first, count * 16u, full + s, policy);
+                if (++s == stages) { s = 0; parity ^= 1u; }
             }
         }
+        return;
     }
-    __syncwarp();
+
+    float4 *mine = lit_all + warp * RL_SPLAT_LIT_SLOTS;
+    uint32_t count = 0;                                                          // warp-uniform
+    uint32_t s = 0, parity = 0;
+    for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        mbar_wait(full + s, parity);
+        const uint64_t first = c * RL_SPLAT_CHUNK;
+        const uint32_t valid = (uint32_t)(n - first < RL_SPLAT_CHUNK ? n - first : RL_SPLAT_CHUNK);
+        const float4 *src = ring + (size_t)s * RL_SPLAT_CHUNK + warp * 128u;
+        float4 ph[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) ph[k] = src[k * 32 + lane];                  // {x, y, probability, wavelength}
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);                                   // slice lifted: the stage may be refilled
+        if (++s == stages) { s = 0; parity ^= 1u; }
+        uint32_t mask[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)      // adding cie * 0 changes nothing (plot_unit.rs:80-83)
+            mask[k] = __ballot_sync(0xffffffffu, warp * 128u + k * 32 + lane < valid && ph[k].z != 0.0f);
+        uint32_t at = count;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (mask[k] >> lane & 1u) mine[at + __popc(mask[k] & lanes_below)] = ph[k];
+            at += __popc(mask[k]);
+        }
+        count = at;
+        __syncwarp();
+        while (count >= 32) {
+            const float4 r = mine[count - 32 + lane];
+            count -= 32;
+            splat_photon_from(cie, accum, width, height, aspect, r.x, r.y, r.w, r.z);
+        }
+        __syncwarp();
+    }
     if (lane < count) {
         const float4 r = mine[lane];
-        splat_photon(accum, width, height, aspect, r.x, r.y, r.w, r.z);
+        splat_photon_from(cie, accum, width, height, aspect, r.x, r.y, r.w, r.z);
     }
 }
 
 cudaError_t launch_splat(const rl_mapped_photon *records, uint64_t n, float4 *accum, uint32_t width,
                          uint32_t height, int sm_count, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    uint64_t want = (n + 255) / 256;
-    uint64_t full = (uint64_t)sm_count * 8;
-    unsigned grid = (unsigned)(want < full ? want : full);
-    splat_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(records), n, accum,
-                                       (int)width, (int)height, (float)width / (float)height);
+    uint32_t stages = (uint32_t)env_int("RL_SPLAT_STAGES", RL_SPLAT_STAGES);
+    if (stages < 1 || stages > 12) stages = RL_SPLAT_STAGES;
+    const size_t smem = (size_t)stages * RL_SPLAT_CHUNK * sizeof(float4)
+                        + (RL_SPLAT_CONSUMERS * RL_SPLAT_LIT_SLOTS + 84) * sizeof(float4) + 2 * stages * sizeof(uint64_t);
+    static std::mutex attr_lock;
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> guard(attr_lock);
+        cudaError_t err = cudaFuncSetAttribute(splat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err == cudaSuccess)
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, splat_kernel, RL_SPLAT_THREADS, smem);
+        if (err != cudaSuccess) return err;
+        if (per_sm < 1) per_sm = 1;
+        // one block per SM: eight consumer warps keep up with the stream, and fewer reductions in
+        // flight at once measured slightly faster than two or three blocks (tools/splat_probe.py)
+        const int cap = env_int("RL_SPLAT_BLOCKS_PER_SM", 1);
+        if (cap > 0 && cap < per_sm) per_sm = cap;
+        const uint64_t want = (n + RL_SPLAT_CHUNK - 1) / RL_SPLAT_CHUNK;
+        const uint64_t full = (uint64_t)sm_count * per_sm;
+        const unsigned grid = (unsigned)(want < full ? want : full);
+        splat_kernel<<<grid, RL_SPLAT_THREADS, smem, st>>>(reinterpret_cast<const float4 *>(records), n, accum,
+                                                           (int)width, (int)height, (float)width / (float)height,
+                                                           stages);
+    }
     g_launches++;
     return cudaGetLastError();
 }

@@ -4,6 +4,8 @@
   1  fused trace+splat, built-in scene, 1024^2, 2^24 photons: the bench configuration (768 x 1)
   2  one reference batch (524 288 photons) into records: the small-launch configuration (256 x 3)
   3  splat of those records
+  4  trace of 2^25 photons into records (512 MiB)
+  5  splat of 2^25 records: the configuration bench.py times for K2
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -21,5 +23,10 @@ tu.sync()
 tu.render_range(scene, 1 << 26, 524288, download=False)
 tu.sync()
 pl.plot(tu)
+pl.sync()
+big = pkg.TraceUnit(1, W, H, seed=0x5EED, batch=1 << 25)
+big.render_range(scene, 0, 1 << 25, download=False)
+big.sync()
+pl.plot(big)
 pl.sync()
 print("rays", tu.ray_count())
