@@ -198,6 +198,35 @@ def test_empty_and_ragged_batches(gpu, orc):
         assert_records_equal(got, want, f"ragged n={n}")
 
 
+def test_page_locked_host_buffers_and_transfer_counters(gpu, orc):
+    # the shim page-locks a unit's Vec once (rl_host_register); results are the same bytes, and
+    # the ABI counts what crosses the host/device boundary (bench.py's h2d/d2h bytes per step)
+    import ctypes as C
+    b = gpu.SceneBuilder(1)
+    sc = gpu.Scene(b)
+    n = 8192
+    tu = gpu.TraceUnit(0, 96, 64, seed=SEED, batch=n)
+    pinned = np.zeros(n, dtype=gpu.MAPPED_PHOTON)
+    ptr = pinned.ctypes.data_as(C.c_void_p)
+    assert gpu.lib().rl_host_register(ptr, pinned.nbytes) == gpu.RL_OK
+    assert gpu.lib().rl_host_register(ptr, pinned.nbytes) == gpu.RL_OK          # idempotent per address
+    gpu.reset_transfer_counters()
+    tu.render_range(sc, 0, n, out=pinned)
+    plain = tu.render_range(sc, 0, n).copy()
+    assert gpu.transfer_counters() == (0, 2 * n * 16)
+    assert_records_equal(pinned, plain, "page-locked vs pageable destination")
+    assert_records_equal(pinned, orc.trace(b.desc(), SEED, 96, 64, 0, n), "page-locked destination")
+    pl = gpu.PlotUnit(0, 96, 64)
+    pl.plot(pinned)
+    h2d, d2h = gpu.transfer_counters()
+    assert h2d == n * 16 and d2h == 2 * n * 16
+    pl.download()
+    assert gpu.transfer_counters() == (n * 16, 2 * n * 16 + 96 * 64 * 12)
+    assert gpu.lib().rl_host_unregister(ptr) == gpu.RL_OK
+    assert gpu.lib().rl_host_unregister(ptr) == gpu.RL_OK                        # not registered: not an error
+    assert gpu.lib().rl_host_register(None, 16) == gpu.RL_ERR_INVALID
+
+
 def test_launch_geometry_does_not_change_results(gpu, monkeypatch):
     # block size, share of the SMs' block slots and the order in which a block's pool hands
     # out photon ids are scheduling only: records and ray counts are bit-equal under every policy
