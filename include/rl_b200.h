@@ -194,6 +194,14 @@ int rl_trace_unit_set_stream(rl_trace_unit *unit, void *cuda_stream);
  * it receives batch_size records (the shim's `mapped_photons` Vec) and the
  * call blocks; with NULL the records stay on the device for plot_device. */
 int rl_trace_unit_render(rl_trace_unit *unit, const rl_scene *scene, rl_mapped_photon *out);
+/* The same call without the wait: the kernel and the copy into `out` are
+ * queued on the unit's stream and the call returns; `out` (page-locked by
+ * rl_host_register, or the copy degrades to a blocking one) is valid after
+ * rl_trace_unit_sync.  The shim makes `mapped_photons` a buffer that waits when
+ * it is first read, so a worker thread hands the GPU a batch
+ * and goes on to its next task: the GPU's queue is then as deep as the 3C trace
+ * units of task_scheduler.rs:100, not as the C worker threads. */
+int rl_trace_unit_render_async(rl_trace_unit *unit, const rl_scene *scene, rl_mapped_photon *out);
 /* Same, for an explicit photon-id range [first_photon, first_photon + n). */
 int rl_trace_unit_render_range(rl_trace_unit *unit, const rl_scene *scene,
                                uint64_t first_photon, uint64_t n_photons,

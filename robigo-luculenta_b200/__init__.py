@@ -110,6 +110,7 @@ SYMBOLS = {
     "rl_trace_unit_set_batch_size": (_I, [_P, _U64]),
     "rl_trace_unit_set_stream": (_I, [_P, _P]),
     "rl_trace_unit_render": (_I, [_P, _P, _P]),
+    "rl_trace_unit_render_async": (_I, [_P, _P, _P]),
     "rl_trace_unit_render_range": (_I, [_P, _P, _U64, _U64, _P]),
     "rl_trace_unit_render_fused": (_I, [_P, _P, _P, _U64, _U64]),
     "rl_trace_unit_ray_count": (_I, [_P, C.POINTER(_U64)]),
@@ -354,12 +355,15 @@ class TraceUnit:
     def set_stream(self, cuda_stream):
         _check(lib().rl_trace_unit_set_stream(self._h, _P(cuda_stream)))
 
-    def render(self, scene, download=True):
-        """TraceUnit::render (trace_unit.rs:151-168); fills `mapped_photons`."""
+    def render(self, scene, download=True, wait=True):
+        """TraceUnit::render (trace_unit.rs:151-168); fills `mapped_photons`.  With
+        wait=False the batch is only queued (rl_trace_unit_render_async): call sync()
+        before reading `mapped_photons`."""
         if download:
             if self.mapped_photons.shape[0] != self.batch:
                 self.mapped_photons = np.zeros(self.batch, dtype=MAPPED_PHOTON)
-            _check(lib().rl_trace_unit_render(self._h, scene._h, _ptr(self.mapped_photons)))
+            fn = lib().rl_trace_unit_render if wait else lib().rl_trace_unit_render_async
+            _check(fn(self._h, scene._h, _ptr(self.mapped_photons)))
         else:
             _check(lib().rl_trace_unit_render(self._h, scene._h, None))
 

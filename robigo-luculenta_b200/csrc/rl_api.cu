@@ -655,8 +655,8 @@ static int ensure_records(rl_trace_unit *u, uint64_t n) {
     return RL_OK;
 }
 
-int rl_trace_unit_render_range(rl_trace_unit *u, const rl_scene *scene, uint64_t first_photon,
-                               uint64_t n_photons, rl_mapped_photon *out) {
+static int render_range(rl_trace_unit *u, const rl_scene *scene, uint64_t first_photon,
+                        uint64_t n_photons, rl_mapped_photon *out, bool wait) {
     if (!u || !scene) return fail(RL_ERR_INVALID, "rl_trace_unit_render: null argument");
     if (scene->dev.index != u->dev.index) return fail(RL_ERR_INVALID, "scene and unit on different devices");
     RL_CUDA(cudaSetDevice(u->dev.index));
@@ -671,15 +671,26 @@ int rl_trace_unit_render_range(rl_trace_unit *u, const rl_scene *scene, uint64_t
     if (out) {
         RL_CUDA(copy_async(out, u->d_records, n_photons * sizeof(rl_mapped_photon),
                                 cudaMemcpyDeviceToHost, u->ss.stream));
-        RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+        if (wait) RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     }
     return RL_OK;
+}
+
+int rl_trace_unit_render_range(rl_trace_unit *u, const rl_scene *scene, uint64_t first_photon,
+                               uint64_t n_photons, rl_mapped_photon *out) {
+    return render_range(u, scene, first_photon, n_photons, out, true);
 }
 
 int rl_trace_unit_render(rl_trace_unit *u, const rl_scene *scene, rl_mapped_photon *out) {
     if (!u) return fail(RL_ERR_INVALID, "null unit");
     const uint64_t b = g_next_batch.fetch_add(1);
-    return rl_trace_unit_render_range(u, scene, b * u->batch, u->batch, out);
+    return render_range(u, scene, b * u->batch, u->batch, out, true);
+}
+
+int rl_trace_unit_render_async(rl_trace_unit *u, const rl_scene *scene, rl_mapped_photon *out) {
+    if (!u) return fail(RL_ERR_INVALID, "null unit");
+    const uint64_t b = g_next_batch.fetch_add(1);
+    return render_range(u, scene, b * u->batch, u->batch, out, false);
 }
 
 int rl_trace_unit_render_fused(rl_trace_unit *u, const rl_scene *scene, rl_plot_unit *plot,

@@ -44,9 +44,13 @@ template <typename T> inline void unpin(std::vector<T> &v) {
 // a plot task plots a dozen trace units into one plot unit (task_scheduler.rs:192-207) before
 // anybody looks at the result.  Reads go through the conversions below, which is where a Rust
 // shim puts `impl Deref<Target = [Vector3]>` -- `&unit.tristimulus_buffer` at the call sites
-// of app.rs coerces to `&[Vector3]` unchanged.  `lazy_host_mirrors() = false` copies back
+// of app.rs coerces to `&[Vector3]` unchanged.  `mapped_photons` of TraceUnit (trace_unit.rs:56)
+// is the same kind of field: render() queues the kernel and the copy into it, the first read
+// (app.rs:139, in a later plot task) waits for them.  `lazy_host_mirrors() = false` copies back
 // eagerly after every change instead (A/B measurements).
 inline bool &lazy_host_mirrors() { static bool on = true; return on; }
+// TraceUnit::render returns once the batch is queued (true) or once `mapped_photons` is filled
+inline bool &async_render() { static bool on = true; return on; }
 template <typename T> class HostMirror {
 public:
     using Download = std::function<void(T *)>;
@@ -66,6 +70,7 @@ public:
         if (!lazy_host_mirrors()) sync();
     }
     const std::vector<T> &get() const { sync(); return storage_; }
+    T *destination() { return storage_.data(); }       // where the device copy lands (no wait)
     operator const std::vector<T> &() const { return get(); }
     const T *data() const { return get().data(); }
     size_t size() const { return storage_.size(); }
@@ -108,17 +113,21 @@ public:
         : id(id_), keep_on_device_(keep_on_device) {
         expect(rl_trace_unit_create(id_, width, height, seed, &handle_), "rl_trace_unit_create");
         expect(rl_trace_unit_set_batch_size(handle_, batch), "rl_trace_unit_set_batch_size");
-        if (!keep_on_device) mapped_photons.assign(batch, MappedPhoton{0.f, 0.f, 0.f, 0.f});
-        pin(mapped_photons);
+        if (!keep_on_device)
+            mapped_photons.init(batch, [this](MappedPhoton *) { expect(rl_trace_unit_sync(handle_), "rl_trace_unit_sync"); });
     }
-    ~TraceUnit() { rl_trace_unit_destroy(handle_); unpin(mapped_photons); }
+    ~TraceUnit() { rl_trace_unit_destroy(handle_); }
     TraceUnit(const TraceUnit &) = delete;
     TraceUnit &operator=(const TraceUnit &) = delete;
 
-    // trace_unit.rs:151-168
+    // trace_unit.rs:151-168.  The batch is queued (kernel, then the copy into the page-locked
+    // `mapped_photons`) and the call returns; whoever reads `mapped_photons` first waits for it
+    // (app.rs:139 in the plot task), so the worker thread is free for its next task meanwhile.
     void render(const Scene &scene) {
-        expect(rl_trace_unit_render(handle_, scene.handle(), keep_on_device_ ? nullptr : mapped_photons.data()),
+        expect(rl_trace_unit_render_async(handle_, scene.handle(), keep_on_device_ ? nullptr : mapped_photons.destination()),
                "rl_trace_unit_render");
+        mapped_photons.invalidate();
+        if (!async_render() && !keep_on_device_) mapped_photons.get();
     }
     uint64_t ray_count() {
         uint64_t n = 0;
@@ -127,7 +136,7 @@ public:
     }
     rl_trace_unit *handle() { return handle_; }
 
-    std::vector<MappedPhoton> mapped_photons;          // trace_unit.rs:56
+    HostMirror<MappedPhoton> mapped_photons;           // trace_unit.rs:56
     size_t id;                                         // trace_unit.rs:59
 
 private:

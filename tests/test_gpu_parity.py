@@ -227,6 +227,24 @@ def test_page_locked_host_buffers_and_transfer_counters(gpu, orc):
     assert gpu.lib().rl_host_register(None, 16) == gpu.RL_ERR_INVALID
 
 
+def test_render_async_fills_the_buffer_behind_the_call(gpu, orc):
+    # rl_trace_unit_render_async queues kernel + copy and returns; after sync() the buffers hold
+    # exactly what the blocking call delivers, whatever the order the units were queued in
+    b = gpu.SceneBuilder(2)
+    sc = gpu.Scene(b)
+    n = 30000
+    gpu.reset_batch_counter(40)
+    units = [gpu.TraceUnit(i, 200, 120, seed=SEED, batch=n) for i in range(5)]
+    for u in units:
+        u.render(sc, wait=False)                    # batches 40..44, one per unit, all in flight
+    for u in reversed(units):
+        u.sync()
+    want = orc.trace(b.desc(), SEED, 200, 120, 40 * n, 5 * n)
+    for i, u in enumerate(units):
+        assert_records_equal(u.mapped_photons, want[i * n:(i + 1) * n], f"async unit {i}")
+    gpu.reset_batch_counter(0)
+
+
 def test_launch_geometry_does_not_change_results(gpu, monkeypatch):
     # block size, share of the SMs' block slots and the order in which a block's pool hands
     # out photon ids are scheduling only: records and ray counts are bit-equal under every policy

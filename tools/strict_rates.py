@@ -79,8 +79,8 @@ if "--replay" in sys.argv:
     batches = "2048"
     # (policy knobs, mode, page-locked host buffers, lazy host mirrors, worker threads)
     runs = [(None, "strict", 1, 1, threads), (None, "strict", 1, 0, threads), (None, "strict", 0, 0, threads),
-            (None, "device", 1, 1, threads), (None, "strict", 1, 1, 4), (None, "device", 1, 1, 4),
-            ((0, 256, 0), "strict", 1, 1, threads), ((0, 256, 0), "device", 1, 1, threads)]
+            (None, "device", 1, 1, threads), (None, "strict", 1, 1, 8), (None, "strict", 1, 1, 4),
+            (None, "strict", 1, 1, 2), (None, "device", 1, 1, 4), ((0, 256, 0), "strict", 1, 1, threads)]
     for knobs, mode, pin, lazy, thr in runs:
         clear_policy()
         if knobs:
