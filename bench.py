@@ -113,6 +113,61 @@ class DeviceView:
         self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_pci_address(torch, index):
+    """sysfs name of the GPU's PCI function (dddd:bb:dd.f), '' if it cannot be found."""
+    props = torch.cuda.get_device_properties(index)
+    try:
+        return f"{int(props.pci_domain_id):04x}:{int(props.pci_bus_id):02x}:{int(props.pci_device_id):02x}.0"
+    except (AttributeError, TypeError, ValueError):
+        pass
+    try:
+        out = subprocess.run(["nvidia-smi", f"--id={index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if out.count(":") == 2:
+            dom, bus, rest = out.split(":")
+            return f"{dom[-4:]}:{bus}:{rest}"
+    except (OSError, subprocess.SubprocessError):
+        pass
+    return ""
+
+
+def host_cpus_for_rank(local_rank, world, pci_bus_id):
+    """The CPUs rank `local_rank`'s host-side work should run on: its share of the cores of the
+    NUMA node its GPU hangs off (so that the page-locked buffers it allocates, and the DMA to and
+    from them, stay on that socket), else an even share of the allowed cores."""
+    allowed = sorted(os.sched_getaffinity(0))
+    node = -1
+    try:
+        with open(f"/sys/bus/pci/devices/{pci_bus_id.lower()}/numa_node") as f:
+            node = int(f.read().strip())
+    except (OSError, ValueError):
+        pass
+    if node >= 0:
+        try:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                local = sorted(_parse_cpulist(f.read()) & set(allowed))
+            n_nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+            per_node = max(1, (world + n_nodes - 1) // n_nodes)          # ranks sharing this node
+            if len(local) >= per_node:
+                share = len(local) // per_node
+                k = local_rank % per_node
+                return local[k * share:(k + 1) * share], node
+        except OSError:
+            pass
+    share = max(1, len(allowed) // world)
+    return allowed[local_rank * share:(local_rank + 1) * share] or allowed, node
+
+
 def cpu_reference_run(orc, desc, n_photons, threads, first=0):
     """The reference's CPU pipeline shape on host threads (oracle port, glibc math)."""
     # the bounded sample is cut into 8 batches per thread (the reference's 524 288-photon batch
@@ -361,7 +416,11 @@ def main():
     # buffer.raw flush) weigh as they do in a long render
     e2e_steps = min(max(args.steps, 4), 16)
     replay_batches = e2e_steps * (n // 524288)
-    workers = max(2, min(16, (os.cpu_count() or 8) // world))
+    # one replay process per GPU, pinned to its share of the cores next to that GPU
+    pci = gpu_pci_address(torch, local_rank)
+    cpus, numa_node = (host_cpus_for_rank(local_rank, world, pci) if world > 1
+                       else (sorted(os.sched_getaffinity(0)), -1))
+    workers = max(2, min(16, len(cpus)))
     exe = entry.build_replay()
     out_prefix = f"/tmp/rl_bench_replay_{os.getpid()}"
     cmd = [exe, "--width", str(WIDTH), "--height", str(HEIGHT), "--threads", str(workers), "--batches",
@@ -370,7 +429,8 @@ def main():
     visible = os.environ.get("CUDA_VISIBLE_DEVICES")
     env = dict(os.environ, CUDA_VISIBLE_DEVICES=visible.split(",")[local_rank] if visible else str(local_rank))
     barrier()
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1200)
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1200,
+                         preexec_fn=(lambda: os.sched_setaffinity(0, cpus)) if world > 1 else None)
     if res.returncode != 0:
         raise RuntimeError("rl_replay failed: " + res.stderr[-500:])
     replay = json.loads(res.stdout.strip().splitlines()[-1])
@@ -399,6 +459,7 @@ def main():
            "h2d_bytes_per_step": (int(r[1]) + frame_bytes * world) // e2e_steps,
            "d2h_bytes_per_step": (int(r[2]) + frame_bytes) // e2e_steps,
            "steps": e2e_steps, "batches_per_step_per_gpu": n // 524288, "worker_threads_per_gpu": workers,
+           "host_cpus_rank0": f"{len(cpus)} cores" + (f" of NUMA node {numa_node}" if numa_node >= 0 else ""),
            "seconds": float(t[0]),
            "path": "strict mode: the reference host's call pattern replayed against the C ABI with host buffers "
                    "(host/rl_replay.cpp; app.rs:95-164, task_scheduler.rs:91-182): 524 288-photon TraceUnit::render "
