@@ -428,12 +428,27 @@ def main():
            "--out", out_prefix, "--first-batch", str(rank * replay_batches)]
     visible = os.environ.get("CUDA_VISIBLE_DEVICES")
     env = dict(os.environ, CUDA_VISIBLE_DEVICES=visible.split(",")[local_rank] if visible else str(local_rank))
-    barrier()
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1200,
-                         preexec_fn=(lambda: os.sched_setaffinity(0, cpus)) if world > 1 else None)
-    if res.returncode != 0:
-        raise RuntimeError("rl_replay failed: " + res.stderr[-500:])
-    replay = json.loads(res.stdout.strip().splitlines()[-1])
+    def run_replay(extra):
+        barrier()
+        res = subprocess.run(cmd + extra, capture_output=True, text=True, env=env, timeout=1200,
+                             preexec_fn=(lambda: os.sched_setaffinity(0, cpus)) if world > 1 else None)
+        if res.returncode != 0:
+            raise RuntimeError("rl_replay failed: " + res.stderr[-500:])
+        return json.loads(res.stdout.strip().splitlines()[-1])
+
+    # the same unchanged call sites with the records left on the device until host code reads them
+    # (PlotUnit::plot recognises `&unit.mapped_photons` by its type: INTEGRATION.md, rl_units.hpp)
+    deferred = run_replay(["--records", "deferred"])
+    t = torch.tensor([deferred["seconds"]], dtype=torch.float64, device="cuda")
+    r = torch.tensor([deferred["rays"], deferred["h2d_bytes"], deferred["d2h_bytes"]], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    e2e_deferred = {"value": int(r[0]) / float(t[0]) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(r[1]) // e2e_steps,
+                    "d2h_bytes_per_step": int(r[2]) // e2e_steps, "steps": e2e_steps,
+                    "path": "the strict-mode replay with `mapped_photons` copied out only when host code reads it "
+                            "(never, in app.rs): frames and buffer.raw still cross PCIe; per-rank frames not combined"}
+    replay = run_replay([])
     combine_s = 0.0
     if world > 1:
         t0 = time.perf_counter()
@@ -583,6 +598,7 @@ def main():
         "batches_per_s": n * world * args.steps / (step_ms * 1e-3) / 524288,
         "clocks": clocks,
         "e2e": e2e,
+        "e2e_deferred_records": e2e_deferred,
         "e2e_device": e2e_device,
         "gpu_launches": launches,
         "roofline": roofline,

@@ -202,6 +202,10 @@ int rl_trace_unit_render(rl_trace_unit *unit, const rl_scene *scene, rl_mapped_p
  * and goes on to its next task: the GPU's queue is then as deep as the 3C trace
  * units of task_scheduler.rs:100, not as the C worker threads. */
 int rl_trace_unit_render_async(rl_trace_unit *unit, const rl_scene *scene, rl_mapped_photon *out);
+/* Copy the records of the last render out of the device (blocking); lets the
+ * shim leave them there (`out` = NULL above) until host code really reads
+ * `mapped_photons`. */
+int rl_trace_unit_download(rl_trace_unit *unit, rl_mapped_photon *out);
 /* Same, for an explicit photon-id range [first_photon, first_photon + n). */
 int rl_trace_unit_render_range(rl_trace_unit *unit, const rl_scene *scene,
                                uint64_t first_photon, uint64_t n_photons,

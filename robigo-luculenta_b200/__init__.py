@@ -111,6 +111,7 @@ SYMBOLS = {
     "rl_trace_unit_set_stream": (_I, [_P, _P]),
     "rl_trace_unit_render": (_I, [_P, _P, _P]),
     "rl_trace_unit_render_async": (_I, [_P, _P, _P]),
+    "rl_trace_unit_download": (_I, [_P, _P]),
     "rl_trace_unit_render_range": (_I, [_P, _P, _U64, _U64, _P]),
     "rl_trace_unit_render_fused": (_I, [_P, _P, _P, _U64, _U64]),
     "rl_trace_unit_ray_count": (_I, [_P, C.POINTER(_U64)]),
@@ -366,6 +367,14 @@ class TraceUnit:
             _check(fn(self._h, scene._h, _ptr(self.mapped_photons)))
         else:
             _check(lib().rl_trace_unit_render(self._h, scene._h, None))
+
+    def download(self, out=None):
+        """Records of the last render, copied out of the device now (rl_trace_unit_download)."""
+        if out is None:
+            out = np.zeros(self.batch, dtype=MAPPED_PHOTON)
+        _check(lib().rl_trace_unit_download(self._h, _ptr(out)))
+        self.mapped_photons = out
+        return out
 
     def render_range(self, scene, first_photon, n_photons, download=True, out=None):
         if download:

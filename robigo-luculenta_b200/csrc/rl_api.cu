@@ -693,6 +693,16 @@ int rl_trace_unit_render_async(rl_trace_unit *u, const rl_scene *scene, rl_mappe
     return render_range(u, scene, b * u->batch, u->batch, out, false);
 }
 
+int rl_trace_unit_download(rl_trace_unit *u, rl_mapped_photon *out) {
+    if (!u || !out) return fail(RL_ERR_INVALID, "rl_trace_unit_download: null argument");
+    RL_CUDA(cudaSetDevice(u->dev.index));
+    if (u->n_valid)
+        RL_CUDA(copy_async(out, u->d_records, u->n_valid * sizeof(rl_mapped_photon), cudaMemcpyDeviceToHost,
+                           u->ss.stream));
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    return RL_OK;
+}
+
 int rl_trace_unit_render_fused(rl_trace_unit *u, const rl_scene *scene, rl_plot_unit *plot,
                                uint64_t first_photon, uint64_t n_photons) {
     if (!u || !scene || !plot) return fail(RL_ERR_INVALID, "rl_trace_unit_render_fused: null argument");

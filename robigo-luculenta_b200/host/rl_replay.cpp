@@ -11,6 +11,7 @@
 //
 //   rl_replay --width W --height H --threads C --batches B [--batch N] [--seed S]
 //             [--mode strict|device] [--scene 1..4] [--out PREFIX] [--pin 0|1] [--lazy 0|1] [--async-render 0|1]
+//             [--records host|deferred]
 //             [--first-batch K]
 // --first-batch: photon ids start at K * batch (a second process -- another GPU -- continues
 // the id range of the first).
@@ -215,6 +216,7 @@ int main(int argc, char **argv) {
     pin_host_buffers() = atoi(arg(argc, argv, "--pin", "1")) != 0;
     lazy_host_mirrors() = atoi(arg(argc, argv, "--lazy", "1")) != 0;
     async_render() = atoi(arg(argc, argv, "--async-render", "1")) != 0;
+    deferred_records() = !strcmp(arg(argc, argv, "--records", "host"), "deferred");
 
     try {
         rl_scene_builder *builder = nullptr;
@@ -272,11 +274,12 @@ int main(int argc, char **argv) {
             fclose(f);
         }
         const uint64_t rays = scheduler.rays();
-        printf("{\"mode\": \"%s\", \"pinned\": %s, \"lazy\": %s, \"async_render\": %s, \"width\": %u, \"height\": %u, \"threads\": %zu, \"batches\": %llu, \"batch\": %llu, \"seconds\": %.6f, "
+        printf("{\"mode\": \"%s\", \"pinned\": %s, \"lazy\": %s, \"async_render\": %s, \"records\": \"%s\", \"width\": %u, \"height\": %u, \"threads\": %zu, \"batches\": %llu, \"batch\": %llu, \"seconds\": %.6f, "
                "\"batches_per_s\": %.3f, \"rays\": %llu, \"mrays_per_s\": %.3f, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"worker_seconds\": {\"sleep\": [%llu, %.3f], "
                "\"trace\": [%llu, %.3f], \"plot\": [%llu, %.3f], \"gather\": [%llu, %.3f], \"tonemap\": [%llu, %.3f]}}\n",
                device ? "device" : "strict", pin_host_buffers() ? "true" : "false",
-               lazy_host_mirrors() ? "true" : "false", async_render() ? "true" : "false", w, h, threads, (unsigned long long)scheduler.traces_completed(),
+               lazy_host_mirrors() ? "true" : "false", async_render() ? "true" : "false",
+               deferred_records() ? "deferred" : "host", w, h, threads, (unsigned long long)scheduler.traces_completed(),
                (unsigned long long)batch, seconds, scheduler.traces_completed() / seconds,
                (unsigned long long)rays, rays / seconds / 1e6, (unsigned long long)h2d, (unsigned long long)d2h,
                (unsigned long long)g_stats[0].calls, g_stats[0].ns * 1e-9, (unsigned long long)g_stats[1].calls,

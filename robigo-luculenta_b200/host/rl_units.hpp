@@ -51,6 +51,10 @@ template <typename T> inline void unpin(std::vector<T> &v) {
 inline bool &lazy_host_mirrors() { static bool on = true; return on; }
 // TraceUnit::render returns once the batch is queued (true) or once `mapped_photons` is filled
 inline bool &async_render() { static bool on = true; return on; }
+// `mapped_photons` is copied out of the device by render() (false: the records cross PCIe twice,
+// as a literal reading of app.rs:133-139 has it) or only when host code reads it (true:
+// PlotUnit::plot recognises the field by its type and splats from the device records)
+inline bool &deferred_records() { static bool on = false; return on; }
 template <typename T> class HostMirror {
 public:
     using Download = std::function<void(T *)>;
@@ -71,6 +75,9 @@ public:
     }
     const std::vector<T> &get() const { sync(); return storage_; }
     T *destination() { return storage_.data(); }       // where the device copy lands (no wait)
+    // the unit whose device buffer this field mirrors, while that buffer is newer than the host copy
+    void set_owner(void *unit_handle) { owner_ = unit_handle; }
+    void *device_owner() const { return stale_ && deferred_records() ? owner_ : nullptr; }
     operator const std::vector<T> &() const { return get(); }
     const T *data() const { return get().data(); }
     size_t size() const { return storage_.size(); }
@@ -89,6 +96,7 @@ private:
     mutable std::vector<T> storage_;
     mutable bool stale_ = false;
     Download download_;
+    void *owner_ = nullptr;
 };
 
 // Stands in for Arc<Scene> (app.rs:63): the flattened scene on the device.
@@ -113,8 +121,13 @@ public:
         : id(id_), keep_on_device_(keep_on_device) {
         expect(rl_trace_unit_create(id_, width, height, seed, &handle_), "rl_trace_unit_create");
         expect(rl_trace_unit_set_batch_size(handle_, batch), "rl_trace_unit_set_batch_size");
-        if (!keep_on_device)
-            mapped_photons.init(batch, [this](MappedPhoton *) { expect(rl_trace_unit_sync(handle_), "rl_trace_unit_sync"); });
+        if (!keep_on_device) {
+            mapped_photons.init(batch, [this](MappedPhoton *dst) {
+                if (deferred_records()) expect(rl_trace_unit_download(handle_, dst), "rl_trace_unit_download");
+                else expect(rl_trace_unit_sync(handle_), "rl_trace_unit_sync");
+            });
+            mapped_photons.set_owner(handle_);
+        }
     }
     ~TraceUnit() { rl_trace_unit_destroy(handle_); }
     TraceUnit(const TraceUnit &) = delete;
@@ -124,7 +137,8 @@ public:
     // `mapped_photons`) and the call returns; whoever reads `mapped_photons` first waits for it
     // (app.rs:139 in the plot task), so the worker thread is free for its next task meanwhile.
     void render(const Scene &scene) {
-        expect(rl_trace_unit_render_async(handle_, scene.handle(), keep_on_device_ ? nullptr : mapped_photons.destination()),
+        expect(rl_trace_unit_render_async(handle_, scene.handle(),
+                                          keep_on_device_ || deferred_records() ? nullptr : mapped_photons.destination()),
                "rl_trace_unit_render");
         mapped_photons.invalidate();
         if (!async_render() && !keep_on_device_) mapped_photons.get();
@@ -163,6 +177,18 @@ public:
     void plot(const std::vector<MappedPhoton> &photons) {
         expect(rl_plot_unit_plot(handle_, photons.data(), photons.size()), "rl_plot_unit_plot");
         tristimulus_buffer.invalidate();
+    }
+    // `plot(&unit.mapped_photons)` as app.rs:139 writes it: the argument is the trace unit's own
+    // field, recognised by its type (Rust: `plot<P: AsPhotons + ?Sized>(&mut self, photons: &P)`,
+    // implemented for [MappedPhoton] and for HostMirror<MappedPhoton>).  While the device records
+    // are newer than the host copy they are splatted where they are; no byte crosses PCIe.
+    void plot(const HostMirror<MappedPhoton> &photons) {
+        if (void *owner = photons.device_owner()) {
+            expect(rl_plot_unit_plot_device(handle_, static_cast<rl_trace_unit *>(owner)), "rl_plot_unit_plot_device");
+            tristimulus_buffer.invalidate();
+        } else {
+            plot(photons.get());
+        }
     }
     // the same on records a trace unit left on the device
     void plot(TraceUnit &unit) {

@@ -13,17 +13,24 @@ import __graft_entry__ as entry
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("mode,threads", [("strict", 4), ("device", 4), ("strict", 1), ("device", 7)])
-def test_scheduler_replay_matches_oracle(gpu, orc, tmp_path, mode, threads):
+# strict: host buffers as app.rs:132-164 passes them; "deferred": the same unchanged call sites,
+# the records leave the device only if host code reads them (PlotUnit::plot recognises the trace
+# unit's own field); the extra flags switch the page-locking, lazy mirrors and queued render off
+@pytest.mark.parametrize("mode,threads,extra", [
+    ("strict", 4, []), ("device", 4, []), ("strict", 1, []), ("device", 7, []),
+    ("strict", 5, ["--records", "deferred"]), ("strict", 2, ["--records", "deferred", "--lazy", "0"]),
+    ("strict", 3, ["--pin", "0", "--lazy", "0", "--async-render", "0"])])
+def test_scheduler_replay_matches_oracle(gpu, orc, tmp_path, mode, threads, extra):
     exe = entry.build_replay()
     w, h, batch, batches, seed = 320, 180, 4096, 24, 24301
     out = str(tmp_path / f"replay_{mode}")
     res = subprocess.run([exe, "--width", str(w), "--height", str(h), "--threads", str(threads), "--batches",
                           str(batches), "--batch", str(batch), "--seed", str(seed), "--mode", mode, "--scene", "2",
-                          "--out", out], capture_output=True, text=True, timeout=600)
+                          "--out", out] + extra, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr
     stats = json.loads(res.stdout.strip().splitlines()[-1])
     assert stats["batches"] == batches and stats["mode"] == mode
+    assert stats["records"] == ("deferred" if "deferred" in extra else "host")
     # whichever unit rendered which batch, the union of photons is ids [0, batches * batch)
     d = gpu.SceneBuilder(2).desc()
     ct = orc.Counters()
