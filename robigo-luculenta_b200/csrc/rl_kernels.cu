@@ -216,49 +216,52 @@ static size_t trace_kernel_smem_bytes(const DevScene &sc, int threads) {
     return tracing_smem_bytes(sc, threads) + (RL_SORT_PATHS ? (size_t)RL_SORT_BYTES_PER_THREAD * threads : 0);
 }
 
-// Small launches in flight, one entry per launch: an event recorded behind the kernel on the
-// unit's stream.  launch_trace (under its lock) drops the completed ones and counts the other
-// streams that still have a small launch queued or running -- the concurrency the host's worker
-// threads are producing right now (app.rs:95-111 runs C of them over 3C trace units).
-struct SmallLaunch { cudaEvent_t done; cudaStream_t stream; int device; };
-static std::vector<SmallLaunch> g_small_inflight;
-static std::vector<SmallLaunch> g_small_events;   // recycled events (stream unused)
+// Small launches in flight: one mark per stream, an event re-recorded behind that stream's latest
+// small launch.  launch_trace (under its lock) counts the OTHER streams whose mark has not
+// completed -- the concurrency the host's worker threads are producing right now (app.rs:95-111
+// runs C of them over 3C trace units) -- and stops at the number that already gives the smallest
+// share, scanning from where it last found one in flight: two or three event queries per launch
+// in the steady state, however many units there are.
+struct StreamMark { cudaStream_t stream; int device; cudaEvent_t done; };
+static std::vector<StreamMark> g_marks;
+static size_t g_scan_from = 0;
 
-static int other_streams_in_flight(int device, cudaStream_t mine) {
-    std::vector<cudaStream_t> seen;
-    size_t keep = 0;
-    for (size_t i = 0; i < g_small_inflight.size(); i++) {
-        const SmallLaunch l = g_small_inflight[i];
-        if (cudaEventQuery(l.done) == cudaErrorNotReady) {
-            g_small_inflight[keep++] = l;
-            if (l.device == device && l.stream != mine) {
-                bool dup = false;
-                for (cudaStream_t s : seen) dup |= s == l.stream;
-                if (!dup) seen.push_back(l.stream);
-            }
-        } else {
-            g_small_events.push_back(l);
+static int other_streams_in_flight(int device, cudaStream_t mine, int enough) {
+    const size_t n = g_marks.size();
+    int found = 0;
+    for (size_t k = 0; k < n && found < enough; k++) {
+        const size_t i = (g_scan_from + k) % n;
+        const StreamMark &m = g_marks[i];
+        if (m.device != device || m.stream == mine) continue;
+        if (cudaEventQuery(m.done) == cudaErrorNotReady) {
+            if (found == 0) g_scan_from = i;
+            found++;
         }
     }
-    g_small_inflight.resize(keep);
     cudaGetLastError();   // cudaErrorNotReady is not an error
-    return (int)seen.size();
+    return found;
 }
 
 static void note_small_launch(int device, cudaStream_t st) {
-    SmallLaunch l{nullptr, st, device};
-    for (size_t i = 0; i < g_small_events.size(); i++)
-        if (g_small_events[i].device == device) {
-            l.done = g_small_events[i].done;
-            g_small_events.erase(g_small_events.begin() + i);
-            break;
+    for (StreamMark &m : g_marks)
+        if (m.stream == st && m.device == device) {
+            if (cudaEventRecord(m.done, st) != cudaSuccess) cudaGetLastError();
+            return;
         }
-    if (!l.done && cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming) != cudaSuccess) {
+    if (g_marks.size() >= 4096) {                       // streams of units long gone: forget the finished ones
+        size_t keep = 0;
+        for (size_t i = 0; i < g_marks.size(); i++) {
+            if (cudaEventQuery(g_marks[i].done) == cudaErrorNotReady) g_marks[keep++] = g_marks[i];
+            else cudaEventDestroy(g_marks[i].done);
+        }
+        g_marks.resize(keep);
+        g_scan_from = 0;
         cudaGetLastError();
-        return;
     }
-    if (cudaEventRecord(l.done, st) == cudaSuccess) g_small_inflight.push_back(l);
-    else { cudaGetLastError(); g_small_events.push_back(l); }
+    StreamMark m{st, device, nullptr};
+    if (cudaEventCreateWithFlags(&m.done, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaEventRecord(m.done, st) == cudaSuccess) g_marks.push_back(m);
+    else { cudaGetLastError(); cudaEventDestroy(m.done); }
 }
 
 static int env_int(const char *name, int fallback) {
@@ -274,10 +277,22 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     std::lock_guard<std::mutex> guard(launch_lock);
     // the largest CTA (up to RL_TRACE_THREADS) whose tables + scratch fit the shared memory of an SM:
     // big CTAs fill the per-CTA task list of the body evaluation best
-    int dev = 0, max_smem = 0;
+    // what the attribute calls last set, per device: thousands of identical small launches per
+    // second should not each pay for three driver round trips while holding the lock
+    struct Cached { int max_smem = 0, threads = 0, per_sm = 0, pct = -2; size_t smem = 0; };
+    static Cached cache[16];
+    int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
-    if (err == cudaSuccess) err = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (err != cudaSuccess) return err;
+    Cached scratch_entry;
+    Cached &cached = dev >= 0 && dev < 16 ? cache[dev] : scratch_entry;
+    if (cached.max_smem == 0) {
+        err = cudaDeviceGetAttribute(&cached.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cached.max_smem);
+        if (err != cudaSuccess) { cached.max_smem = 0; return err; }
+    }
+    const int max_smem = cached.max_smem;
     int threads = RL_TRACE_THREADS;
     while (threads > 128 && trace_kernel_smem_bytes(sc, threads) > (size_t)max_smem) threads -= 128;
     // Small batches (the reference's 524 288 photons are 4.6 per thread of a full grid) spend most
@@ -296,12 +311,13 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
                        && p.n_photons < small_paths * (uint64_t)sm_count * (uint64_t)threads;
     if (small) threads = small_cta;
     const size_t smem = trace_kernel_smem_bytes(sc, threads);
-    err = cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    if (err != cudaSuccess) return err;
-    int per_sm = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel, threads, smem);
-    if (err != cudaSuccess) return err;
-    if (per_sm < 1) per_sm = 1;
+    if (cached.threads != threads || cached.smem != smem) {
+        int occ = 0;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_kernel, threads, smem);
+        if (err != cudaSuccess) return err;
+        cached.threads = threads; cached.smem = smem; cached.per_sm = occ < 1 ? 1 : occ;
+    }
+    const int per_sm = cached.per_sm;
     // carve out only the shared memory the resident CTAs need (+1 KB each that the system
     // reserves); the rest of the 228 KB stays L1 for the material records, the exact sphere
     // records and the few spilled registers
@@ -309,7 +325,10 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
         const char *env = getenv("RL_TRACE_CARVEOUT");
         int pct = env ? atoi(env) : (int)((per_sm * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
         if (pct > 100) pct = 100;
-        if (pct >= 0) cudaFuncSetAttribute(trace_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        if (pct >= 0 && pct != cached.pct) {
+            cudaFuncSetAttribute(trace_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cached.pct = pct;
+        }
     }
     uint64_t want = (p.n_photons + threads - 1) / threads;
     uint64_t full = (uint64_t)sm_count * per_sm;
@@ -317,7 +336,7 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
         // RL_TRACE_BLOCKS_PER_SM > 0 fixes the share (experiments); default: by the concurrency seen
         int share = env_int("RL_TRACE_BLOCKS_PER_SM", 0);
         if (share <= 0) {
-            const int others = other_streams_in_flight(dev, st);
+            const int others = other_streams_in_flight(dev, st, per_sm - 1 > 1 ? per_sm - 1 : 1);
             share = (per_sm + others) / (others + 1);
         }
         if (share < per_sm) full = (uint64_t)sm_count * (share < 1 ? 1 : share);
