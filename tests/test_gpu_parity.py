@@ -534,6 +534,27 @@ def test_full_resolution_properties(gpu, orc):
     assert np.all(img >= 0.0) and np.isfinite(img).all()
 
 
+def test_request_larger_than_one_launch(gpu):
+    # the kernel indexes the photons of a launch with 32 bits; a request of more than 2^31 photons
+    # (C3 is 2^30 per frame, C4 2^31, C5 2^36) is split into launches that continue the id range
+    w = h = 256
+    n = (1 << 31) + 4099
+    sc = gpu.Scene(gpu.SceneBuilder(1))            # sphere + emissive plane: 1.09 rays per photon
+    one = gpu.PlotUnit(0, w, h)
+    tu = gpu.TraceUnit(0, w, h, seed=SEED, batch=1)
+    tu.render_fused(sc, one, 7, n)
+    rays_one = tu.ray_count()
+    two = gpu.PlotUnit(1, w, h)
+    tu2 = gpu.TraceUnit(1, w, h, seed=SEED, batch=1)
+    tu2.render_fused(sc, two, 7, 1 << 31)
+    tu2.render_fused(sc, two, 7 + (1 << 31), 4099)
+    assert tu2.ray_count() == rays_one
+    a, b = one.tristimulus_buffer, two.tristimulus_buffer
+    # 2^31 float atomics per image in different orders: sums of ~3e4 terms per pixel
+    assert float(np.abs(a - b).max()) <= 2e-4 * float(np.abs(a).max())
+    assert rays_one > n
+
+
 def test_c5_canvas_properties(gpu, orc):
     # BASELINE configs[4] canvas (4096x4096, built-in scene): 201 MB frames, far more pixels than
     # photons here -- the laws that do not depend on size, plus gather + clear + tonemap at that size
