@@ -67,3 +67,19 @@ def test_two_rank_reduce_equals_single_rank(tmp_path, pkg, orc):
     # same photon set, different summation order
     assert float(np.abs(got - want).max()) <= 1e-5 * float(np.abs(want).max()) + 1e-12
     assert got.any()
+
+
+def test_host_cpu_shares_for_replay_processes():
+    # bench.py pins one scheduler-replay process per GPU to its share of the host's cores; without
+    # NUMA information (numa_node = -1, as on the VMs here) the allowed cores are split evenly
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("rl_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    allowed = sorted(os.sched_getaffinity(0))
+    world = 2 if len(allowed) >= 2 else 1
+    shares = [bench.host_cpus_for_rank(r, world, "ffff:ff:1f.0")[0] for r in range(world)]
+    assert all(shares) and all(set(s) <= set(allowed) for s in shares)
+    if world == 2:
+        assert not set(shares[0]) & set(shares[1])
+    assert bench._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
