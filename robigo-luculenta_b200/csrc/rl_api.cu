@@ -994,6 +994,11 @@ int rl_gather_unit_save(rl_gather_unit *u, const char *path) {
     for (const std::string &p : wr.proven) proven |= p == path;
     int idx = 0;
     if (proven) {
+        {
+            // a snapshot queued for another file is not this one's to replace: let it land first
+            std::unique_lock<std::mutex> lock(wr.m);
+            wr.cv.wait(lock, [&] { return wr.pending < 0 || wr.pending_path == path; });
+        }
         std::lock_guard<std::mutex> lock(wr.m);
         if (!wr.error.empty()) {
             std::string e;

@@ -141,7 +141,10 @@ public:
                                           keep_on_device_ || deferred_records() ? nullptr : mapped_photons.destination()),
                "rl_trace_unit_render");
         mapped_photons.invalidate();
-        if (!async_render() && !keep_on_device_) mapped_photons.get();
+        if (!async_render()) {
+            if (keep_on_device_ || deferred_records()) expect(rl_trace_unit_sync(handle_), "rl_trace_unit_sync");
+            else mapped_photons.get();
+        }
     }
     uint64_t ray_count() {
         uint64_t n = 0;

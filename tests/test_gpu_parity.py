@@ -443,6 +443,18 @@ def test_buffer_raw_background_writer(gpu, tmp_path):
         assert any(np.array_equal(raw, st) for st in states)
     g.flush()
     assert np.array_equal(np.fromfile(path, dtype="<f4"), states[-1])
+    # two files in turn: a newer snapshot only replaces a queued one for the same file
+    path2 = str(tmp_path / "second.raw")
+    last = {}
+    for i in range(6):
+        g.accumulate(rng.uniform(0, 5, (h, w, 3)).astype(np.float32))
+        acc, comp = g.download(with_compensation=True)
+        target = path if i % 2 else path2
+        last[target] = np.concatenate([acc.reshape(-1), comp.reshape(-1)])
+        g.save(target, wait=False)
+    g.flush()
+    for target, want in last.items():
+        assert np.array_equal(np.fromfile(target, dtype="<f4"), want)
     # load waits for a queued save of the same file; destroy writes out what is still queued
     g.accumulate(rng.uniform(0, 5, (h, w, 3)).astype(np.float32))
     acc, comp = g.download(with_compensation=True)
