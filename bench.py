@@ -421,7 +421,11 @@ def main():
     cpus, numa_node = (host_cpus_for_rank(local_rank, world, pci) if world > 1
                        else (sorted(os.sched_getaffinity(0)), -1))
     workers = max(2, min(16, len(cpus)))
-    exe = entry.build_replay()
+    try:
+        exe = entry.build_replay()
+    except (OSError, subprocess.SubprocessError) as e:
+        print(f"[bench] rank {rank}: building rl_replay failed: {e!r}", file=sys.stderr, flush=True)
+        exe = "/nonexistent/rl_replay"
     out_prefix = f"/tmp/rl_bench_replay_{os.getpid()}"
     cmd = [exe, "--width", str(WIDTH), "--height", str(HEIGHT), "--threads", str(workers), "--batches",
            str(replay_batches), "--batch", "524288", "--seed", str(SEED), "--mode", "strict", "--scene", "2",
@@ -429,28 +433,52 @@ def main():
     visible = os.environ.get("CUDA_VISIBLE_DEVICES")
     env = dict(os.environ, CUDA_VISIBLE_DEVICES=visible.split(",")[local_rank] if visible else str(local_rank))
     def run_replay(extra):
+        """One replay per rank; None on every rank if it failed on any (so that the ranks stay in
+        step and the bench line is still printed, with the failure noted in it)."""
         barrier()
-        res = subprocess.run(cmd + extra, capture_output=True, text=True, env=env, timeout=1200,
-                             preexec_fn=(lambda: os.sched_setaffinity(0, cpus)) if world > 1 else None)
-        if res.returncode != 0:
-            raise RuntimeError("rl_replay failed: " + res.stderr[-500:])
-        return json.loads(res.stdout.strip().splitlines()[-1])
+        out, why = None, ""
+        try:
+            res = subprocess.run(cmd + extra, capture_output=True, text=True, env=env, timeout=1200,
+                                 preexec_fn=(lambda: os.sched_setaffinity(0, cpus)) if world > 1 else None)
+            if res.returncode == 0:
+                out = json.loads(res.stdout.strip().splitlines()[-1])
+            else:
+                why = res.stderr[-300:]
+        except (OSError, ValueError, IndexError, subprocess.SubprocessError) as e:
+            why = repr(e)
+        ok = torch.tensor([1 if out is not None else 0], dtype=torch.int32, device="cuda")
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok[0]) == 0:
+            if why:
+                print(f"[bench] rank {rank}: rl_replay {' '.join(extra)} failed: {why}", file=sys.stderr, flush=True)
+            return None
+        return out
+
+    def replay_failed(what):
+        d = dict(e2e_device)
+        d["note"] = f"{what} replay failed on this box (stderr has the reason): this entry repeats e2e_device"
+        return d
 
     # the same unchanged call sites with the records left on the device until host code reads them
     # (PlotUnit::plot recognises `&unit.mapped_photons` by its type: INTEGRATION.md, rl_units.hpp)
     deferred = run_replay(["--records", "deferred"])
-    t = torch.tensor([deferred["seconds"]], dtype=torch.float64, device="cuda")
-    r = torch.tensor([deferred["rays"], deferred["h2d_bytes"], deferred["d2h_bytes"]], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(r, op=dist.ReduceOp.SUM)
-    e2e_deferred = {"value": int(r[0]) / float(t[0]) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(r[1]) // e2e_steps,
-                    "d2h_bytes_per_step": int(r[2]) // e2e_steps, "steps": e2e_steps,
-                    "path": "the strict-mode replay with `mapped_photons` copied out only when host code reads it "
-                            "(never, in app.rs): frames and buffer.raw still cross PCIe; per-rank frames not combined"}
+    if deferred is None:
+        e2e_deferred = replay_failed("deferred-records")
+    else:
+        t = torch.tensor([deferred["seconds"]], dtype=torch.float64, device="cuda")
+        r = torch.tensor([deferred["rays"], deferred["h2d_bytes"], deferred["d2h_bytes"]], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        e2e_deferred = {"value": int(r[0]) / float(t[0]) / 1e6, "unit": "Mrays/s",
+                        "h2d_bytes_per_step": int(r[1]) // e2e_steps, "d2h_bytes_per_step": int(r[2]) // e2e_steps,
+                        "steps": e2e_steps,
+                        "path": "the strict-mode replay with `mapped_photons` copied out only when host code reads it "
+                                "(never, in app.rs): frames and buffer.raw still cross PCIe; per-rank frames not combined"}
     replay = run_replay([])
     combine_s = 0.0
-    if world > 1:
+    if replay is not None and world > 1:
         t0 = time.perf_counter()
         frame = np.fromfile(out_prefix + ".raw", dtype="<f4", count=WIDTH * HEIGHT * 3)
         dev_frame = torch.from_numpy(frame).cuda()
@@ -464,6 +492,11 @@ def main():
             os.remove(out_prefix + suffix)
         except OSError:
             pass
+    if replay is None:
+        replay = {"seconds": 1.0, "rays": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+        strict_failed = True
+    else:
+        strict_failed = False
     t = torch.tensor([replay["seconds"] + combine_s], dtype=torch.float64, device="cuda")
     r = torch.tensor([replay["rays"], replay["h2d_bytes"], replay["d2h_bytes"]], dtype=torch.int64, device="cuda")
     if world > 1:
@@ -480,6 +513,9 @@ def main():
                    "(host/rl_replay.cpp; app.rs:95-164, task_scheduler.rs:91-182): 524 288-photon TraceUnit::render "
                    "into host memory, PlotUnit::plot / GatherUnit::accumulate from host memory, buffer.raw saved "
                    "after every gather, tonemap at the end" + ("; ranks' frames summed onto rank 0" if world > 1 else "")}
+
+    if strict_failed:
+        e2e = replay_failed("strict-mode")
 
     if rank != 0:
         if world > 1:
