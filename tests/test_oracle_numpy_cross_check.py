@@ -249,3 +249,50 @@ def test_oracle_plot_matches_scalar_restatement(orc):
     got = orc.plot(w, h, photons)
     assert np.array_equal(got.view(np.uint32), buf.view(np.uint32))
     assert buf.any()
+
+
+def test_oracle_gather_and_tonemap_match_numpy_restatement(orc):
+    # GatherUnit::accumulate (gather_unit.rs:49-64), TonemapUnit::find_exposure / tonemap
+    # (tonemap_unit.rs:55-100), srgb::transform / gamma_correct (srgb.rs:20-41) restated in numpy f32;
+    # ln and powf go through the oracle's specified functions (orc.math), the rest is arithmetic
+    rng = np.random.default_rng(5)
+    w, h = 48, 31
+    acc = np.zeros((h, w, 3), dtype=F)
+    comp = np.zeros((h, w, 3), dtype=F)
+    mine_acc, mine_comp = acc.copy(), comp.copy()
+    for _ in range(7):
+        px = (rng.uniform(0, 1, (h, w, 3)) ** 6 * 40).astype(F)     # a few bright pixels, many dim ones
+        orc.gather_accumulate(acc, comp, px)
+        extra = px - mine_comp
+        total = mine_acc + extra
+        mine_comp = (total - mine_acc) - extra
+        mine_acc = total
+    assert np.array_equal(acc.view(np.uint32), mine_acc.view(np.uint32))
+    assert np.array_equal(comp.view(np.uint32), mine_comp.view(np.uint32))
+
+    # find_exposure: two sequential f32 folds over the pixels in order
+    y = acc[..., 1].reshape(-1)
+    n = F(w * h)
+    mean = np.cumsum(y, dtype=F)[-1] / n
+    sqr_mean = np.cumsum(y * y, dtype=F)[-1] / n
+    white = mean + np.sqrt(sqr_mean - mean * mean)
+    assert F(orc.find_exposure(acc)) == white
+
+    def fn(code, x, x2=None):
+        return orc.math(code, np.ascontiguousarray(x, dtype=F).reshape(-1), None if x2 is None else
+                        np.ascontiguousarray(x2, dtype=F).reshape(-1), mode=orc.MATH_SPEC).reshape(np.shape(x))
+
+    ln4 = fn(6, np.array([4.0], dtype=F))[0]
+    cie = fn(6, acc / white + F(1)) / ln4
+    x, yy, z = cie[..., 0], cie[..., 1], cie[..., 2]
+    lin = np.stack([F(3.2406) * x - F(1.5372) * yy - F(0.4986) * z,
+                    F(-0.9689) * x + F(1.8758) * yy + F(0.0415) * z,
+                    F(0.0557) * x - F(0.2040) * yy + F(1.0570) * z], axis=-1)
+    with np.errstate(invalid="ignore"):
+        powed = fn(7, lin, np.full(lin.shape, F(1) / F(2.4), dtype=F))
+        gamma = np.where(lin <= F(0.0031308), F(12.92) * lin, F(1.055) * powed - F(0.055))
+    clamped = np.where(gamma < 0, F(0), np.where(gamma > 1, F(1), gamma))
+    rgb = np.floor(clamped * F(255)).astype(np.uint8)                # `as u8` truncates; all values are in [0, 255]
+    got = orc.tonemap(acc, orc.MATH_SPEC)
+    assert np.array_equal(got, rgb)
+    assert len(np.unique(rgb)) > 100                                 # a real image, not a flat one
