@@ -242,12 +242,21 @@ def trace(pkg, orc, desc, seed, width, height, first, n, mode):
     (4, 64, 512, 512, 99, 2500),                # random spheres: grey, coloured, glossy, soap
 ])
 def test_oracle_trace_matches_numpy_restatement(pkg, orc, which, param, w, h, first, n):
+    check(pkg, orc, which, param, w, h, first, n, orc.MATH_SPEC)
+
+
+def test_oracle_trace_matches_numpy_restatement_libm_mode(pkg, orc):
+    # the mode the CPU baseline runs in (glibc's functions, what the Rust binary calls)
+    check(pkg, orc, 2, 0, 1024, 1024, 5_000_000, 1500, orc.MATH_LIBM)
+
+
+def check(pkg, orc, which, param, w, h, first, n, mode):
     desc = pkg.SceneBuilder(which, param).desc()
     seed = 0x5EED
     ct = orc.Counters()
-    want = orc.trace(desc, seed, w, h, first, n, orc.MATH_SPEC, False, ct)
+    want = orc.trace(desc, seed, w, h, first, n, mode, False, ct)
     with np.errstate(all="ignore"):
-        got, rays = trace(pkg, orc, desc, seed, w, h, first, n, orc.MATH_SPEC)
+        got, rays = trace(pkg, orc, desc, seed, w, h, first, n, mode)
     assert rays == ct.rays
     for field in ("wavelength", "x", "y", "probability"):
         a, b = got[field].view(np.uint32), want[field].view(np.uint32)
