@@ -96,3 +96,17 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 text = open(os.path.join(base, f), errors="replace").read()
                 assert "oracle" not in text.lower(), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c(tmp_path):
+    # the boundary is a C ABI: the header compiles as C99, pedantically, without a C++ compiler
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "rl_b200.h"\n'
+                   "int use(void) {\n"
+                   "    rl_scene_desc d; rl_mapped_photon p; rl_hit h; rl_ray r;\n"
+                   "    (void)d; (void)p; (void)h; (void)r;\n"
+                   "    return (int)sizeof(rl_surface) + RL_ABI_VERSION + (int)RL_BATCH_PHOTONS + (rl_abi_version() == RL_ABI_VERSION);\n"
+                   "}\n")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    "-c", str(src), "-o", str(tmp_path / "use_header.o")], check=True)
