@@ -582,7 +582,10 @@ def main():
              "traffic_source": "profiles/r1_s2_splat_kernel_ncu.txt: dram read + write of one 2^25-record launch"},
             {"kernel": "gather_kernel (GatherUnit::accumulate + clear, 4096^2)", "bound": "hbm",
              "achieved": gw * gw * GATHER_BYTES_PER_PIXEL / (gather_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-             "frac": gw * gw * GATHER_BYTES_PER_PIXEL / (gather_ms * 1e-3) / 1e9 / peak, "ms": gather_ms},
+             "frac": gw * gw * GATHER_BYTES_PER_PIXEL / (gather_ms * 1e-3) / 1e9 / peak, "ms": gather_ms,
+             "traffic": 1357937152.0,
+             "traffic_source": "profiles/r1_s2_gather_kernel_ncu.txt: dram read + write of one 4096^2 launch "
+                               "(80 B/pixel are really moved: the source frame is padded to float4)"},
         ],
     }
 

@@ -6,6 +6,7 @@
   3  splat of those records
   4  trace of 2^25 photons into records (512 MiB)
   5  splat of 2^25 records: the configuration bench.py times for K2
+  6, 7  gather + clear of a 4096^2 frame: the configuration bench.py times for K3
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -29,4 +30,9 @@ big.render_range(scene, 0, 1 << 25, download=False)
 big.sync()
 pl.plot(big)
 pl.sync()
+del big
+gp, gg = pkg.PlotUnit(2, 4096, 4096), pkg.GatherUnit(4096, 4096)
+for _ in range(2):
+    gg.accumulate(gp, clear=True)
+gg.sync()
 print("rays", tu.ray_count())
