@@ -43,6 +43,7 @@ WORKLOAD = "built-in scene (app.rs:166-363, 339 objects), 1024x1024, 256 spp = 2
 SPLAT_FUSED_BYTES_PER_PHOTON = 48      # 4 px x 3 ch x 4 B accumulator payload, no record round trip
 SPLAT_BYTES_PER_PHOTON = 64            # + 16 B MappedPhoton read
 GATHER_BYTES_PER_PIXEL = 72            # read px/acc/comp, write acc/comp, clear px (12 B each)
+TONEMAP_BYTES_PER_PIXEL = 27           # moments pass reads 12 B, map pass reads 12 B and writes 3 B
 
 
 def measured_peaks():
@@ -552,7 +553,15 @@ def main():
     gp, gg = pkg.PlotUnit(101, gw, gw), pkg.GatherUnit(gw, gw)
     gp.set_stream(stream); gg.set_stream(stream)
     gather_ms = time_ms(lambda: gg.accumulate(gp, clear=True), 5)
-    del gp, gg, tr2
+    # K4 on the same canvas: a frame with structure (a few accumulated splats), image left on the device
+    tm = pkg.TonemapUnit(gw, gw)
+    tm.set_stream(stream)
+    tr3 = pkg.TraceUnit(102, gw, gw, seed=SEED, batch=1 << 22)
+    tr3.set_stream(stream)
+    tr3.render_fused(scene, gp, 0, 1 << 22)
+    gg.accumulate(gp, clear=True)
+    tonemap_ms = time_ms(lambda: tm.tonemap(gg, download=False), 5)
+    del gp, gg, tr2, tr3, tm
 
     kernel_s = kernel_ms * 1e-3 / args.steps
     photons_per_launch = n
@@ -586,6 +595,12 @@ def main():
              "traffic": 1357937152.0,
              "traffic_source": "profiles/r1_s2_gather_kernel_ncu.txt: dram read + write of one 4096^2 launch "
                                "(80 B/pixel are really moved: the source frame is padded to float4)"},
+            {"kernel": "tonemap kernels (TonemapUnit::tonemap: moments, exposure, map; 4096^2)",
+             "bound": "alu, not hbm: six specified ln, three exp and six IEEE divisions per pixel "
+                      "(tonemap_unit.rs:82-86, srgb.rs:20-26); runs once per 30 s in the reference",
+             "achieved": gw * gw * TONEMAP_BYTES_PER_PIXEL / (tonemap_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+             "frac": gw * gw * TONEMAP_BYTES_PER_PIXEL / (tonemap_ms * 1e-3) / 1e9 / peak, "ms": tonemap_ms,
+             "bytes": "27 B/pixel: 12 B read for the moments, 12 B read + 3 B written by the map"},
         ],
     }
 

@@ -527,10 +527,12 @@ class TonemapUnit:
     def set_stream(self, cuda_stream):
         _check(lib().rl_tonemap_unit_set_stream(self._h, _P(cuda_stream)))
 
-    def tonemap(self, tristimuli):
-        """TonemapUnit::tonemap (tonemap_unit.rs:73-100): a host buffer or a GatherUnit."""
+    def tonemap(self, tristimuli, download=True):
+        """TonemapUnit::tonemap (tonemap_unit.rs:73-100): a host buffer or a GatherUnit
+        (`download=False`: leave the image on the device)."""
         if isinstance(tristimuli, GatherUnit):
-            _check(lib().rl_tonemap_unit_tonemap_gather(self._h, tristimuli._h, _ptr(self.rgb_buffer)))
+            _check(lib().rl_tonemap_unit_tonemap_gather(self._h, tristimuli._h,
+                                                         _ptr(self.rgb_buffer) if download else None))
         else:
             t = np.ascontiguousarray(tristimuli, dtype=np.float32)
             assert t.size == self.width * self.height * 3
