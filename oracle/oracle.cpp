@@ -12,7 +12,11 @@
  * not vendored), and no Rust toolchain exists in this environment, so the
  * reference binary cannot produce fixtures either.  What pins this file is
  * (a) the closed-form known-answer tests derived from the reference source
- * (tests/test_oracle_kat.py) and (b) line-by-line citation below.
+ * (tests/test_oracle_kat.py), (b) a second, independent restatement in numpy
+ * that it agrees with bit for bit -- Scene::intersect, whole photon paths,
+ * plot, gather, tonemap, and the built-in scene (tests/test_oracle_numpy_cross_check.py,
+ * tests/test_oracle_path_cross_check.py, tests/test_scene_builder_cross_check.py) --
+ * and (c) line-by-line citation below.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * the reference's src/).  It is a restatement over a flattened POD scene
