@@ -296,3 +296,32 @@ def test_oracle_gather_and_tonemap_match_numpy_restatement(orc):
     got = orc.tonemap(acc, orc.MATH_SPEC)
     assert np.array_equal(got, rgb)
     assert len(np.unique(rgb)) > 100                                 # a real image, not a flat one
+
+
+def test_oracle_blackbody_and_sellmeier_match_numpy_restatement(orc):
+    # boltzmann / BlackBodyMaterial (material.rs:61-74, :92-105, constants.rs:19-25) in numpy f64; numpy's
+    # exp is not glibc's bit for bit, so the f32 result may differ in the last place -- and the SF10
+    # Sellmeier index (material.rs:203-213), which is arithmetic only: bit-equal
+    h, k, c, wien = 6.62606957e-34, 1.3806488e-23, 299792458.0, 2.897772126e-3
+
+    def boltzmann(wavelength_nm, temperature):
+        f = c / (wavelength_nm * 1.0e-9)
+        return (2.0 * h * f * f * f) / (c * c * (np.exp(h * f / (k * temperature)) - 1.0))
+
+    wl = np.linspace(380.0, 780.0, 2001).astype(F)
+    for temperature, intensity in ((6504.0, 1.0), (7600.0, 0.6), (5000.0, 0.6), (2700.0, 3.0)):
+        t32 = F(temperature)
+        norm = F(intensity) / F(boltzmann((wien / float(t32)) * 1.0e9, float(t32)))
+        want = (boltzmann(wl.astype(np.float64), float(t32)).astype(F) * norm).astype(F)
+        got = orc.blackbody_intensity(float(t32), float(norm), wl, orc.MATH_LIBM)
+        ulps = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+        assert ulps.max() <= 1, f"T={temperature}: {ulps.max()} ulp"
+        spec = orc.blackbody_intensity(float(t32), float(norm), wl, orc.MATH_SPEC)
+        assert np.abs(spec.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64)).max() <= 2
+
+    w2 = (wl * wl * F(1.0e-6)).astype(np.float64)
+    n2 = (1.0 + 1.737596950 * w2 / (w2 - 0.0131887070) + 0.313747346 * w2 / (w2 - 0.0623068142)
+          + 1.898781010 * w2 / (w2 - 155.23629000))
+    ior = np.sqrt(n2).astype(F)
+    got = orc.math(5, wl)
+    assert np.array_equal(got.view(np.uint32), ior.view(np.uint32))
