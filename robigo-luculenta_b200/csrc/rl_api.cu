@@ -1022,14 +1022,27 @@ int rl_gather_unit_save(rl_gather_unit *u, const char *path) {
         wr.proven.push_back(path);
         return RL_OK;
     }
+    bool no_thread = false;
     {
         std::lock_guard<std::mutex> lock(wr.m);
         if (!wr.started) {
-            wr.thread = std::thread([&wr] { wr.run(); });
-            wr.started = true;
+            try {
+                wr.thread = std::thread([&wr] { wr.run(); });
+                wr.started = true;
+            } catch (const std::exception &) {      // no exception crosses the C boundary
+                no_thread = true;
+            }
         }
-        wr.pending = idx;
-        wr.pending_path = path;
+        if (!no_thread) {
+            wr.pending = idx;
+            wr.pending_path = path;
+        }
+    }
+    if (no_thread) {
+        // no writer thread to be had: write in the caller, as the first save does
+        std::string err;
+        if (!SaveWriter::write_file(path, host, 2 * n, err)) return fail(RL_ERR_IO, err);
+        return RL_OK;
     }
     wr.cv.notify_all();
     return RL_OK;
