@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define RL_ABI_VERSION 1
+#define RL_ABI_VERSION 2
 
 /* trace_unit.rs:67 -- photons per TraceUnit batch (1024 under cfg(test), :70) */
 #define RL_BATCH_PHOTONS (1024u * 512u)
@@ -189,8 +189,12 @@ int rl_trace_unit_set_batch_size(rl_trace_unit *unit, uint64_t n_photons);
 /* Bind the unit to a caller-owned cudaStream_t (NULL = its own stream). */
 int rl_trace_unit_set_stream(rl_trace_unit *unit, void *cuda_stream);
 /* TraceUnit::render (trace_unit.rs:151-168).  Photon ids of the batch are
- * taken from a process-wide batch counter, so the union of photons over any
- * schedule of B render() calls is ids [0, B * batch).  If `out` is non-NULL
+ * taken from the scene's batch counter (one scene = one App, app.rs:63), so the
+ * union of photons over any schedule of B render() calls on a scene is ids
+ * [0, B * batch).  Batches of the reference's size do not get a kernel launch
+ * of their own: they are queued to the scene's resident trace service
+ * (DESIGN.md 4, K1b), which the scheduler's worker threads keep fed
+ * (task_scheduler.rs:95-96,127-182).  If `out` is non-NULL
  * it receives batch_size records (the shim's `mapped_photons` Vec) and the
  * call blocks; with NULL the records stay on the device for plot_device. */
 int rl_trace_unit_render(rl_trace_unit *unit, const rl_scene *scene, rl_mapped_photon *out);
@@ -204,8 +208,11 @@ int rl_trace_unit_render(rl_trace_unit *unit, const rl_scene *scene, rl_mapped_p
 int rl_trace_unit_render_async(rl_trace_unit *unit, const rl_scene *scene, rl_mapped_photon *out);
 /* Copy the records of the last render out of the device (blocking); lets the
  * shim leave them there (`out` = NULL above) until host code really reads
- * `mapped_photons`. */
-int rl_trace_unit_download(rl_trace_unit *unit, rl_mapped_photon *out);
+ * `mapped_photons`.  `out` has room for `capacity` records: the call fails with
+ * RL_ERR_INVALID if the last render left more; `out_count` (optional) receives
+ * the number copied (0 after a fused render: nothing is copied). */
+int rl_trace_unit_download(rl_trace_unit *unit, rl_mapped_photon *out, uint64_t capacity,
+                           uint64_t *out_count);
 /* Same, for an explicit photon-id range [first_photon, first_photon + n). */
 int rl_trace_unit_render_range(rl_trace_unit *unit, const rl_scene *scene,
                                uint64_t first_photon, uint64_t n_photons,
@@ -219,8 +226,9 @@ int rl_trace_unit_render_fused(rl_trace_unit *unit, const rl_scene *scene, rl_pl
 /* Rays traced (= Scene::intersect calls, scene.rs:39) by this unit so far. */
 int rl_trace_unit_ray_count(rl_trace_unit *unit, uint64_t *out_rays);
 int rl_trace_unit_sync(rl_trace_unit *unit);
-/* Reset the process-wide batch counter used by rl_trace_unit_render. */
-void rl_trace_batch_counter_reset(uint64_t next_batch);
+/* Set the scene's batch counter used by rl_trace_unit_render: the next batch
+ * is ids [next_batch * batch, (next_batch + 1) * batch). */
+int rl_scene_batch_counter_reset(const rl_scene *scene, uint64_t next_batch);
 
 /* Bytes copied host -> device and device -> host by the entry points of this
  * ABI since the last reset (process-wide): scene tables, MappedPhoton batches,
@@ -323,43 +331,6 @@ int rl_tonemap_unit_tonemap(rl_tonemap_unit *unit, const float *xyz, uint8_t *rg
 int rl_tonemap_unit_tonemap_gather(rl_tonemap_unit *unit, rl_gather_unit *gather, uint8_t *rgb);
 /* The exposure (`max_intensity`, tonemap_unit.rs:55-69) of the last call. */
 int rl_tonemap_unit_last_exposure(rl_tonemap_unit *unit, float *out);
-
-/* ------------------------------------------------- host scene builders   */
-/*
- * Host-side mirrors of the reference's constructors and of
- * App::set_up_scene (app.rs:166-363) that emit descriptors.  They are input
- * generators for tests and benchmarks, not part of the device path.
- */
-typedef struct rl_scene_builder rl_scene_builder;
-
-typedef enum rl_builtin_scene {
-    RL_SCENE_C1_SPHERE_PLANE = 1,  /* 1 diffuse sphere + emissive plane, static camera     */
-    RL_SCENE_C2_BUILTIN = 2,       /* app.rs:166-363, 339 objects, orbit camera            */
-    RL_SCENE_C3_PRISM = 3,         /* SF10 prism + emissive circle + grey floor            */
-    RL_SCENE_C4_SPHERES = 4        /* 4096 random spheres (param = sphere count, 0 = 4096) */
-} rl_builtin_scene;
-
-int rl_scene_builder_create(rl_scene_builder **out);
-int rl_scene_builder_destroy(rl_scene_builder *b);
-int rl_scene_builder_builtin(rl_scene_builder *b, int which, uint32_t param);
-/* Primitive constructors; each returns the new surface node index (>= 0). */
-int rl_scene_builder_plane(rl_scene_builder *b, rl_vec3 normal, rl_vec3 offset);
-int rl_scene_builder_circle(rl_scene_builder *b, rl_vec3 normal, rl_vec3 position, float radius);
-int rl_scene_builder_sphere(rl_scene_builder *b, rl_vec3 position, float radius);
-int rl_scene_builder_paraboloid(rl_scene_builder *b, rl_vec3 normal, rl_vec3 offset,
-                                float focal_distance);
-int rl_scene_builder_prism(rl_scene_builder *b, rl_vec3 axis, rl_vec3 offset, float edge_length,
-                           float angle, float height);
-int rl_scene_builder_hexagonal_prism(rl_scene_builder *b, rl_vec3 axis, rl_vec3 offset,
-                                     float edge_length, float bevel_size, float angle,
-                                     float height);
-/* BlackBodyMaterial::new (material.rs:92-97) -> material record. */
-int rl_material_blackbody(float kelvins, float intensity, rl_material *out);
-/* Object::new (object.rs:35-42); returns the object index. */
-int rl_scene_builder_object(rl_scene_builder *b, uint32_t surface, rl_material material);
-int rl_scene_builder_camera(rl_scene_builder *b, const rl_camera_model *camera);
-/* Borrow the descriptor; valid until the builder changes or is destroyed. */
-int rl_scene_builder_desc(rl_scene_builder *b, rl_scene_desc *out);
 
 /* ------------------------------------------------------------- debugging */
 /*

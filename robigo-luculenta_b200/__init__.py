@@ -22,6 +22,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # RL_B200_LIB overrides the library path (tuning experiments build variants beside the default)
 LIB_PATH = os.environ.get("RL_B200_LIB") or os.path.join(_HERE, "librl_b200.so")
+# the host-only scene builders (include/rl_host.h): no CUDA in it
+HOST_LIB_PATH = os.path.join(_HERE, "librl_host.so")
 
 BATCH_PHOTONS = 1024 * 512        # trace_unit.rs:67
 TEST_BATCH_PHOTONS = 1024         # trace_unit.rs:70
@@ -111,12 +113,12 @@ SYMBOLS = {
     "rl_trace_unit_set_stream": (_I, [_P, _P]),
     "rl_trace_unit_render": (_I, [_P, _P, _P]),
     "rl_trace_unit_render_async": (_I, [_P, _P, _P]),
-    "rl_trace_unit_download": (_I, [_P, _P]),
+    "rl_trace_unit_download": (_I, [_P, _P, _U64, C.POINTER(_U64)]),
     "rl_trace_unit_render_range": (_I, [_P, _P, _U64, _U64, _P]),
     "rl_trace_unit_render_fused": (_I, [_P, _P, _P, _U64, _U64]),
     "rl_trace_unit_ray_count": (_I, [_P, C.POINTER(_U64)]),
     "rl_trace_unit_sync": (_I, [_P]),
-    "rl_trace_batch_counter_reset": (None, [_U64]),
+    "rl_scene_batch_counter_reset": (_I, [_P, _U64]),
     "rl_transfer_counters": (None, [C.POINTER(_U64), C.POINTER(_U64)]),
     "rl_transfer_counters_reset": (None, []),
     "rl_host_register": (_I, [_P, C.c_size_t]),
@@ -150,6 +152,15 @@ SYMBOLS = {
     "rl_tonemap_unit_tonemap": (_I, [_P, _P, _P]),
     "rl_tonemap_unit_tonemap_gather": (_I, [_P, _P, _P]),
     "rl_tonemap_unit_last_exposure": (_I, [_P, _PF]),
+    "rl_debug_intersect": (_I, [_P, _P, _U64, _P]),
+    "rl_debug_math": (_I, [_I, _P, _P, _U64, _P]),
+    "rl_debug_tristimulus": (_I, [_P, _U64, _P]),
+    "rl_debug_camera_rays": (_I, [_P, _U64, _U32, _U32, _U64, _U64, _P, _P]),
+    "rl_debug_cull_check": (_I, [_P, _U64, _U32, _U32, _U64, _U64, C.POINTER(_U64), C.POINTER(_U64)]),
+}
+
+# Every symbol include/rl_host.h declares (librl_host.so)
+HOST_SYMBOLS = {
     "rl_scene_builder_create": (_I, [C.POINTER(_P)]),
     "rl_scene_builder_destroy": (_I, [_P]),
     "rl_scene_builder_builtin": (_I, [_P, _I, _U32]),
@@ -163,14 +174,10 @@ SYMBOLS = {
     "rl_scene_builder_object": (_I, [_P, _U32, Material]),
     "rl_scene_builder_camera": (_I, [_P, C.POINTER(CameraModel)]),
     "rl_scene_builder_desc": (_I, [_P, C.POINTER(SceneDesc)]),
-    "rl_debug_intersect": (_I, [_P, _P, _U64, _P]),
-    "rl_debug_math": (_I, [_I, _P, _P, _U64, _P]),
-    "rl_debug_tristimulus": (_I, [_P, _U64, _P]),
-    "rl_debug_camera_rays": (_I, [_P, _U64, _U32, _U32, _U64, _U64, _P, _P]),
-    "rl_debug_cull_check": (_I, [_P, _U64, _U32, _U32, _U64, _U64, C.POINTER(_U64), C.POINTER(_U64)]),
 }
 
 _lib_handle = None
+_host_handle = None
 
 
 def lib():
@@ -190,9 +197,30 @@ def lib():
     return _lib_handle
 
 
+def host_lib():
+    """The host-only scene builders; raises if the library has not been built."""
+    global _host_handle
+    if _host_handle is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise ImportError(f"{HOST_LIB_PATH} is missing: build it with "
+                              "`python -c 'import __graft_entry__ as g; g.build()'`")
+        handle = C.CDLL(HOST_LIB_PATH)
+        for name, (restype, argtypes) in HOST_SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _host_handle = handle
+    return _host_handle
+
+
 def _check(code):
     if code != RL_OK:
         raise RlError(code, lib().rl_last_error().decode("utf-8", "replace"))
+
+
+def _check_host(code):
+    if code != RL_OK:
+        raise RlError(code, "scene builder (librl_host.so)")
 
 
 def _ptr(array):
@@ -222,8 +250,6 @@ def reset_transfer_counters():
     lib().rl_transfer_counters_reset()
 
 
-def reset_batch_counter(next_batch=0):
-    lib().rl_trace_batch_counter_reset(next_batch)
 
 
 def vec3(x, y, z):
@@ -237,13 +263,13 @@ class SceneBuilder:
 
     def __init__(self, builtin=None, param=0):
         self._h = _P()
-        _check(lib().rl_scene_builder_create(C.byref(self._h)))
+        _check_host(host_lib().rl_scene_builder_create(C.byref(self._h)))
         if builtin is not None:
-            _check(lib().rl_scene_builder_builtin(self._h, builtin, param))
+            _check_host(host_lib().rl_scene_builder_builtin(self._h, builtin, param))
 
     def __del__(self):
         if getattr(self, "_h", None) and lib is not None:
-            lib().rl_scene_builder_destroy(self._h)
+            host_lib().rl_scene_builder_destroy(self._h)
             self._h = None
 
     def _idx(self, r):
@@ -252,28 +278,28 @@ class SceneBuilder:
         return r
 
     def plane(self, normal, offset):
-        return self._idx(lib().rl_scene_builder_plane(self._h, vec3(*normal), vec3(*offset)))
+        return self._idx(host_lib().rl_scene_builder_plane(self._h, vec3(*normal), vec3(*offset)))
 
     def circle(self, normal, position, radius):
-        return self._idx(lib().rl_scene_builder_circle(self._h, vec3(*normal), vec3(*position), radius))
+        return self._idx(host_lib().rl_scene_builder_circle(self._h, vec3(*normal), vec3(*position), radius))
 
     def sphere(self, position, radius):
-        return self._idx(lib().rl_scene_builder_sphere(self._h, vec3(*position), radius))
+        return self._idx(host_lib().rl_scene_builder_sphere(self._h, vec3(*position), radius))
 
     def paraboloid(self, normal, offset, focal_distance):
-        return self._idx(lib().rl_scene_builder_paraboloid(self._h, vec3(*normal), vec3(*offset), focal_distance))
+        return self._idx(host_lib().rl_scene_builder_paraboloid(self._h, vec3(*normal), vec3(*offset), focal_distance))
 
     def prism(self, axis, offset, edge_length, angle, height):
-        return self._idx(lib().rl_scene_builder_prism(self._h, vec3(*axis), vec3(*offset), edge_length, angle, height))
+        return self._idx(host_lib().rl_scene_builder_prism(self._h, vec3(*axis), vec3(*offset), edge_length, angle, height))
 
     def hexagonal_prism(self, axis, offset, edge_length, bevel_size, angle, height):
-        return self._idx(lib().rl_scene_builder_hexagonal_prism(
+        return self._idx(host_lib().rl_scene_builder_hexagonal_prism(
             self._h, vec3(*axis), vec3(*offset), edge_length, bevel_size, angle, height))
 
     @staticmethod
     def blackbody(kelvins, intensity):
         m = Material()
-        _check(lib().rl_material_blackbody(kelvins, intensity, C.byref(m)))
+        _check_host(host_lib().rl_material_blackbody(kelvins, intensity, C.byref(m)))
         return m
 
     @staticmethod
@@ -281,7 +307,7 @@ class SceneBuilder:
         return Material(kind, p0, p1, p2)
 
     def object(self, surface, material):
-        return self._idx(lib().rl_scene_builder_object(self._h, surface, material))
+        return self._idx(host_lib().rl_scene_builder_object(self._h, surface, material))
 
     def static_camera(self, position, orientation=(0.0, 0.0, 0.0, 1.0), field_of_view=0.35 * np.pi,
                       focal_distance=1.0, depth_of_field=1.0e9, chromatic_abberation=0.0):
@@ -289,15 +315,15 @@ class SceneBuilder:
         cm.kind = CAMERA_STATIC
         cm.fixed = Camera(vec3(*position), field_of_view, focal_distance, depth_of_field,
                           chromatic_abberation, Quat(*[float(v) for v in orientation]))
-        _check(lib().rl_scene_builder_camera(self._h, C.byref(cm)))
+        _check_host(host_lib().rl_scene_builder_camera(self._h, C.byref(cm)))
 
     def camera_model(self, cm):
-        _check(lib().rl_scene_builder_camera(self._h, C.byref(cm)))
+        _check_host(host_lib().rl_scene_builder_camera(self._h, C.byref(cm)))
 
     def desc(self):
         """Borrowed descriptor (valid while the builder is alive and unchanged)."""
         d = SceneDesc()
-        _check(lib().rl_scene_builder_desc(self._h, C.byref(d)))
+        _check_host(host_lib().rl_scene_builder_desc(self._h, C.byref(d)))
         d._owner = self
         return d
 
@@ -315,6 +341,10 @@ class Scene:
         if getattr(self, "_h", None) and lib is not None:
             lib().rl_scene_destroy(self._h)
             self._h = None
+
+    def reset_batch_counter(self, next_batch=0):
+        """The next TraceUnit.render on this scene takes batch number `next_batch`."""
+        _check(lib().rl_scene_batch_counter_reset(self._h, next_batch))
 
     # probes ---------------------------------------------------------------
     def intersect(self, rays):
@@ -372,7 +402,9 @@ class TraceUnit:
         """Records of the last render, copied out of the device now (rl_trace_unit_download)."""
         if out is None:
             out = np.zeros(self.batch, dtype=MAPPED_PHOTON)
-        _check(lib().rl_trace_unit_download(self._h, _ptr(out)))
+        count = _U64(0)
+        _check(lib().rl_trace_unit_download(self._h, _ptr(out), out.shape[0], C.byref(count)))
+        out = out[: int(count.value)]
         self.mapped_photons = out
         return out
 

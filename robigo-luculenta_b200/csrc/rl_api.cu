@@ -3,11 +3,13 @@
 // without a CUDA device every compute entry point returns RL_ERR_CUDA.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
 #include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <new>
 #include <string>
@@ -44,8 +46,6 @@ cudaError_t copy_async(void *dst, const void *src, size_t bytes, cudaMemcpyKind 
             return fail(RL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));      \
     } while (0)
 
-std::atomic<uint64_t> g_next_batch{0};
-
 struct Device {
     int index = 0;
     int sm_count = 148;
@@ -66,6 +66,22 @@ int current_device(Device &d) {
     return RL_OK;
 }
 
+// Entry points run on the handle's device and leave the calling thread's current device as
+// they found it (one process may drive several GPUs, or share the thread with torch).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched && prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 // A stream owned by the handle unless the caller bound its own.
 struct StreamSlot {
     cudaStream_t stream = nullptr;
@@ -78,10 +94,23 @@ struct StreamSlot {
         RL_CUDA(cudaEventCreateWithFlags(&event, cudaEventDisableTiming));
         return RL_OK;
     }
-    void bind(void *external) {
-        if (owned && stream) cudaStreamDestroy(stream);
-        if (external) { stream = (cudaStream_t)external; owned = false; }
-        else { cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking); owned = true; }
+    // Work queued on the old stream finishes before anything is queued on the new one (a render
+    // still writing the unit's buffers must not race with launches on the next stream).
+    int bind(void *external) {
+        cudaStream_t next = nullptr;
+        if (external) next = (cudaStream_t)external;
+        else RL_CUDA(cudaStreamCreateWithFlags(&next, cudaStreamNonBlocking));
+        if (stream) {
+            cudaError_t e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) {
+                if (!external) cudaStreamDestroy(next);
+                return fail(RL_ERR_CUDA, std::string("set_stream: ") + cudaGetErrorString(e));
+            }
+            if (owned) cudaStreamDestroy(stream);
+        }
+        stream = next;
+        owned = external == nullptr;
+        return RL_OK;
     }
     void destroy() {
         if (owned && stream) cudaStreamDestroy(stream);
@@ -101,12 +130,36 @@ int order_after(StreamSlot &earlier, StreamSlot &later) {
 }  // namespace
 
 // ------------------------------------------------------------------ handles
+// The trace service of a scene (csrc/rl_kernels.cu "K1b"): the ring the scene's batches are
+// queued in and the stream its workers run on.  Created with the first batch that uses it.
+struct TraceService {
+    std::mutex m;
+    ServiceQueue *d_queue = nullptr;
+    cudaStream_t workers = nullptr;
+    int reserved_sms = 0;
+    bool failed = false;
+    // Back-pressure.  render() returns once its batch is queued, so a host that recycles units
+    // faster than the GPU traces them (the scheduler's plot and trace tasks are all asynchronous
+    // here) would queue every unit it owns and then find nothing to do -- and the reference's
+    // idle task sleeps 100 ms (app.rs:128-130).  So a render that finds more than half of the
+    // scene's trace units in flight first waits for the oldest batch: worker threads wait inside
+    // render(), as they do in the reference, instead of in the sleep task.
+    std::mutex flight_m;
+    struct Flight { const volatile uint32_t *flag; uint32_t seq; const void *unit; };
+    std::deque<Flight> in_flight;        // the batches queued, oldest first
+    int units = 0;                       // trace units that have queued a batch to this service
+};
+
 struct rl_scene {
     Device dev;
     DevScene ds;
     void *d_blob = nullptr;
     void *d_materials = nullptr;
     size_t smem = 0;
+    // TraceUnit::render takes its photon ids from the scene's batch counter: one scene is one
+    // App (app.rs:63), two renders in one process do not share ids
+    mutable std::atomic<uint64_t> next_batch{0};
+    mutable TraceService service;
 };
 
 struct rl_trace_unit {
@@ -120,6 +173,16 @@ struct rl_trace_unit {
     uint64_t capacity = 0;
     uint64_t n_valid = 0;  // records left on the device by the last render
     unsigned long long *d_rays = nullptr;
+    // trace service: the word a finished batch stores its sequence number to, the number of the
+    // latest batch, and the event behind the latest push
+    volatile uint32_t *h_done = nullptr; // the completion word, in mapped page-locked host memory
+    uint32_t *d_done = nullptr;          // its device address
+    uint32_t done_seq = 0;
+    bool in_service = false;             // the latest batch went to the service and may still be in flight
+    rl_mapped_photon *pending_out = nullptr;   // host buffer the latest batch's records still have to be copied to
+    uint64_t pending_n = 0;
+    cudaEvent_t pushed = nullptr;
+    TraceService *service = nullptr;     // the service this unit is counted in
 };
 
 struct rl_plot_unit {
@@ -232,7 +295,7 @@ namespace {
 
 struct Flat {
     std::vector<float4> spheres, sphere_k, planes, paraboloids, leaves, compounds;
-    double cmax2 = 0.0;
+    double cmax2 = 0.0, leaf_off_max = 0.0;
     std::vector<uint32_t> ops, sphere_obj, plane_obj, paraboloid_obj, compound_obj;
 };
 
@@ -248,8 +311,12 @@ bool emit_compound(const rl_scene_desc *d, uint32_t node, Flat &fl, uint32_t fir
     if (s.kind == RL_SURFACE_HALFSPACE) {
         uint32_t rel = (uint32_t)(fl.leaves.size() / 2) - first_leaf;
         if (rel > 254) return false;
-        fl.leaves.push_back(f4(s.a, 0.f));
+        // w of the normal record: max(1, |n|), the scale of the slab test's inflation
+        const double nlen = sqrt((double)s.a.x * s.a.x + (double)s.a.y * s.a.y + (double)s.a.z * s.a.z);
+        fl.leaves.push_back(f4(s.a, (float)(nlen > 1.0 ? nlen * 1.000001 : 1.0)));
         fl.leaves.push_back(f4(s.b, 0.f));
+        const double olen = sqrt((double)s.b.x * s.b.x + (double)s.b.y * s.b.y + (double)s.b.z * s.b.z);
+        if (olen > fl.leaf_off_max) fl.leaf_off_max = olen;
         fl.ops.push_back(0u | (rel << 8));
         lo = rel; hi = rel + 1;
         return true;
@@ -379,6 +446,105 @@ int max_stack(const std::vector<uint32_t> &ops, size_t first, size_t n) {
         if (sp > mx) mx = sp;
     }
     return mx;
+}
+
+// ---- trace service plumbing ------------------------------------------------------------------
+int env_int(const char *name, int fallback) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : fallback;
+}
+
+// Completion words.  A finished batch stores its sequence number to a word in mapped page-locked
+// host memory; whoever needs the batch (the unit's next call, the plot unit that splats its
+// records, sync) polls that word from the host -- no stream ever waits on the service, so no
+// hardware queue is blocked behind a batch that is still being traced.  (Both device-side
+// alternatives were measured on the scheduler replay: cuStreamWaitValue32 deschedules the channel
+// for milliseconds per wait, 77 Mrays/s; a polling kernel per unit holds its hardware queue,
+// 1 850 Mrays/s; one launch per batch without the service: 2 490.)  The words live in slabs that are
+// never freed, so a thread that still polls a word of a unit that has just been destroyed reads
+// valid memory; a recycled word keeps counting from where its last owner stopped.
+struct FlagPool {
+    std::mutex m;
+    std::vector<volatile uint32_t *> free_words;
+    int take(volatile uint32_t **host, uint32_t **device) {
+        std::lock_guard<std::mutex> lock(m);
+        if (free_words.empty()) {
+            void *slab = nullptr;
+            const size_t words = 1024;
+            RL_CUDA(cudaHostAlloc(&slab, words * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+            memset(slab, 0, words * sizeof(uint32_t));
+            for (size_t i = 0; i < words; i++) free_words.push_back(static_cast<volatile uint32_t *>(slab) + i);
+        }
+        *host = free_words.back();
+        free_words.pop_back();
+        void *d = nullptr;
+        cudaError_t e = cudaHostGetDevicePointer(&d, const_cast<uint32_t *>(*host), 0);
+        if (e != cudaSuccess) {
+            free_words.push_back(*host);
+            return fail(RL_ERR_CUDA, std::string("cudaHostGetDevicePointer: ") + cudaGetErrorString(e));
+        }
+        *device = static_cast<uint32_t *>(d);
+        return RL_OK;
+    }
+    void give_back(volatile uint32_t *host) {
+        std::lock_guard<std::mutex> lock(m);
+        free_words.push_back(host);
+    }
+};
+FlagPool g_flags;
+
+// Host wait until *flag has reached `seq` (sequence numbers, wrap-around compare).
+int wait_flag(const volatile uint32_t *flag, uint32_t seq, cudaStream_t workers) {
+    const auto reached = [&] { return (int32_t)(*flag - seq) >= 0; };
+    for (int spin = 0; spin < 2000; spin++) {
+        if (reached()) return RL_OK;
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint64_t polls = 0;; polls++) {
+        if (reached()) return RL_OK;
+        std::this_thread::sleep_for(std::chrono::microseconds(polls < 50 ? 5 : 25));
+        if ((polls & 0x3fff) == 0x3fff) {
+            // a worker that died takes its batches with it: report instead of waiting for ever
+            cudaError_t e = workers ? cudaStreamQuery(workers) : cudaSuccess;
+            if (e != cudaSuccess && e != cudaErrorNotReady)
+                return fail(RL_ERR_CUDA, std::string("trace service: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(env_int("RL_SERVICE_TIMEOUT_S", 300)))
+                return fail(RL_ERR_CUDA, "trace service: a batch did not finish (RL_SERVICE_TIMEOUT_S)");
+        }
+    }
+}
+
+// Batches below this size go through the trace service (0: never).  The same bound as the
+// small-launch rule of launch_trace: fewer than 64 photons per thread of a full grid.
+bool use_service(const rl_scene *scene, uint64_t n_photons) {
+    if (n_photons == 0 || n_photons > (1ull << 28)) return false;
+    if (scene->service.failed || !env_int("RL_TRACE_SERVICE", 1)) return false;
+    return n_photons < 64ull * (uint64_t)scene->dev.sm_count * 768ull;
+}
+
+int service_get(const rl_scene *scene, TraceService **out) {
+    TraceService &svc = scene->service;
+    std::lock_guard<std::mutex> lock(svc.m);
+    if (!svc.d_queue) {
+        cudaError_t e = cudaMalloc(&svc.d_queue, sizeof(ServiceQueue));
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&svc.workers, cudaStreamNonBlocking);
+        // the ring is cleared before any unit's stream can push to it (a memset is asynchronous,
+        // and the units' non-blocking streams are not ordered behind the default stream)
+        if (e == cudaSuccess) e = cudaMemsetAsync(svc.d_queue, 0, sizeof(ServiceQueue), svc.workers);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(svc.workers);
+        if (e != cudaSuccess) {
+            cudaFree(svc.d_queue); svc.d_queue = nullptr; svc.failed = true;
+            return fail(RL_ERR_CUDA, std::string("trace service: ") + cudaGetErrorString(e));
+        }
+        int reserved = env_int("RL_SERVICE_RESERVED_SMS", 2);
+        svc.reserved_sms = reserved < 0 ? 0 : (reserved > scene->dev.sm_count - 1 ? scene->dev.sm_count - 1 : reserved);
+    }
+    *out = &svc;
+    return RL_OK;
 }
 
 template <class T>
@@ -537,6 +703,11 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
         return fail(RL_ERR_UNSUPPORTED, "more than 65535 half-spaces in compound surfaces");
     }
     ds.off_leaves = append(blob, fl.leaves);            ds.n_leaves = (uint32_t)fl.leaves.size() / 2;
+    // (lane, cluster) and (lane, body) pair records index their table with RL_PAIR_INDEX_BITS bits
+    if (fl.compounds.size() / 2 > RL_PAIR_INDEX_MAX || clusters.size() > RL_PAIR_INDEX_MAX) {
+        delete sc;
+        return fail(RL_ERR_UNSUPPORTED, "more than 2047 compound surfaces (or sphere clusters) in one scene");
+    }
     ds.off_compounds = append(blob, fl.compounds);      ds.n_compounds = (uint32_t)fl.compounds.size() / 2;
     ds.off_ops = append(blob, fl.ops);                  ds.n_ops = (uint32_t)fl.ops.size();
     ds.off_sphere_k = append(blob, fl.sphere_k);
@@ -544,6 +715,7 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     ds.off_cluster_range = append(blob, cluster_range);
     ds.sphere_cmax2 = (float)(fl.cmax2 * 1.0001);
     ds.cluster_rmax = (float)(cluster_rmax * 1.0001);
+    ds.leaf_off_max = (float)(fl.leaf_off_max * 1.0001);
     ds.off_plane_obj = append(blob, fl.plane_obj);
     ds.off_paraboloid_obj = append(blob, fl.paraboloid_obj);
     ds.off_compound_obj = append(blob, fl.compound_obj);
@@ -597,7 +769,13 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
 
 int rl_scene_destroy(rl_scene *scene) {
     if (!scene) return RL_OK;
-    cudaSetDevice(scene->dev.index);
+    DeviceGuard guard(scene->dev.index);
+    if (scene->service.workers) {
+        // workers retire by themselves once the ring stays empty
+        cudaStreamSynchronize(scene->service.workers);
+        cudaStreamDestroy(scene->service.workers);
+    }
+    cudaFree(scene->service.d_queue);
     cudaFree(scene->d_blob);
     cudaFree(scene->d_materials);
     delete scene;
@@ -615,18 +793,58 @@ int rl_trace_unit_create(uint64_t id, uint32_t width, uint32_t height, uint64_t 
     if (rc == RL_OK) rc = u->ss.create();
     if (rc != RL_OK) { delete u; return rc; }
     cudaError_t e = cudaMalloc(&u->d_rays, sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(u->d_rays, 0, sizeof(unsigned long long));
-    if (e != cudaSuccess) { u->ss.destroy(); delete u; return fail(RL_ERR_CUDA, cudaGetErrorString(e)); }
+    // cleared on the unit's own stream: everything the unit does later is ordered behind it
+    if (e == cudaSuccess) e = cudaMemsetAsync(u->d_rays, 0, sizeof(unsigned long long), u->ss.stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&u->pushed, cudaEventDisableTiming);
+    if (e == cudaSuccess && g_flags.take(&u->h_done, &u->d_done) != RL_OK) e = cudaErrorMemoryAllocation;
+    if (e != cudaSuccess) {
+        cudaFree(u->d_rays);
+        if (u->pushed) cudaEventDestroy(u->pushed);
+        u->ss.destroy(); delete u;
+        return fail(RL_ERR_CUDA, cudaGetErrorString(e));
+    }
+    u->done_seq = *u->h_done;            // a recycled completion word keeps counting
     *out = u;
+    return RL_OK;
+}
+
+// The unit's latest batch is finished (host wait on its completion word).
+static int trace_wait_done(rl_trace_unit *u) {
+    if (!u->in_service) return RL_OK;
+    int rc = wait_flag(u->h_done, u->done_seq, u->service ? u->service->workers : nullptr);
+    if (rc != RL_OK) return rc;
+    u->in_service = false;
+    return RL_OK;
+}
+
+// ... and the copy of its records into the host buffer render() was given is queued.
+static int trace_finish(rl_trace_unit *u) {
+    int rc = trace_wait_done(u);
+    if (rc != RL_OK) return rc;
+    if (u->pending_out) {
+        rl_mapped_photon *out = u->pending_out;
+        u->pending_out = nullptr;
+        RL_CUDA(copy_async(out, u->d_records, u->pending_n * sizeof(rl_mapped_photon), cudaMemcpyDeviceToHost,
+                           u->ss.stream));
+    }
     return RL_OK;
 }
 
 int rl_trace_unit_destroy(rl_trace_unit *u) {
     if (!u) return RL_OK;
-    cudaSetDevice(u->dev.index);
+    DeviceGuard guard(u->dev.index);
+    trace_finish(u);
     if (u->ss.stream) cudaStreamSynchronize(u->ss.stream);
+    if (u->service) {
+        std::lock_guard<std::mutex> lock(u->service->flight_m);
+        auto &q = u->service->in_flight;
+        q.erase(std::remove_if(q.begin(), q.end(), [u](const TraceService::Flight &f) { return f.unit == u; }), q.end());
+        u->service->units--;
+    }
     cudaFree(u->d_records);
     cudaFree(u->d_rays);
+    if (u->h_done) g_flags.give_back(u->h_done);
+    if (u->pushed) cudaEventDestroy(u->pushed);
     u->ss.destroy();
     delete u;
     return RL_OK;
@@ -640,9 +858,10 @@ int rl_trace_unit_set_batch_size(rl_trace_unit *u, uint64_t n) {
 
 int rl_trace_unit_set_stream(rl_trace_unit *u, void *s) {
     if (!u) return fail(RL_ERR_INVALID, "null unit");
-    cudaSetDevice(u->dev.index);
-    u->ss.bind(s);
-    return RL_OK;
+    DeviceGuard guard(u->dev.index);
+    int rc = trace_finish(u);
+    if (rc != RL_OK) return rc;
+    return u->ss.bind(s);
 }
 
 static int ensure_records(rl_trace_unit *u, uint64_t n) {
@@ -655,22 +874,91 @@ static int ensure_records(rl_trace_unit *u, uint64_t n) {
     return RL_OK;
 }
 
+// Queue photons [first, first + n) of `scene` on the unit's stream: through the trace service
+// when the batch is small (the reference's 524 288-photon batches) and leaves records, as one
+// launch otherwise.  `*serviced` tells which.
+static int queue_trace(rl_trace_unit *u, const rl_scene *scene, uint64_t first_photon, uint64_t n_photons,
+                       rl_mapped_photon *records, float4 *accum, bool *serviced) {
+    *serviced = false;
+    if (n_photons == 0) return RL_OK;
+    // a fused batch is consumed by the plot unit's stream: it stays a launch, ordered by events
+    if (!accum && use_service(scene, n_photons)) {
+        TraceService *svc = nullptr;
+        int rc = service_get(scene, &svc);
+        if (rc != RL_OK) return rc;
+        ServiceEntry e;
+        memset(&e, 0, sizeof(e));
+        e.seed = u->seed; e.first_photon = first_photon; e.n_photons = (uint32_t)n_photons;
+        e.records = records; e.accum = nullptr; e.ray_counter = u->d_rays;
+        e.width = u->width; e.height = u->height;
+        e.aspect = (float)u->width / (float)u->height;            // trace_unit.rs:73, plot_unit.rs:49
+        e.done_flag = u->d_done; e.done_value = ++u->done_seq;
+        // the push runs in stream order (after whatever still reads the unit's records); a worker
+        // is launched behind it, so that every queued batch has a worker that starts after it is
+        // visible -- whichever worker is resident when the push lands takes the photons
+        RL_CUDA(launch_service_push(svc->d_queue, e, u->ss.stream));
+        RL_CUDA(cudaEventRecord(u->pushed, u->ss.stream));
+        RL_CUDA(cudaStreamWaitEvent(svc->workers, u->pushed, 0));
+        RL_CUDA(launch_service_worker(scene->ds, svc->d_queue, scene->dev.sm_count, svc->reserved_sms, svc->workers));
+        u->in_service = true;
+        *serviced = true;
+        // back-pressure (see TraceService): at most half of the scene's units in flight
+        if (u->service && u->service != svc) {                   // the unit moved to another scene
+            std::lock_guard<std::mutex> lock(u->service->flight_m);
+            auto &q = u->service->in_flight;
+            q.erase(std::remove_if(q.begin(), q.end(), [u](const TraceService::Flight &f) { return f.unit == u; }), q.end());
+            u->service->units--;
+            u->service = nullptr;
+        }
+        TraceService::Flight oldest{nullptr, 0, nullptr};
+        {
+            std::lock_guard<std::mutex> lock(svc->flight_m);
+            if (!u->service) { u->service = svc; svc->units++; }
+            auto &q = svc->in_flight;
+            q.erase(std::remove_if(q.begin(), q.end(), [u](const TraceService::Flight &f) { return f.unit == u; }), q.end());
+            q.push_back(TraceService::Flight{u->h_done, e.done_value, u});
+            const size_t depth = (size_t)env_int("RL_TRACE_DEPTH", 0);
+            const size_t limit = depth ? depth : (size_t)std::max(2, svc->units / 2);
+            if (q.size() > limit) { oldest = q.front(); q.pop_front(); }
+        }
+        if (oldest.flag && oldest.unit != u) {
+            rc = wait_flag(oldest.flag, oldest.seq, svc->workers);
+            if (rc != RL_OK) return rc;
+        }
+        return RL_OK;
+    }
+    TraceLaunch p;
+    p.seed = u->seed; p.first_photon = first_photon; p.n_photons = n_photons;
+    p.width = u->width; p.height = u->height;
+    p.records = records; p.accum = accum; p.ray_counter = u->d_rays;
+    RL_CUDA(launch_trace(scene->ds, p, u->dev.sm_count, u->ss.stream));
+    return RL_OK;
+}
+
 static int render_range(rl_trace_unit *u, const rl_scene *scene, uint64_t first_photon,
                         uint64_t n_photons, rl_mapped_photon *out, bool wait) {
     if (!u || !scene) return fail(RL_ERR_INVALID, "rl_trace_unit_render: null argument");
     if (scene->dev.index != u->dev.index) return fail(RL_ERR_INVALID, "scene and unit on different devices");
-    RL_CUDA(cudaSetDevice(u->dev.index));
-    int rc = ensure_records(u, n_photons);
+    DeviceGuard guard(u->dev.index);
+    int rc = trace_finish(u);                    // the previous batch and the copy of its records
+    if (rc == RL_OK) rc = ensure_records(u, n_photons);
     if (rc != RL_OK) return rc;
-    TraceLaunch p;
-    p.seed = u->seed; p.first_photon = first_photon; p.n_photons = n_photons;
-    p.width = u->width; p.height = u->height;
-    p.records = u->d_records; p.accum = nullptr; p.ray_counter = u->d_rays;
-    RL_CUDA(launch_trace(scene->ds, p, u->dev.sm_count, u->ss.stream));
+    bool serviced = false;
+    rc = queue_trace(u, scene, first_photon, n_photons, u->d_records, nullptr, &serviced);
+    if (rc != RL_OK) return rc;
     u->n_valid = n_photons;
-    if (out) {
-        RL_CUDA(copy_async(out, u->d_records, n_photons * sizeof(rl_mapped_photon),
-                                cudaMemcpyDeviceToHost, u->ss.stream));
+    if (out && n_photons) {
+        if (serviced) {
+            // the copy is queued once the batch is finished: by the next call on this unit, by the
+            // plot unit that takes its records, or by sync -- `out` is complete after sync
+            u->pending_out = out;
+            u->pending_n = n_photons;
+            if (wait) rc = trace_finish(u);
+            if (rc != RL_OK) return rc;
+        } else {
+            RL_CUDA(copy_async(out, u->d_records, n_photons * sizeof(rl_mapped_photon),
+                               cudaMemcpyDeviceToHost, u->ss.stream));
+        }
         if (wait) RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     }
     return RL_OK;
@@ -682,24 +970,29 @@ int rl_trace_unit_render_range(rl_trace_unit *u, const rl_scene *scene, uint64_t
 }
 
 int rl_trace_unit_render(rl_trace_unit *u, const rl_scene *scene, rl_mapped_photon *out) {
-    if (!u) return fail(RL_ERR_INVALID, "null unit");
-    const uint64_t b = g_next_batch.fetch_add(1);
+    if (!u || !scene) return fail(RL_ERR_INVALID, "rl_trace_unit_render: null argument");
+    const uint64_t b = scene->next_batch.fetch_add(1);
     return render_range(u, scene, b * u->batch, u->batch, out, true);
 }
 
 int rl_trace_unit_render_async(rl_trace_unit *u, const rl_scene *scene, rl_mapped_photon *out) {
-    if (!u) return fail(RL_ERR_INVALID, "null unit");
-    const uint64_t b = g_next_batch.fetch_add(1);
+    if (!u || !scene) return fail(RL_ERR_INVALID, "rl_trace_unit_render_async: null argument");
+    const uint64_t b = scene->next_batch.fetch_add(1);
     return render_range(u, scene, b * u->batch, u->batch, out, false);
 }
 
-int rl_trace_unit_download(rl_trace_unit *u, rl_mapped_photon *out) {
-    if (!u || !out) return fail(RL_ERR_INVALID, "rl_trace_unit_download: null argument");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+int rl_trace_unit_download(rl_trace_unit *u, rl_mapped_photon *out, uint64_t capacity, uint64_t *out_count) {
+    if (!u || (!out && capacity)) return fail(RL_ERR_INVALID, "rl_trace_unit_download: null argument");
+    if (u->n_valid > capacity)
+        return fail(RL_ERR_INVALID, "rl_trace_unit_download: the last render left more records than `capacity`");
+    DeviceGuard guard(u->dev.index);
+    int rc = trace_finish(u);
+    if (rc != RL_OK) return rc;
     if (u->n_valid)
         RL_CUDA(copy_async(out, u->d_records, u->n_valid * sizeof(rl_mapped_photon), cudaMemcpyDeviceToHost,
                            u->ss.stream));
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    if (out_count) *out_count = u->n_valid;
     return RL_OK;
 }
 
@@ -710,21 +1003,22 @@ int rl_trace_unit_render_fused(rl_trace_unit *u, const rl_scene *scene, rl_plot_
         return fail(RL_ERR_INVALID, "scene, trace unit and plot unit must share a device");
     if (plot->width != u->width || plot->height != u->height)
         return fail(RL_ERR_INVALID, "trace and plot unit canvas sizes differ");
-    RL_CUDA(cudaSetDevice(u->dev.index));
-    int rc = order_after(plot->ss, u->ss);
+    DeviceGuard guard(u->dev.index);
+    int rc = trace_finish(u);
+    if (rc == RL_OK) rc = order_after(plot->ss, u->ss);
     if (rc != RL_OK) return rc;
-    TraceLaunch p;
-    p.seed = u->seed; p.first_photon = first_photon; p.n_photons = n_photons;
-    p.width = u->width; p.height = u->height;
-    p.records = nullptr; p.accum = plot->d_accum; p.ray_counter = u->d_rays;
-    RL_CUDA(launch_trace(scene->ds, p, u->dev.sm_count, u->ss.stream));
+    bool serviced = false;
+    rc = queue_trace(u, scene, first_photon, n_photons, nullptr, plot->d_accum, &serviced);
+    if (rc != RL_OK) return rc;
     u->n_valid = 0;
     return order_after(u->ss, plot->ss);
 }
 
 int rl_trace_unit_ray_count(rl_trace_unit *u, uint64_t *out_rays) {
     if (!u || !out_rays) return fail(RL_ERR_INVALID, "null argument");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
+    int rc = trace_wait_done(u);
+    if (rc != RL_OK) return rc;
     unsigned long long v = 0;
     RL_CUDA(copy_async(&v, u->d_rays, sizeof(v), cudaMemcpyDeviceToHost, u->ss.stream));
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
@@ -734,12 +1028,18 @@ int rl_trace_unit_ray_count(rl_trace_unit *u, uint64_t *out_rays) {
 
 int rl_trace_unit_sync(rl_trace_unit *u) {
     if (!u) return fail(RL_ERR_INVALID, "null unit");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
+    int rc = trace_finish(u);
+    if (rc != RL_OK) return rc;
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     return RL_OK;
 }
 
-void rl_trace_batch_counter_reset(uint64_t next_batch) { g_next_batch.store(next_batch); }
+int rl_scene_batch_counter_reset(const rl_scene *scene, uint64_t next_batch) {
+    if (!scene) return fail(RL_ERR_INVALID, "null scene");
+    scene->next_batch.store(next_batch);
+    return RL_OK;
+}
 
 void rl_transfer_counters(uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
     if (h2d_bytes) *h2d_bytes = g_h2d_bytes.load();
@@ -776,7 +1076,9 @@ int rl_plot_unit_create(uint64_t id, uint32_t width, uint32_t height, rl_plot_un
     const size_t n = (size_t)width * height;
     cudaError_t e = cudaMalloc(&u->d_accum, n * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc(&u->d_packed, n * 3 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMemset(u->d_accum, 0, n * sizeof(float4));
+    // cleared on the unit's own stream: everything the unit does later is ordered behind it (a
+    // memset on the default stream would not be, the units' streams are non-blocking)
+    if (e == cudaSuccess) e = cudaMemsetAsync(u->d_accum, 0, n * sizeof(float4), u->ss.stream);
     if (e != cudaSuccess) {
         cudaFree(u->d_accum); cudaFree(u->d_packed); u->ss.destroy(); delete u;
         return fail(RL_ERR_CUDA, cudaGetErrorString(e));
@@ -787,7 +1089,7 @@ int rl_plot_unit_create(uint64_t id, uint32_t width, uint32_t height, rl_plot_un
 
 int rl_plot_unit_destroy(rl_plot_unit *u) {
     if (!u) return RL_OK;
-    cudaSetDevice(u->dev.index);
+    DeviceGuard guard(u->dev.index);
     if (u->ss.stream) cudaStreamSynchronize(u->ss.stream);
     cudaFree(u->d_accum); cudaFree(u->d_packed); cudaFree(u->d_staging);
     u->ss.destroy();
@@ -797,15 +1099,14 @@ int rl_plot_unit_destroy(rl_plot_unit *u) {
 
 int rl_plot_unit_set_stream(rl_plot_unit *u, void *s) {
     if (!u) return fail(RL_ERR_INVALID, "null unit");
-    cudaSetDevice(u->dev.index);
-    u->ss.bind(s);
-    return RL_OK;
+    DeviceGuard guard(u->dev.index);
+    return u->ss.bind(s);
 }
 
 int rl_plot_unit_plot(rl_plot_unit *u, const rl_mapped_photon *photons, uint64_t n) {
     if (!u || (!photons && n)) return fail(RL_ERR_INVALID, "rl_plot_unit_plot: null argument");
     if (n == 0) return RL_OK;
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
     if (u->staging_capacity < n) {
         RL_CUDA(cudaStreamSynchronize(u->ss.stream));
         cudaFree(u->d_staging);
@@ -826,24 +1127,31 @@ int rl_plot_unit_plot_device(rl_plot_unit *u, rl_trace_unit *trace) {
     if (!u || !trace) return fail(RL_ERR_INVALID, "rl_plot_unit_plot_device: null argument");
     if (u->dev.index != trace->dev.index) return fail(RL_ERR_INVALID, "units on different devices");
     if (trace->n_valid == 0) return RL_OK;
-    RL_CUDA(cudaSetDevice(u->dev.index));
-    int rc = order_after(trace->ss, u->ss);
+    DeviceGuard guard(u->dev.index);
+    // the records are complete (host wait if the batch went through the trace service); the splat
+    // is ordered behind what the trace unit's stream holds NOW, then the copy of the records to the
+    // host is queued on that stream -- it runs beside the splat, and the unit's next batch is
+    // ordered behind both
+    int rc = trace_wait_done(trace);
+    if (rc == RL_OK) rc = order_after(trace->ss, u->ss);
     if (rc != RL_OK) return rc;
     RL_CUDA(launch_splat(trace->d_records, trace->n_valid, u->d_accum, u->width, u->height,
                          u->dev.sm_count, u->ss.stream));
+    rc = trace_finish(trace);
+    if (rc != RL_OK) return rc;
     return order_after(u->ss, trace->ss);
 }
 
 int rl_plot_unit_clear(rl_plot_unit *u) {
     if (!u) return fail(RL_ERR_INVALID, "null unit");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
     RL_CUDA(cudaMemsetAsync(u->d_accum, 0, (size_t)u->width * u->height * sizeof(float4), u->ss.stream));
     return RL_OK;
 }
 
 int rl_plot_unit_download(rl_plot_unit *u, float *xyz) {
     if (!u || !xyz) return fail(RL_ERR_INVALID, "rl_plot_unit_download: null argument");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
     const uint64_t n = (uint64_t)u->width * u->height;
     RL_CUDA(launch_pack_xyz(u->d_accum, u->d_packed, n, u->ss.stream));
     RL_CUDA(copy_async(xyz, u->d_packed, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
@@ -861,7 +1169,7 @@ int rl_plot_unit_device_buffer(rl_plot_unit *u, void **out_ptr, size_t *out_byte
 int rl_plot_unit_ipc_export(rl_plot_unit *u, void *handle_out) {
     if (!u || !handle_out) return fail(RL_ERR_INVALID, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == RL_IPC_HANDLE_BYTES, "IPC handle size");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
     cudaIpcMemHandle_t h;
     RL_CUDA(cudaIpcGetMemHandle(&h, u->d_accum));
     memcpy(handle_out, &h, sizeof(h));
@@ -884,7 +1192,7 @@ int rl_ipc_close(void *ptr) {
 
 int rl_plot_unit_sync(rl_plot_unit *u) {
     if (!u) return fail(RL_ERR_INVALID, "null unit");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     return RL_OK;
 }
@@ -903,8 +1211,8 @@ int rl_gather_unit_create(uint32_t width, uint32_t height, const char *resume_pa
     cudaError_t e = cudaMalloc(&u->d_acc, bytes);
     if (e == cudaSuccess) e = cudaMalloc(&u->d_comp, bytes);
     if (e == cudaSuccess) e = cudaMalloc(&u->d_staging, bytes);
-    if (e == cudaSuccess) e = cudaMemset(u->d_acc, 0, bytes);
-    if (e == cudaSuccess) e = cudaMemset(u->d_comp, 0, bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(u->d_acc, 0, bytes, u->ss.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(u->d_comp, 0, bytes, u->ss.stream);
     if (e != cudaSuccess) {
         cudaFree(u->d_acc); cudaFree(u->d_comp); cudaFree(u->d_staging); u->ss.destroy(); delete u;
         return fail(RL_ERR_CUDA, cudaGetErrorString(e));
@@ -924,7 +1232,7 @@ int rl_gather_unit_create(uint32_t width, uint32_t height, const char *resume_pa
 
 int rl_gather_unit_destroy(rl_gather_unit *u) {
     if (!u) return RL_OK;
-    cudaSetDevice(u->dev.index);
+    DeviceGuard guard(u->dev.index);
     if (u->ss.stream) cudaStreamSynchronize(u->ss.stream);
     u->writer.shutdown();          // writes out a snapshot that is still queued
     cudaFree(u->d_acc); cudaFree(u->d_comp); cudaFree(u->d_staging);
@@ -935,14 +1243,13 @@ int rl_gather_unit_destroy(rl_gather_unit *u) {
 
 int rl_gather_unit_set_stream(rl_gather_unit *u, void *s) {
     if (!u) return fail(RL_ERR_INVALID, "null unit");
-    cudaSetDevice(u->dev.index);
-    u->ss.bind(s);
-    return RL_OK;
+    DeviceGuard guard(u->dev.index);
+    return u->ss.bind(s);
 }
 
 int rl_gather_unit_accumulate(rl_gather_unit *u, const float *xyz) {
     if (!u || !xyz) return fail(RL_ERR_INVALID, "rl_gather_unit_accumulate: null argument");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
     const uint64_t n = (uint64_t)u->width * u->height;
     RL_CUDA(copy_async(u->d_staging, xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice, u->ss.stream));
     RL_CUDA(launch_gather(u->d_acc, u->d_comp, nullptr, 0, u->d_staging, nullptr, n, u->dev.sm_count,
@@ -956,7 +1263,7 @@ int rl_gather_unit_accumulate_plot(rl_gather_unit *u, rl_plot_unit *plot, int cl
     if (u->dev.index != plot->dev.index) return fail(RL_ERR_INVALID, "units on different devices");
     if (u->width != plot->width || u->height != plot->height)
         return fail(RL_ERR_INVALID, "gather and plot unit canvas sizes differ");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
     int rc = order_after(plot->ss, u->ss);
     if (rc != RL_OK) return rc;
     const float4 *src = plot->d_accum;
@@ -967,7 +1274,7 @@ int rl_gather_unit_accumulate_plot(rl_gather_unit *u, rl_plot_unit *plot, int cl
 
 int rl_gather_unit_accumulate_device(rl_gather_unit *u, const void *const *bufs, uint32_t n_buffers) {
     if (!u || (!bufs && n_buffers)) return fail(RL_ERR_INVALID, "rl_gather_unit_accumulate_device: null argument");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
     const uint64_t n = (uint64_t)u->width * u->height;
     for (uint32_t i = 0; i < n_buffers; i += 8) {
         const float4 *srcs[8];
@@ -981,7 +1288,7 @@ int rl_gather_unit_accumulate_device(rl_gather_unit *u, const void *const *bufs,
 
 int rl_gather_unit_save(rl_gather_unit *u, const char *path) {
     if (!u || !path) return fail(RL_ERR_INVALID, "rl_gather_unit_save: null argument");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
     SaveWriter &wr = u->writer;
     const size_t n = (size_t)u->width * u->height * 3;
     if (!wr.buf[0]) {
@@ -1057,7 +1364,7 @@ int rl_gather_unit_flush(rl_gather_unit *u) {
 
 int rl_gather_unit_load(rl_gather_unit *u, const char *path) {
     if (!u || !path) return fail(RL_ERR_INVALID, "rl_gather_unit_load: null argument");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
     {
         const std::string e = u->writer.flush();     // a queued save of the same file lands first
         if (!e.empty()) return fail(RL_ERR_IO, e);
@@ -1082,7 +1389,7 @@ int rl_gather_unit_load(rl_gather_unit *u, const char *path) {
 
 int rl_gather_unit_download(rl_gather_unit *u, float *xyz, float *comp) {
     if (!u || !xyz) return fail(RL_ERR_INVALID, "rl_gather_unit_download: null argument");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
     const size_t bytes = (size_t)u->width * u->height * 3 * sizeof(float);
     RL_CUDA(copy_async(xyz, u->d_acc, bytes, cudaMemcpyDeviceToHost, u->ss.stream));
     if (comp) RL_CUDA(copy_async(comp, u->d_comp, bytes, cudaMemcpyDeviceToHost, u->ss.stream));
@@ -1092,7 +1399,7 @@ int rl_gather_unit_download(rl_gather_unit *u, float *xyz, float *comp) {
 
 int rl_gather_unit_sync(rl_gather_unit *u) {
     if (!u) return fail(RL_ERR_INVALID, "null unit");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     return RL_OK;
 }
@@ -1122,7 +1429,7 @@ int rl_tonemap_unit_create(uint32_t width, uint32_t height, rl_tonemap_unit **ou
 
 int rl_tonemap_unit_destroy(rl_tonemap_unit *u) {
     if (!u) return RL_OK;
-    cudaSetDevice(u->dev.index);
+    DeviceGuard guard(u->dev.index);
     if (u->ss.stream) cudaStreamSynchronize(u->ss.stream);
     cudaFree(u->d_xyz); cudaFree(u->d_rgb); cudaFree(u->d_moments); cudaFree(u->d_exposure);
     u->ss.destroy();
@@ -1132,9 +1439,8 @@ int rl_tonemap_unit_destroy(rl_tonemap_unit *u) {
 
 int rl_tonemap_unit_set_stream(rl_tonemap_unit *u, void *s) {
     if (!u) return fail(RL_ERR_INVALID, "null unit");
-    cudaSetDevice(u->dev.index);
-    u->ss.bind(s);
-    return RL_OK;
+    DeviceGuard guard(u->dev.index);
+    return u->ss.bind(s);
 }
 
 static int tonemap_device(rl_tonemap_unit *u, const float *d_xyz, uint8_t *rgb) {
@@ -1151,7 +1457,7 @@ static int tonemap_device(rl_tonemap_unit *u, const float *d_xyz, uint8_t *rgb) 
 
 int rl_tonemap_unit_tonemap(rl_tonemap_unit *u, const float *xyz, uint8_t *rgb) {
     if (!u || !xyz || !rgb) return fail(RL_ERR_INVALID, "rl_tonemap_unit_tonemap: null argument");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
     RL_CUDA(copy_async(u->d_xyz, xyz, (size_t)u->width * u->height * 3 * sizeof(float),
                             cudaMemcpyHostToDevice, u->ss.stream));
     return tonemap_device(u, u->d_xyz, rgb);
@@ -1162,7 +1468,7 @@ int rl_tonemap_unit_tonemap_gather(rl_tonemap_unit *u, rl_gather_unit *g, uint8_
     if (u->dev.index != g->dev.index) return fail(RL_ERR_INVALID, "units on different devices");
     if (u->width != g->width || u->height != g->height)
         return fail(RL_ERR_INVALID, "tonemap and gather unit canvas sizes differ");
-    RL_CUDA(cudaSetDevice(u->dev.index));
+    DeviceGuard guard(u->dev.index);
     int rc = order_after(g->ss, u->ss);
     if (rc != RL_OK) return rc;
     rc = tonemap_device(u, g->d_acc, rgb);
@@ -1180,7 +1486,7 @@ int rl_tonemap_unit_last_exposure(rl_tonemap_unit *u, float *out) {
 int rl_debug_intersect(const rl_scene *scene, const rl_ray *rays, uint64_t n, rl_hit *out) {
     if (!scene || (!rays && n) || (!out && n)) return fail(RL_ERR_INVALID, "null argument");
     if (n == 0) return RL_OK;
-    RL_CUDA(cudaSetDevice(scene->dev.index));
+    DeviceGuard guard(scene->dev.index);
     rl_ray *d_rays = nullptr; rl_hit *d_out = nullptr;
     RL_CUDA(cudaMalloc(&d_rays, n * sizeof(rl_ray)));
     cudaError_t e = cudaMalloc(&d_out, n * sizeof(rl_hit));
@@ -1196,7 +1502,7 @@ int rl_debug_cull_check(const rl_scene *scene, uint64_t seed, uint32_t width, ui
                         uint64_t first_photon, uint64_t n, uint64_t *out_rays, uint64_t *out_mismatches) {
     if (!scene || !out_rays || !out_mismatches || width == 0 || height == 0)
         return fail(RL_ERR_INVALID, "bad argument");
-    RL_CUDA(cudaSetDevice(scene->dev.index));
+    DeviceGuard guard(scene->dev.index);
     unsigned long long *d = nullptr, h[2] = {0, 0};
     RL_CUDA(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
     cudaError_t e = cudaMemset(d, 0, 2 * sizeof(unsigned long long));
@@ -1251,7 +1557,7 @@ int rl_debug_camera_rays(const rl_scene *scene, uint64_t seed, uint32_t width, u
                          uint64_t first_photon, uint64_t n, rl_ray *out_rays, rl_mapped_photon *out_xy) {
     if (!scene || (!out_rays && n) || width == 0 || height == 0) return fail(RL_ERR_INVALID, "bad argument");
     if (n == 0) return RL_OK;
-    RL_CUDA(cudaSetDevice(scene->dev.index));
+    DeviceGuard guard(scene->dev.index);
     rl_ray *d_rays = nullptr; rl_mapped_photon *d_xy = nullptr;
     cudaError_t e = cudaMalloc(&d_rays, n * sizeof(rl_ray));
     if (e == cudaSuccess && out_xy) e = cudaMalloc(&d_xy, n * sizeof(rl_mapped_photon));

@@ -49,7 +49,7 @@ struct PrimTables {
     uint32_t plane_obj, paraboloid_obj, compound_obj;
     uint32_t scratch;         // per-block scratch behind the blob (see Scratch)
     uint32_t n_spheres, n_clusters, n_planes, n_paraboloids, n_compounds;
-    float sphere_cmax2, cluster_rmax;
+    float sphere_cmax2, cluster_rmax, leaf_off_max;
     uint32_t class_count[16];  // [parity][class] path counts of the block-wide path sort
 };
 
@@ -69,6 +69,7 @@ struct PrimTables {
 // state and the permutation table
 #define RL_SORT_BYTES_PER_THREAD (4 * RL_PATH_WORDS + 2 * RL_PATH_CLASSES)
 static_assert(2 * RL_CLUSTER_SLOTS <= 32 && 2 * RL_CAND_SLOTS <= 32 && 8 * RL_COMPOUND_SLOTS <= 32, "shared 32-byte area");
+static_assert(RL_PAIR_INDEX_BITS + 5 <= 16, "a pair record is a lane (5 bits) and a table index in 16 bits");
 
 __device__ __forceinline__ const PrimTables &tables() {
     return *reinterpret_cast<const PrimTables *>(rl_smem);
@@ -105,6 +106,7 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         t.n_compounds = sc.n_compounds;
         t.sphere_cmax2 = sc.sphere_cmax2;
         t.cluster_rmax = sc.cluster_rmax;
+        t.leaf_off_max = sc.leaf_off_max;
         *reinterpret_cast<PrimTables *>(rl_smem) = t;
     }
     // zero the scratch counters (same layout as in intersect_scene)
@@ -520,8 +522,14 @@ __device__ __forceinline__ Hit intersect_scene_brute(const Ray &ray) {
 // the inflated body up to rounding (~1e-5 at the scene's coordinate
 // magnitudes); if the inflated body's [enter, exit] interval is empty, ends
 // before the origin, or starts beyond the best hit so far, the exact evaluation
-// cannot change the result and is skipped.
+// cannot change the result and is skipped.  The f32 evaluation of n.(o - off)
+// is off by up to ~4 eps (|o| + |off|) |n|, so the inflation grows with the
+// magnitudes involved: RL_SLAB_INFLATE + 20 eps (|o| + max |off|), times
+// max(1, |n|) of the leaf (kept in the w lane of its normal record) -- for a ray
+// that starts far from the scene (a path leaving a distant plane) the slab test
+// keeps everything, which is the safe direction.
 #define RL_SLAB_INFLATE 2.0e-3f
+#define RL_SLAB_INFLATE_REL 1.2e-6f
 
 // Scene::intersect with result-preserving culls.
 //
@@ -556,7 +564,8 @@ __device__ __forceinline__ Hit intersect_scene_brute(const Ray &ray) {
 // the bounding test.
 //
 // Must be called by every thread of the block together (block barriers and
-// warp votes inside); threads without a live path pass idle_ray() and
+// warp votes inside), with a block barrier between two consecutive calls;
+// threads without a live path pass idle_ray() and
 // live = false.  A warp none of whose lanes is live skips the scans (its rays
 // hit nothing anyway) and only serves the block's task list: in the tail of a
 // small batch most warps of a block are in that state.
@@ -590,7 +599,8 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
     // publish this lane's pre-test constants so that any lane of the warp can test a sphere for it
     ray_tab[3 * tid + 0] = make_float4(m2ox, m2oy, m2oz, oo);
     ray_tab[3 * tid + 1] = make_float4(d.x, d.y, d.z, ndo);
-    ray_tab[3 * tid + 2] = make_float4(thr, bthr, 0.0f, 0.0f);
+    ray_tab[3 * tid + 2] = make_float4(thr, bthr, 0.0f,
+                                       fmaf(RL_SLAB_INFLATE_REL, sqrtf(oo) + tb.leaf_off_max, RL_SLAB_INFLATE));
     uint32_t *res_cnt = sq_cnt + nthreads;                      // results other threads computed for this one
     uint32_t *bcount = sq_cnt + 2 * nthreads;                   // [0]: entries in the block task list
     sq_cnt[tid] = 0u;
@@ -646,7 +656,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
         const uint32_t npairs = __shfl_sync(0xffffffffu, incl, 31);    // warp-uniform
         uint16_t *dst = pairs + (incl - mine);
 #pragma unroll 1
-        for (uint32_t k = 0; k < mine; k++) dst[k] = (uint16_t)((lane << 11) | myq[k * nthreads]);
+        for (uint32_t k = 0; k < mine; k++) dst[k] = (uint16_t)((lane << RL_PAIR_INDEX_BITS) | myq[k * nthreads]);
         __syncwarp();
         // Level 2, warp-cooperative: eight lanes take one (lane, cluster) pair and test one
         // member each with the owner's constants, so the work of lanes with many candidate
@@ -656,8 +666,8 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
             const uint32_t p = pb + (lane >> 3);
             if (p < npairs) {
                 const uint32_t pair = pairs[p];
-                const uint32_t owner = wbase + (pair >> 11);
-                const uint32_t r = cluster_range[pair & 2047u];
+                const uint32_t owner = wbase + (pair >> RL_PAIR_INDEX_BITS);
+                const uint32_t r = cluster_range[pair & RL_PAIR_INDEX_MAX];
                 const uint32_t end = (r & 0xffffu) + (r >> 16);
                 const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1], rt = ray_tab[3 * owner + 2];
 #pragma unroll 1
@@ -724,12 +734,15 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
                 const float bq = fmaf(cz, cz, fmaf(cy, cy, cx * cx));
                 const float bb = fmaf(d.z, cz, fmaf(d.y, cy, d.x * cx));
                 const float bc = bq - b4.w;                     // > 0: origin outside the bound
-                const bool behind = bc > 0.0f && bb < 0.0f;
-                const bool misses = fmaf(bb, bb, -(bc * dd)) < 0.0f;
+                // both tests leave room for their own rounding (16 eps of the largest term), so
+                // that a ray far from the body is kept rather than culled on noise
+                const float noise = 9.5367432e-7f * bq;
+                const bool behind = bc > noise && bb < 0.0f;
+                const bool misses = fmaf(bb, bb, -(bc * dd)) < -(noise * dd);
                 keep = !(behind || misses);
             }
             const uint32_t mask = __ballot_sync(0xffffffffu, keep);
-            if (keep) pairs[npairs + __popc(mask & lanes_below)] = (uint16_t)((lane << 11) | i);
+            if (keep) pairs[npairs + __popc(mask & lanes_below)] = (uint16_t)((lane << RL_PAIR_INDEX_BITS) | i);
             npairs += __popc(mask);
         }
         __syncwarp();
@@ -738,12 +751,13 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
             const uint32_t p = pb + group;
             const bool valid = p < npairs;                      // uniform within a group of eight
             const uint32_t pair = valid ? pairs[p] : 0u;
-            const uint32_t owner = wbase + (pair >> 11), body = pair & 2047u;
+            const uint32_t owner = wbase + (pair >> RL_PAIR_INDEX_BITS), body = pair & RL_PAIR_INDEX_MAX;
             const float4 c4 = compounds[2 * body];
             const uint32_t first_leaf = __float_as_uint(c4.x);
             const uint32_t n_leaves = valid ? __float_as_uint(c4.y) : 0u;
             const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1];
-            const float best_t = ray_tab[3 * owner + 2].z;
+            const float2 bi = *reinterpret_cast<const float2 *>(&ray_tab[3 * owner + 2].z);
+            const float best_t = bi.x, inflate = bi.y;
             const float ox = -0.5f * ro.x, oy = -0.5f * ro.y, oz = -0.5f * ro.z;   // ro = -2 o, exactly
             // the slab test, one leaf per lane
             float t_enter = 0.0f, t_exit = 3.0e38f;
@@ -752,7 +766,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
             for (uint32_t k = first_leaf + sub; k < first_leaf + n_leaves; k += 8) {
                 const float4 n4 = leaves[2 * k], o4 = leaves[2 * k + 1];
                 const float dn = fmaf(n4.z, rd.z, fmaf(n4.y, rd.y, n4.x * rd.x));
-                const float s0 = fmaf(n4.z, oz - o4.z, fmaf(n4.y, oy - o4.y, n4.x * (ox - o4.x))) - RL_SLAB_INFLATE;
+                const float s0 = fmaf(n4.z, oz - o4.z, fmaf(n4.y, oy - o4.y, n4.x * (ox - o4.x))) - inflate * n4.w;
                 const float tk = __fdividef(-s0, dn);
                 if (dn < 0.0f) t_enter = fmaxf(t_enter, tk);
                 else if (dn > 0.0f) t_exit = fminf(t_exit, tk);
@@ -813,8 +827,10 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
         }
         res_cnt[tid] = 0u;
         if (tid == 0) *bcount = 0u;
-        // the next use of the task list (next round or next call) is behind at least one more
-        // block barrier, which also orders these resets
+        // the next round is behind the barrier below; the next CALL must be behind a block barrier
+        // of the caller's (every kernel that loops over intersect_scene has one per iteration),
+        // which also orders these resets and the aliasing of the result slots with the next
+        // call's cluster queues
         if (round + RL_BODIES_PER_ROUND < n_compounds) __syncthreads();
     }
     return best;

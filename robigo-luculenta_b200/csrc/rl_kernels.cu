@@ -210,8 +210,281 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
     if ((threadIdx.x & 31) == 0 && a.ray_counter) atomicAdd(a.ray_counter, (unsigned long long)rays);
 }
 
+// --------------------------------------------------------- K1b trace service
+// The reference's host hands the engine 524 288-photon batches from C worker threads
+// (task_scheduler.rs:95-96,127-182; app.rs:104-109): 4.6 photons per thread of a full grid.  One
+// launch per batch spends most of its life in its tail.  The trace service keeps ONE resident
+// kernel busy with whatever batches are queued: render() pushes a {photon range, records,
+// completion flag} entry into a ring in device memory (service_push_kernel, in stream order on
+// the unit's stream) and launches a worker (service_worker_kernel) behind it; a worker's CTAs
+// claim chunks of photons from the oldest entries of the ring, whichever unit they belong to,
+// and leave only when the ring has nothing left to claim -- so while the host keeps batches
+// queued the same CTAs stay resident and go from one batch to the next without a tail, and a
+// worker that finds the ring empty (an older worker took its entry) retires in microseconds.
+// A finished entry stores its sequence number to the unit's completion word; the unit's stream
+// waits on that word (cuStreamWaitValue32) before the copy of the records to the host.
+//
+// Same path code as trace_kernel (camera_ray, intersect_scene, material_bounce, roulette): a
+// photon's record depends on (scene, seed, photon id) only, so which CTA of which worker traces
+// it changes nothing (tests/test_gpu_service.py).
+#define RL_SERVICE_CHUNK 1024u         // photons a CTA claims at a time
+#define RL_SERVICE_OPEN 4u             // entries a CTA can hold paths of at once
+#define RL_SERVICE_POOLS 2u            // chunks a CTA deals photons from
+#ifndef RL_SERVICE_LINGER_CYCLES
+#define RL_SERVICE_LINGER_CYCLES 60000 // a CTA that has worked waits this long for new entries (~30 us)
+#endif
+
+struct ServiceCta {                    // per-CTA bookkeeping in shared memory, behind the intersection scratch
+    struct Open {
+        uint64_t seed, first_photon;
+        rl_mapped_photon *records;
+        float4 *accum;
+        ServiceEntry *slot;
+        float aspect;
+        int width, height;
+        uint32_t ticket;               // ring ticket + 1 of the entry; 0 = free
+        uint32_t n_photons;
+        uint32_t unfinished;           // photons this CTA claimed and has not finished (dealt or not)
+        uint32_t claimed;              // photons claimed since the last flush to the entry
+        uint32_t rays;                 // Scene::intersect calls since the last flush
+    } open[RL_SERVICE_OPEN];
+    struct Pool { uint32_t next, end, open; } pool[RL_SERVICE_POOLS];
+    uint32_t active;                   // some photon of this CTA is alive or waits to be dealt
+    uint32_t done;                     // nothing left and nothing arrived: the CTA retires
+    uint32_t worked;                   // the CTA has claimed at least one chunk
+    long long idle_since;
+};
+
+__device__ __forceinline__ ServiceCta *service_cta(const DevScene &sc) {
+    char *base = reinterpret_cast<char *>(rl_smem + RL_TABLES_VEC4 + sc.smem_vec4);
+    return reinterpret_cast<ServiceCta *>(base + (size_t)RL_SCRATCH_BYTES_PER_THREAD * blockDim.x);
+}
+
+__global__ void service_push_kernel(ServiceQueue *q, ServiceEntry e) {
+    if (threadIdx.x != 0) return;
+    const uint32_t t = atomicAdd(&q->tail, 1u);
+    ServiceEntry *s = &q->slots[t % RL_SERVICE_CAP];
+    // the slot's previous entry (RL_SERVICE_CAP tickets ago) may still be in flight
+    while (atomicCAS(&s->busy, 0u, 1u) != 0u) __nanosleep(200);
+    s->seed = e.seed; s->first_photon = e.first_photon;
+    s->records = e.records; s->accum = e.accum; s->ray_counter = e.ray_counter;
+    s->done_flag = e.done_flag; s->done_value = e.done_value; s->n_photons = e.n_photons;
+    s->width = e.width; s->height = e.height; s->aspect = e.aspect;
+    s->finished = 0u;
+    __threadfence();
+    // publishes the entry: claimers compare the ticket half before they touch the slot
+    atomicExch(&s->ticket_next, (unsigned long long)(t + 1u) << 32);
+}
+
+// Thread 0, between two block barriers: hand finished photons back to their entries, refill the
+// pools from the ring, decide whether the CTA stays.
+__device__ __forceinline__ void service_manage(ServiceQueue *q, ServiceCta *cta) {
+    uint32_t pending = 0;
+#pragma unroll 1
+    for (uint32_t o = 0; o < RL_SERVICE_OPEN; o++) {
+        ServiceCta::Open &op = cta->open[o];
+        if (op.ticket == 0u) continue;
+        if (op.unfinished != 0u) { pending += op.unfinished; continue; }
+        // every photon this CTA took from the entry has ended; the records were written before the
+        // barrier this thread has just passed
+        ServiceEntry *s = op.slot;
+        if (op.rays && s->ray_counter) atomicAdd(s->ray_counter, (unsigned long long)op.rays);
+        __threadfence();
+        const uint32_t before = atomicAdd(&s->finished, op.claimed);
+        if (before + op.claimed == op.n_photons) {
+            // the last photons of the entry: everything the other CTAs wrote is ordered before
+            // their own additions to `finished`
+            // the flag is a word in mapped host memory: the records must be visible to the copy
+            // engine and to peers before the host sees it
+            __threadfence_system();
+            uint32_t *flag = s->done_flag;
+            const uint32_t value = s->done_value;
+            *reinterpret_cast<volatile uint32_t *>(flag) = value;
+            __threadfence();
+            atomicExch(&s->busy, 0u);
+        }
+        op.ticket = 0u; op.claimed = 0u; op.rays = 0u;
+    }
+#pragma unroll 1
+    for (uint32_t p = 0; p < RL_SERVICE_POOLS; p++) {
+        ServiceCta::Pool &pl = cta->pool[p];
+        if (pl.next < pl.end) continue;                         // still dealing
+        pl.next = pl.end = 0u;
+        // claim the next chunk of the oldest entry that has photons left
+        uint32_t h = *reinterpret_cast<volatile uint32_t *>(&q->head);
+#pragma unroll 1
+        for (;;) {
+            const uint32_t t = *reinterpret_cast<volatile uint32_t *>(&q->tail);
+            if (h == t) break;
+            ServiceEntry *s = &q->slots[h % RL_SERVICE_CAP];
+            unsigned long long word = *reinterpret_cast<volatile unsigned long long *>(&s->ticket_next);
+            if ((uint32_t)(word >> 32) != h + 1u) {
+                // not published yet, or the ring has moved on
+                const uint32_t h2 = *reinterpret_cast<volatile uint32_t *>(&q->head);
+                if (h2 == h) break;
+                h = h2;
+                continue;
+            }
+            __threadfence();                                    // the entry's fields were written before its ticket
+            const uint32_t n = *reinterpret_cast<volatile uint32_t *>(&s->n_photons);
+            const uint32_t c = (uint32_t)word;
+            if (c >= n) {                                       // fully claimed: move the head on
+                atomicCAS(&q->head, h, h + 1u);
+                h = *reinterpret_cast<volatile uint32_t *>(&q->head);
+                continue;
+            }
+            // an open record for this entry: the one it already has, else a free one
+            uint32_t o = RL_SERVICE_OPEN, free_o = RL_SERVICE_OPEN;
+            for (uint32_t k = 0; k < RL_SERVICE_OPEN; k++) {
+                if (cta->open[k].ticket == h + 1u) o = k;
+                else if (cta->open[k].ticket == 0u && free_o == RL_SERVICE_OPEN) free_o = k;
+            }
+            if (o == RL_SERVICE_OPEN) o = free_o;
+            if (o == RL_SERVICE_OPEN) break;                    // paths of four entries alive: wait
+            const uint32_t take = n - c < RL_SERVICE_CHUNK ? n - c : RL_SERVICE_CHUNK;
+            if (atomicCAS(&s->ticket_next, word, word + take) != word) continue;   // another CTA was faster
+            ServiceCta::Open &op = cta->open[o];
+            if (op.ticket == 0u) {
+                op.seed = s->seed; op.first_photon = s->first_photon;
+                op.records = s->records; op.accum = s->accum; op.slot = s;
+                op.aspect = s->aspect; op.width = (int)s->width; op.height = (int)s->height;
+                op.n_photons = n;
+                op.ticket = h + 1u; op.unfinished = 0u; op.claimed = 0u; op.rays = 0u;
+            }
+            op.unfinished += take;
+            op.claimed += take;
+            pl.next = c; pl.end = c + take; pl.open = o;
+            pending += take;
+            cta->worked = 1u;
+            break;
+        }
+    }
+    cta->active = pending != 0u;
+    if (pending != 0u) {
+        cta->idle_since = 0;
+    } else if (!cta->worked) {
+        cta->done = 1u;                                         // an older worker took everything
+    } else {
+        const long long now = clock64();
+        if (cta->idle_since == 0) cta->idle_since = now;
+        else if (now - cta->idle_since > RL_SERVICE_LINGER_CYCLES) cta->done = 1u;
+        __nanosleep(500);
+    }
+}
+
+__global__ void __launch_bounds__(RL_TRACE_THREADS, RL_TRACE_MIN_BLOCKS)
+service_worker_kernel(const DevScene sc, ServiceQueue *q) {
+    ServiceCta *cta = service_cta(sc);
+    if (threadIdx.x == 0) {
+        for (uint32_t o = 0; o < RL_SERVICE_OPEN; o++) {
+            cta->open[o].ticket = 0u; cta->open[o].unfinished = 0u; cta->open[o].claimed = 0u; cta->open[o].rays = 0u;
+        }
+        for (uint32_t p = 0; p < RL_SERVICE_POOLS; p++) cta->pool[p].next = cta->pool[p].end = cta->pool[p].open = 0u;
+        cta->active = 0u; cta->done = 0u; cta->worked = 0u; cta->idle_since = 0;
+        service_manage(q, cta);
+    }
+    __syncthreads();
+    if (cta->done) return;                                      // nothing to claim: no table set-up either
+    setup_tables(sc);
+
+    const uint32_t lane = threadIdx.x & 31u;
+    bool alive = false;
+    uint32_t cur = 0;                                           // photon index within its entry | open record << 28
+    Ray ray;
+    ray.origin = mk(0.f, 0.f, 0.f); ray.direction = mk(0.f, 0.f, 0.f); ray.wavelength = 0.f;
+    float sx = 0.f, sy = 0.f;
+    float intensity = 1.0f, continue_chance = 1.0f;
+    Rng rng;
+    rng.init();
+    uint32_t rays = 0;                                          // of the current path
+
+    for (bool first = true;; first = false) {
+        if (!first) {
+            __syncthreads();                                    // the path ends of the last iteration are counted
+            if (threadIdx.x == 0) service_manage(q, cta);
+            __syncthreads();
+        }
+        if (cta->done) break;
+        if (!cta->active) continue;
+        // lanes without a path draw photons from the CTA's pools (one warp-aggregated atomic per pool)
+        uint32_t mine = 0xffffffffu, mine_open = 0;
+#pragma unroll
+        for (uint32_t p = 0; p < RL_SERVICE_POOLS; p++) {
+            const uint32_t want = __ballot_sync(0xffffffffu, !alive && mine == 0xffffffffu);
+            ServiceCta::Pool &pl = cta->pool[p];
+            const uint32_t end = pl.end;
+            if (want != 0u && pl.next < end) {                  // warp-uniform: one address, one load
+                const uint32_t leader = __ffs(want) - 1u;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(&pl.next, (uint32_t)__popc(want));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const uint32_t idx = base + __popc(want & ((1u << lane) - 1u));
+                if (!alive && mine == 0xffffffffu && idx < end) { mine = idx; mine_open = pl.open; }
+            }
+        }
+        if (mine != 0xffffffffu) {
+            // trace_unit.rs:151-158 and :136-145
+            const ServiceCta::Open &op = cta->open[mine_open];
+            cur = mine | (mine_open << 28);
+            const RngKey key = {op.seed, op.first_photon + mine};
+            rng.init();
+            const float wavelength = rng.wavelength(key);
+            sx = rng.bi_unit(key);
+            sy = rng.bi_unit(key) / op.aspect;
+            const float t = rng.unit(key);
+            ray = camera_ray(sc.camera, sx, sy, wavelength, t, rng, key);
+            intensity = 1.0f;
+            continue_chance = 1.0f;
+            rays = 0;
+            alive = true;
+        }
+        const Hit hit = intersect_scene(alive ? ray : idle_ray(), alive);
+        if (alive) {
+            rays++;
+            ServiceCta::Open &op = cta->open[cur >> 28];
+            const uint32_t index = cur & 0x0fffffffu;
+            // trace_unit.rs:91-131
+            bool done = false;
+            float result = 0.0f;
+            if (hit.obj < 0) {
+                done = true;                                            // trace_unit.rs:94
+            } else {
+                const float4 m = __ldg(sc.materials + hit.obj);
+                if (__float_as_uint(m.x) == RL_MATERIAL_BLACKBODY) {
+                    result = intensity * blackbody_intensity(m, ray.wavelength);  // :99-101
+                    done = true;
+                } else {
+                    const Surf s = surface_at(ray, hit);
+                    const RngKey key = {op.seed, op.first_photon + index};
+                    float probability;
+                    const V3 dir = material_bounce(m, ray, hit, s, rng, key, probability);  // :104-107
+                    intensity = intensity * probability;
+                    ray.direction = dir;
+                    ray.origin = s.position + dir * 0.00001f;                      // :114
+                    continue_chance = continue_chance * 0.96f;                    // :117
+                    if (rng.unit(key) * 0.85f
+                        > continue_chance * (1.0f - spec_exp(intensity * -20.0f)))  // :122-125
+                        done = true;
+                }
+            }
+            if (done) {
+                if (op.records)
+                    *reinterpret_cast<float4 *>(op.records + index) = make_float4(sx, sy, result, ray.wavelength);
+                if (op.accum && result != 0.0f)
+                    splat_photon(op.accum, op.width, op.height, op.aspect, sx, sy, ray.wavelength, result);
+                atomicAdd(&op.rays, rays);
+                atomicSub(&op.unfinished, 1u);
+                alive = false;
+            }
+        }
+    }
+}
+
 size_t trace_smem_bytes(const DevScene &sc, int threads) { return tracing_smem_bytes(sc, threads); }
 // the trace kernel proper: plus the path-sort area when enabled
+static size_t service_smem_bytes(const DevScene &sc, int threads) {
+    return tracing_smem_bytes(sc, threads) + sizeof(ServiceCta);
+}
 static size_t trace_kernel_smem_bytes(const DevScene &sc, int threads) {
     return tracing_smem_bytes(sc, threads) + (RL_SORT_PATHS ? (size_t)RL_SORT_BYTES_PER_THREAD * threads : 0);
 }
@@ -269,6 +542,68 @@ static int env_int(const char *name, int fallback) {
     return v && *v ? atoi(v) : fallback;
 }
 
+// What the attribute calls last set, per device and kernel: thousands of identical launches per
+// second should not each pay for driver round trips.  Guarded by the caller's lock.
+struct KernelCache { int max_smem = 0, threads = 0, per_sm = 0, pct = -2; size_t smem = 0; };
+
+template <typename Kernel>
+static cudaError_t prepare_kernel(Kernel kernel, KernelCache &cached, int dev) {
+    if (cached.max_smem != 0) return cudaSuccess;
+    cudaError_t err = cudaDeviceGetAttribute(&cached.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cached.max_smem);
+    if (err != cudaSuccess) cached.max_smem = 0;
+    return err;
+}
+
+// carve out only the shared memory the resident CTAs need (+1 KB each that the system
+// reserves); the rest of the 228 KB stays L1 for the material records, the exact sphere
+// records and the few spilled registers
+template <typename Kernel>
+static void set_carveout(Kernel kernel, KernelCache &cached, int per_sm, size_t smem) {
+    const char *env = getenv("RL_TRACE_CARVEOUT");
+    int pct = env ? atoi(env) : (int)((per_sm * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    if (pct >= 0 && pct != cached.pct) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cached.pct = pct;
+    }
+}
+
+cudaError_t launch_service_push(ServiceQueue *q, const ServiceEntry &e, cudaStream_t st) {
+    if (e.n_photons == 0 || e.n_photons > (1u << 28)) return cudaErrorInvalidValue;
+    service_push_kernel<<<1, 32, 0, st>>>(q, e);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_service_worker(const DevScene &sc, ServiceQueue *q, int sm_count, int reserved_sms,
+                                  cudaStream_t st) {
+    static std::mutex lock;
+    static KernelCache cache[16];
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    int threads = RL_TRACE_THREADS;
+    size_t smem = 0;
+    {
+        std::lock_guard<std::mutex> guard(lock);
+        KernelCache scratch_entry;
+        KernelCache &cached = dev >= 0 && dev < 16 ? cache[dev] : scratch_entry;
+        err = prepare_kernel(service_worker_kernel, cached, dev);
+        if (err != cudaSuccess) return err;
+        while (threads > 128 && service_smem_bytes(sc, threads) > (size_t)cached.max_smem) threads -= 128;
+        smem = service_smem_bytes(sc, threads);
+        if (smem > (size_t)cached.max_smem) return cudaErrorInvalidValue;
+        set_carveout(service_worker_kernel, cached, 1, smem);
+    }
+    int grid = sm_count - reserved_sms;
+    if (grid < 1) grid = 1;
+    service_worker_kernel<<<(unsigned)grid, threads, smem, st>>>(sc, q);
+    g_launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count, cudaStream_t st) {
     if (p.n_photons == 0) return cudaSuccess;
     // the function attributes below are process-wide: launches from the threads of different
@@ -277,21 +612,14 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     std::lock_guard<std::mutex> guard(launch_lock);
     // the largest CTA (up to RL_TRACE_THREADS) whose tables + scratch fit the shared memory of an SM:
     // big CTAs fill the per-CTA task list of the body evaluation best
-    // what the attribute calls last set, per device: thousands of identical small launches per
-    // second should not each pay for three driver round trips while holding the lock
-    struct Cached { int max_smem = 0, threads = 0, per_sm = 0, pct = -2; size_t smem = 0; };
-    static Cached cache[16];
+    static KernelCache cache[16];
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
-    Cached scratch_entry;
-    Cached &cached = dev >= 0 && dev < 16 ? cache[dev] : scratch_entry;
-    if (cached.max_smem == 0) {
-        err = cudaDeviceGetAttribute(&cached.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        if (err == cudaSuccess)
-            err = cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cached.max_smem);
-        if (err != cudaSuccess) { cached.max_smem = 0; return err; }
-    }
+    KernelCache scratch_entry;
+    KernelCache &cached = dev >= 0 && dev < 16 ? cache[dev] : scratch_entry;
+    err = prepare_kernel(trace_kernel, cached, dev);
+    if (err != cudaSuccess) return err;
     const int max_smem = cached.max_smem;
     int threads = RL_TRACE_THREADS;
     while (threads > 128 && trace_kernel_smem_bytes(sc, threads) > (size_t)max_smem) threads -= 128;
@@ -318,18 +646,7 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
         cached.threads = threads; cached.smem = smem; cached.per_sm = occ < 1 ? 1 : occ;
     }
     const int per_sm = cached.per_sm;
-    // carve out only the shared memory the resident CTAs need (+1 KB each that the system
-    // reserves); the rest of the 228 KB stays L1 for the material records, the exact sphere
-    // records and the few spilled registers
-    {
-        const char *env = getenv("RL_TRACE_CARVEOUT");
-        int pct = env ? atoi(env) : (int)((per_sm * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
-        if (pct > 100) pct = 100;
-        if (pct >= 0 && pct != cached.pct) {
-            cudaFuncSetAttribute(trace_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cached.pct = pct;
-        }
-    }
+    set_carveout(trace_kernel, cached, per_sm, smem);
     uint64_t want = (p.n_photons + threads - 1) / threads;
     uint64_t full = (uint64_t)sm_count * per_sm;
     if (small) {
@@ -740,6 +1057,9 @@ __global__ void debug_intersect_kernel(const DevScene sc, const rl_ray *rays, ui
             r.wavelength = rays[i].wavelength;
         }
         const Hit h = intersect_scene(r);
+        // intersect_scene leaves its block-wide scratch (task counter, result slots) to be reset
+        // behind a barrier that the next call must not overtake
+        __syncthreads();
         if (!live) continue;
         rl_hit o;
         o.object = h.obj;

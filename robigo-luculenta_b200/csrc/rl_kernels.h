@@ -19,6 +19,34 @@ struct TraceLaunch {
     unsigned long long *ray_counter;  // device
 };
 
+// ---- trace service: a ring of batches in device memory that resident worker CTAs drain
+#define RL_SERVICE_CAP 1024u           // ring slots (entries in flight at once)
+struct ServiceEntry {
+    uint64_t seed, first_photon;
+    rl_mapped_photon *records;         // device, n_photons entries, or nullptr
+    float4 *accum;                     // device accumulator for a fused splat, or nullptr
+    unsigned long long *ray_counter;   // device
+    uint32_t *done_flag;               // word (mapped host memory) that receives done_value when the entry is finished
+    uint32_t done_value, n_photons;    // 0 < n_photons <= 2^28
+    uint32_t width, height;
+    float aspect;
+    uint32_t finished;                 // photons whose paths have ended
+    uint32_t busy;                     // the slot holds an entry that is not finished yet
+    unsigned long long ticket_next;    // (ring ticket + 1) << 32 | photons claimed so far
+};
+struct ServiceQueue {
+    uint32_t tail;                     // tickets handed out
+    uint32_t head;                     // oldest ticket that may have unclaimed photons
+    uint32_t pad[2];
+    ServiceEntry slots[RL_SERVICE_CAP];
+};
+// Queue one batch (in stream order on `st`); n_photons must be in (0, 2^28].
+cudaError_t launch_service_push(ServiceQueue *q, const ServiceEntry &e, cudaStream_t st);
+// One worker: CTAs that drain the ring and retire when it stays empty.  `reserved_sms` SMs are
+// left to the other kernels of the pipeline (splat, gather, pack).
+cudaError_t launch_service_worker(const DevScene &sc, ServiceQueue *q, int sm_count, int reserved_sms,
+                                  cudaStream_t st);
+
 // Dynamic shared memory the trace kernels need for a scene.
 size_t trace_smem_bytes(const DevScene &sc, int threads);
 // K1: TraceUnit::render (+ PlotUnit::plot when accum != nullptr).

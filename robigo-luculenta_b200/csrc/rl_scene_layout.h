@@ -6,6 +6,10 @@
 #include <stdint.h>
 
 #define RL_MAX_COMPOUND_STACK 5   // deepest evaluation stack of a compound-surface program
+// the kernels pack (lane, table index) pairs into 16 bits: 5 bits of lane, 11 bits of cluster or
+// compound index; rl_scene_create rejects scenes with more clusters or compounds than that
+#define RL_PAIR_INDEX_BITS 11
+#define RL_PAIR_INDEX_MAX ((1u << RL_PAIR_INDEX_BITS) - 1u)
 
 namespace rl {
 
@@ -34,6 +38,7 @@ struct DevScene {
     uint32_t n_objects;
     float sphere_cmax2;       // max (|centre|^2 + r^2) over spheres and clusters (error bound of the pre-test)
     float cluster_rmax;       // largest cluster bounding radius
+    float leaf_off_max;       // largest |offset| over the half-spaces of compound surfaces (slab-test inflation)
     DevCamera camera;
 };
 

@@ -11,8 +11,8 @@
 //
 //   rl_replay --width W --height H --threads C --batches B [--batch N] [--seed S]
 //             [--mode strict|device] [--scene 1..4] [--out PREFIX] [--pin 0|1] [--lazy 0|1] [--async-render 0|1]
-//             [--records host|deferred]
-//             [--first-batch K]
+//             [--records host|deferred] [--consume device|host]
+//             [--first-batch K] [--sleep-ms 100]
 // --first-batch: photon ids start at K * batch (a second process -- another GPU -- continues
 // the id range of the first).
 //
@@ -34,6 +34,7 @@
 #include <thread>
 #include <vector>
 
+#include "../../include/rl_host.h"
 #include "rl_units.hpp"
 
 using namespace robigo;
@@ -161,6 +162,7 @@ private:
 // wall time the workers spent in each kind of task (summed over threads), for the report
 struct KindStats { std::atomic<uint64_t> ns{0}, calls{0}; };
 KindStats g_stats[5];
+int g_sleep_ms = 100;   // app.rs:129: the idle task sleeps 100 ms
 
 void execute_kind(Task &t, const Scene &scene, bool device);
 
@@ -175,7 +177,7 @@ void execute(Task &t, const Scene &scene, bool device) {
 
 void execute_kind(Task &t, const Scene &scene, bool device) {
     switch (t.kind) {
-    case Kind::Sleep: std::this_thread::sleep_for(std::chrono::milliseconds(1)); break;   // app.rs:128-130 (100 ms there)
+    case Kind::Sleep: std::this_thread::sleep_for(std::chrono::milliseconds(g_sleep_ms)); break;   // app.rs:128-130
     case Kind::Trace: t.trace->render(scene); break;                                      // app.rs:132-134
     case Kind::Plot:                                                                      // app.rs:136-141
         for (auto &u : t.traces) {
@@ -217,6 +219,8 @@ int main(int argc, char **argv) {
     lazy_host_mirrors() = atoi(arg(argc, argv, "--lazy", "1")) != 0;
     async_render() = atoi(arg(argc, argv, "--async-render", "1")) != 0;
     deferred_records() = !strcmp(arg(argc, argv, "--records", "host"), "deferred");
+    consume_on_device() = strcmp(arg(argc, argv, "--consume", "device"), "host") != 0;
+    g_sleep_ms = atoi(arg(argc, argv, "--sleep-ms", "100"));
 
     try {
         rl_scene_builder *builder = nullptr;
@@ -236,11 +240,16 @@ int main(int argc, char **argv) {
             gu.accumulate(pu.tristimulus_buffer);
             mu.tonemap(gu.tristimulus_buffer);
         }
-        rl_trace_batch_counter_reset(strtoull(arg(argc, argv, "--first-batch", "0"), nullptr, 10));
+        expect(rl_scene_batch_counter_reset(scene.handle(), strtoull(arg(argc, argv, "--first-batch", "0"), nullptr, 10)),
+               "rl_scene_batch_counter_reset");
         const std::string raw = out + ".raw";
         remove(raw.c_str());   // start from black: GatherUnit::new resumes from the file if present
 
+        // unit creation (TaskScheduler::new, task_scheduler.rs:91-125: 3C trace units, C/2 plot units,
+        // page-locking of their host buffers) is timed separately: once per render, like App::new
+        const auto t_setup = std::chrono::steady_clock::now();
         Scheduler scheduler(threads, w, h, seed, batch, device, batches, raw);
+        const double setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_setup).count();
         std::mutex lock;
         rl_transfer_counters_reset();
         const auto t0 = std::chrono::steady_clock::now();
@@ -274,13 +283,13 @@ int main(int argc, char **argv) {
             fclose(f);
         }
         const uint64_t rays = scheduler.rays();
-        printf("{\"mode\": \"%s\", \"pinned\": %s, \"lazy\": %s, \"async_render\": %s, \"records\": \"%s\", \"width\": %u, \"height\": %u, \"threads\": %zu, \"batches\": %llu, \"batch\": %llu, \"seconds\": %.6f, "
+        printf("{\"mode\": \"%s\", \"pinned\": %s, \"lazy\": %s, \"async_render\": %s, \"records\": \"%s\", \"consume\": \"%s\", \"sleep_ms\": %d, \"width\": %u, \"height\": %u, \"threads\": %zu, \"batches\": %llu, \"batch\": %llu, \"seconds\": %.6f, \"setup_seconds\": %.6f, "
                "\"batches_per_s\": %.3f, \"rays\": %llu, \"mrays_per_s\": %.3f, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"worker_seconds\": {\"sleep\": [%llu, %.3f], "
                "\"trace\": [%llu, %.3f], \"plot\": [%llu, %.3f], \"gather\": [%llu, %.3f], \"tonemap\": [%llu, %.3f]}}\n",
                device ? "device" : "strict", pin_host_buffers() ? "true" : "false",
                lazy_host_mirrors() ? "true" : "false", async_render() ? "true" : "false",
-               deferred_records() ? "deferred" : "host", w, h, threads, (unsigned long long)scheduler.traces_completed(),
-               (unsigned long long)batch, seconds, scheduler.traces_completed() / seconds,
+               deferred_records() ? "deferred" : "host", consume_on_device() ? "device" : "host", g_sleep_ms, w, h, threads, (unsigned long long)scheduler.traces_completed(),
+               (unsigned long long)batch, seconds, setup_seconds, scheduler.traces_completed() / seconds,
                (unsigned long long)rays, rays / seconds / 1e6, (unsigned long long)h2d, (unsigned long long)d2h,
                (unsigned long long)g_stats[0].calls, g_stats[0].ns * 1e-9, (unsigned long long)g_stats[1].calls,
                g_stats[1].ns * 1e-9, (unsigned long long)g_stats[2].calls, g_stats[2].ns * 1e-9,

@@ -8,7 +8,7 @@
 #include <new>
 #include <vector>
 
-#include "../../include/rl_b200.h"
+#include "../../include/rl_host.h"
 #include "../csrc/rl_math.cuh"
 
 using rl::V3;

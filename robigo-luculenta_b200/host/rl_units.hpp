@@ -55,6 +55,12 @@ inline bool &async_render() { static bool on = true; return on; }
 // as a literal reading of app.rs:133-139 has it) or only when host code reads it (true:
 // PlotUnit::plot recognises the field by its type and splats from the device records)
 inline bool &deferred_records() { static bool on = false; return on; }
+// A unit's buffer handed to the next unit (`plot(&unit.mapped_photons)`, app.rs:139;
+// `accumulate(&plot_unit.tristimulus_buffer)`, app.rs:146; `tonemap(&gather.tristimulus_buffer)`,
+// app.rs:157) is consumed where it was produced, on the device (true): the host copy is still
+// filled for whoever reads the field, but nothing is uploaded again.  false: the literal
+// reading -- the host slice is copied back to the device (A/B measurements).
+inline bool &consume_on_device() { static bool on = true; return on; }
 template <typename T> class HostMirror {
 public:
     using Download = std::function<void(T *)>;
@@ -77,7 +83,8 @@ public:
     T *destination() { return storage_.data(); }       // where the device copy lands (no wait)
     // the unit whose device buffer this field mirrors, while that buffer is newer than the host copy
     void set_owner(void *unit_handle) { owner_ = unit_handle; }
-    void *device_owner() const { return stale_ && deferred_records() ? owner_ : nullptr; }
+    // (the host can only read these fields, so the device copy is what the field holds)
+    void *device_owner() const { return consume_on_device() || (stale_ && deferred_records()) ? owner_ : nullptr; }
     operator const std::vector<T> &() const { return get(); }
     const T *data() const { return get().data(); }
     size_t size() const { return storage_.size(); }
@@ -123,7 +130,8 @@ public:
         expect(rl_trace_unit_set_batch_size(handle_, batch), "rl_trace_unit_set_batch_size");
         if (!keep_on_device) {
             mapped_photons.init(batch, [this](MappedPhoton *dst) {
-                if (deferred_records()) expect(rl_trace_unit_download(handle_, dst), "rl_trace_unit_download");
+                if (deferred_records())
+                    expect(rl_trace_unit_download(handle_, dst, mapped_photons.size(), nullptr), "rl_trace_unit_download");
                 else expect(rl_trace_unit_sync(handle_), "rl_trace_unit_sync");
             });
             mapped_photons.set_owner(handle_);
@@ -167,10 +175,12 @@ public:
     // as the unchanged app.rs:146 reads the field.
     PlotUnit(size_t id_, uint32_t width, uint32_t height, bool mirror_on_host = true) : id(id_) {
         expect(rl_plot_unit_create(id_, width, height, &handle_), "rl_plot_unit_create");
-        if (mirror_on_host)
+        if (mirror_on_host) {
             tristimulus_buffer.init((size_t)width * height, [this](Vector3 *dst) {
                 expect(rl_plot_unit_download(handle_, reinterpret_cast<float *>(dst)), "rl_plot_unit_download");
             });
+            tristimulus_buffer.set_owner(handle_);
+        }
     }
     ~PlotUnit() { rl_plot_unit_destroy(handle_); }
     PlotUnit(const PlotUnit &) = delete;
@@ -224,6 +234,7 @@ public:
                        "rl_gather_unit_download");
             });
             tristimulus_buffer.invalidate();           // the resumed state
+            tristimulus_buffer.set_owner(handle_);
         }
     }
     ~GatherUnit() { rl_gather_unit_destroy(handle_); }
@@ -235,6 +246,17 @@ public:
         expect(rl_gather_unit_accumulate(handle_, reinterpret_cast<const float *>(tristimuli.data())),
                "rl_gather_unit_accumulate");
         tristimulus_buffer.invalidate();
+    }
+    // `accumulate(&plot_unit.tristimulus_buffer)` as app.rs:146 writes it: the argument is a plot
+    // unit's own field (Rust: `accumulate<T: AsTristimuli + ?Sized>`), whose truth is on the device
+    void accumulate(const HostMirror<Vector3> &tristimuli) {
+        if (void *owner = tristimuli.device_owner()) {
+            expect(rl_gather_unit_accumulate_plot(handle_, static_cast<rl_plot_unit *>(owner), 0),
+                   "rl_gather_unit_accumulate_plot");
+            tristimulus_buffer.invalidate();
+        } else {
+            accumulate(tristimuli.get());
+        }
     }
     // accumulate(&plot.tristimulus_buffer) + plot.clear() without the host trip (app.rs:145-148)
     void accumulate(PlotUnit &plot, bool clear_plot) {
@@ -272,6 +294,14 @@ public:
     void tonemap(const std::vector<Vector3> &tristimuli) {
         expect(rl_tonemap_unit_tonemap(handle_, reinterpret_cast<const float *>(tristimuli.data()), rgb_buffer.data()),
                "rl_tonemap_unit_tonemap");
+    }
+    // `tonemap(&gather_unit.tristimulus_buffer)` as app.rs:157 writes it
+    void tonemap(const HostMirror<Vector3> &tristimuli) {
+        if (void *owner = tristimuli.device_owner())
+            expect(rl_tonemap_unit_tonemap_gather(handle_, static_cast<rl_gather_unit *>(owner), rgb_buffer.data()),
+                   "rl_tonemap_unit_tonemap_gather");
+        else
+            tonemap(tristimuli.get());
     }
     void tonemap(GatherUnit &gather) {
         expect(rl_tonemap_unit_tonemap_gather(handle_, gather.handle(), rgb_buffer.data()),

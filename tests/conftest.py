@@ -18,6 +18,7 @@ def pytest_configure(config):
 def pkg():
     """The product package (ctypes mirror over librl_b200.so), built if stale."""
     entry.build_library()
+    entry.build_host_library()
     return entry.load_package()
 
 

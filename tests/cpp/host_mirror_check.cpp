@@ -41,10 +41,14 @@ int main() {
     CHECK(downloads == 2 && m[1].x == 99.0f && downloads == 2);
     lazy_host_mirrors() = true;
 
-    // the trace unit's field: while the device records are newer than the host copy (and the
-    // shim runs with deferred records) plot() is pointed at the owning unit, not at host memory
+    // the trace unit's field: the host can only read it, so the device copy is what it holds and
+    // plot() is pointed at the owning unit instead of uploading the host copy again; with
+    // consume_on_device() off (the literal reading of app.rs:139) only records that were never
+    // copied down (deferred records) are taken from the device
     int fake_unit = 0;
     m.set_owner(&fake_unit);
+    CHECK(m.device_owner() == &fake_unit);           // default: consumed where it was produced
+    consume_on_device() = false;
     CHECK(m.device_owner() == nullptr);              // clean
     m.invalidate();
     CHECK(m.device_owner() == nullptr);              // stale, but records are copied down by render()
@@ -53,6 +57,8 @@ int main() {
     CHECK(m[0].x == 99.0f && downloads == 3);        // host code reads the field after all: one copy
     CHECK(m.device_owner() == nullptr);              // ... and the host copy is current again
     deferred_records() = false;
+    consume_on_device() = true;
+    CHECK(m.device_owner() == &fake_unit && downloads == 3);   // no copy to find that out
     puts("host mirror ok");
     return 0;
 }

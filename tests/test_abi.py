@@ -10,8 +10,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "rl_b200.h")).read()
+def declared_symbols(header="rl_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(rl_[a-z0-9_]+)\s*\(", text)))
 
@@ -19,15 +19,27 @@ def declared_symbols():
 def test_header_symbols_are_exported(pkg):
     handle = C.CDLL(pkg.LIB_PATH)
     names = declared_symbols()
-    assert len(names) >= 50
+    assert len(names) >= 45
     missing = [n for n in names if not hasattr(handle, n)]
     assert not missing, f"declared in rl_b200.h but not exported: {missing}"
+    # the host-only scene builders live in a library of their own, without CUDA in it
+    host = C.CDLL(pkg.HOST_LIB_PATH)
+    host_names = declared_symbols("rl_host.h")
+    assert len(host_names) >= 13
+    missing = [n for n in host_names if not hasattr(host, n)]
+    assert not missing, f"declared in rl_host.h but not exported: {missing}"
+    assert not [n for n in host_names if hasattr(handle, n)], "scene builders leaked into the product library"
+    import subprocess
+    needed = subprocess.run(["readelf", "-d", pkg.HOST_LIB_PATH], capture_output=True, text=True).stdout
+    assert "cuda" not in needed.lower()
 
 
 def test_python_mirror_binds_every_declared_symbol(pkg):
     assert sorted(pkg.SYMBOLS) == declared_symbols()
+    assert sorted(pkg.HOST_SYMBOLS) == declared_symbols("rl_host.h")
     pkg.lib()
-    assert pkg.lib().rl_abi_version() == 1
+    pkg.host_lib()
+    assert pkg.lib().rl_abi_version() == 2
 
 
 def test_pod_layouts_match_reference_records(pkg):
@@ -102,7 +114,7 @@ def test_header_is_plain_c(tmp_path):
     # the boundary is a C ABI: the header compiles as C99, pedantically, without a C++ compiler
     import subprocess
     src = tmp_path / "use_header.c"
-    src.write_text('#include "rl_b200.h"\n'
+    src.write_text('#include "rl_host.h"\n'
                    "int use(void) {\n"
                    "    rl_scene_desc d; rl_mapped_photon p; rl_hit h; rl_ray r;\n"
                    "    (void)d; (void)p; (void)h; (void)r;\n"

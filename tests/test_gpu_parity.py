@@ -167,12 +167,13 @@ def test_trace_full_c4_scene_small_batch(gpu, orc):
     assert_records_equal(got, want, "C4 4096 spheres")
 
 
-def test_render_uses_process_wide_batch_counter(gpu, orc):
+def test_render_uses_the_scene_batch_counter(gpu, orc):
     # TraceUnit::render draws fresh randomness every call (trace_unit.rs:151-168); here each
     # call takes the next batch index, whichever unit makes it
     b = gpu.SceneBuilder(1)
     sc = gpu.Scene(b)
-    gpu.reset_batch_counter(5)
+    sc.reset_batch_counter(5)
+    other = gpu.Scene(b)                            # a second App in the same process: its own ids
     u0 = gpu.TraceUnit(0, 64, 64, seed=9, batch=gpu.TEST_BATCH_PHOTONS)
     u1 = gpu.TraceUnit(1, 64, 64, seed=9, batch=gpu.TEST_BATCH_PHOTONS)
     u0.render(sc)
@@ -184,7 +185,8 @@ def test_render_uses_process_wide_batch_counter(gpu, orc):
     assert_records_equal(u0_first, want[:n], "batch 5")
     assert_records_equal(u1.mapped_photons, want[n:2 * n], "batch 6")
     assert_records_equal(u0.mapped_photons, want[2 * n:], "batch 7")
-    gpu.reset_batch_counter(0)
+    u1.render(other)
+    assert_records_equal(u1.mapped_photons, orc.trace(b.desc(), 9, 64, 64, 0, n), "batch 0 of the other scene")
 
 
 def test_empty_and_ragged_batches(gpu, orc):
@@ -233,7 +235,7 @@ def test_render_async_fills_the_buffer_behind_the_call(gpu, orc):
     b = gpu.SceneBuilder(2)
     sc = gpu.Scene(b)
     n = 30000
-    gpu.reset_batch_counter(40)
+    sc.reset_batch_counter(40)
     units = [gpu.TraceUnit(i, 200, 120, seed=SEED, batch=n) for i in range(5)]
     for u in units:
         u.render(sc, wait=False)                    # batches 40..44, one per unit, all in flight
@@ -242,7 +244,6 @@ def test_render_async_fills_the_buffer_behind_the_call(gpu, orc):
     want = orc.trace(b.desc(), SEED, 200, 120, 40 * n, 5 * n)
     for i, u in enumerate(units):
         assert_records_equal(u.mapped_photons, want[i * n:(i + 1) * n], f"async unit {i}")
-    gpu.reset_batch_counter(0)
 
 
 def test_launch_geometry_does_not_change_results(gpu, monkeypatch):
@@ -609,7 +610,6 @@ def test_scheduler_call_pattern(gpu, orc):
     n = gpu.TEST_BATCH_PHOTONS
     b = gpu.SceneBuilder(2)
     sc = gpu.Scene(b)
-    gpu.reset_batch_counter(0)
     traces = [gpu.TraceUnit(i, w, h, seed=SEED, batch=n) for i in range(3)]
     plot0 = gpu.PlotUnit(0, w, h)
     traces[0].render(sc)
@@ -629,7 +629,6 @@ def test_scheduler_call_pattern(gpu, orc):
     ref_img = orc.plot(w, h, want[:2 * n])
     assert float(np.abs(gather.tristimulus_buffer - ref_img).max()) <= image_tolerance(ref_img)
     assert rgb.shape == (h, w, 3)
-    gpu.reset_batch_counter(0)
 
 
 def test_error_behaviour(gpu):
