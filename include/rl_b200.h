@@ -192,9 +192,10 @@ int rl_trace_unit_set_stream(rl_trace_unit *unit, void *cuda_stream);
  * taken from the scene's batch counter (one scene = one App, app.rs:63), so the
  * union of photons over any schedule of B render() calls on a scene is ids
  * [0, B * batch).  Batches of the reference's size do not get a kernel launch
- * of their own: they are queued to the scene's resident trace service
- * (DESIGN.md 4, K1b), which the scheduler's worker threads keep fed
- * (task_scheduler.rs:95-96,127-182).  If `out` is non-NULL
+ * of their own: they are queued to the scene's trace dispatcher, which traces
+ * everything the scheduler's worker threads have queued (task_scheduler.rs:
+ * 95-96,127-182) with one launch whenever a launch slot is free (DESIGN.md 4,
+ * "group launches").  If `out` is non-NULL
  * it receives batch_size records (the shim's `mapped_photons` Vec) and the
  * call blocks; with NULL the records stay on the device for plot_device. */
 int rl_trace_unit_render(rl_trace_unit *unit, const rl_scene *scene, rl_mapped_photon *out);
@@ -229,6 +230,9 @@ int rl_trace_unit_sync(rl_trace_unit *unit);
 /* Set the scene's batch counter used by rl_trace_unit_render: the next batch
  * is ids [next_batch * batch, (next_batch + 1) * batch). */
 int rl_scene_batch_counter_reset(const rl_scene *scene, uint64_t next_batch);
+/* What the scene's trace dispatcher has done so far: launches, and the
+ * TraceUnit::render batches they carried (batches / launches = mean group). */
+int rl_scene_dispatch_stats(const rl_scene *scene, uint64_t *out_launches, uint64_t *out_batches);
 
 /* Bytes copied host -> device and device -> host by the entry points of this
  * ABI since the last reset (process-wide): scene tables, MappedPhoton batches,

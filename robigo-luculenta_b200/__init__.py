@@ -119,6 +119,7 @@ SYMBOLS = {
     "rl_trace_unit_ray_count": (_I, [_P, C.POINTER(_U64)]),
     "rl_trace_unit_sync": (_I, [_P]),
     "rl_scene_batch_counter_reset": (_I, [_P, _U64]),
+    "rl_scene_dispatch_stats": (_I, [_P, C.POINTER(_U64), C.POINTER(_U64)]),
     "rl_transfer_counters": (None, [C.POINTER(_U64), C.POINTER(_U64)]),
     "rl_transfer_counters_reset": (None, []),
     "rl_host_register": (_I, [_P, C.c_size_t]),
@@ -345,6 +346,13 @@ class Scene:
     def reset_batch_counter(self, next_batch=0):
         """The next TraceUnit.render on this scene takes batch number `next_batch`."""
         _check(lib().rl_scene_batch_counter_reset(self._h, next_batch))
+
+    def dispatch_stats(self):
+        """(launches, batches) of the scene's trace dispatcher: how many TraceUnit.render
+        batches went out with how many launches."""
+        a, b = _U64(0), _U64(0)
+        _check(lib().rl_scene_dispatch_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     # probes ---------------------------------------------------------------
     def intersect(self, rays):

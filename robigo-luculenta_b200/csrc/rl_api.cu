@@ -18,6 +18,7 @@
 
 #include "../../include/rl_b200.h"
 #include "rl_kernels.h"
+#include "rl_math.cuh"
 
 using namespace rl;
 
@@ -130,24 +131,37 @@ int order_after(StreamSlot &earlier, StreamSlot &later) {
 }  // namespace
 
 // ------------------------------------------------------------------ handles
-// The trace service of a scene (csrc/rl_kernels.cu "K1b"): the ring the scene's batches are
-// queued in and the stream its workers run on.  Created with the first batch that uses it.
-struct TraceService {
+// The trace dispatcher of a scene.  The reference's host hands the engine 524 288-photon batches
+// from C worker threads over 3C trace units (task_scheduler.rs:95-96,127-182; app.rs:104-109):
+// 4.6 photons per thread of a full grid, so a launch per batch spends a third of its life in its
+// tail (the last paths of every CTA).  TraceUnit::render calls of that size are therefore queued
+// here, and a dispatcher thread traces everything that is queued with ONE launch (up to
+// RL_MAX_SEGMENTS batches, csrc/rl_kernels.cu K1) whenever one of its two launch slots is free:
+// while two launches are in flight the queue grows, so under load a launch carries a dozen or
+// more batches and its tail is a few per cent, overlapped by the other slot's launch; a lone
+// batch is launched at once.  Everything is ordered with CUDA events -- the launch waits for
+// what each unit's stream held when render() was called, each unit's stream waits for the launch
+// and then copies the records to the host -- so no stream or thread ever polls.
+// Back-pressure comes with it: a unit's next call waits (on a condition variable) until its
+// previous batch has been launched, so worker threads wait inside render()/plot(), as they do in
+// the reference, instead of in the scheduler's 100 ms sleep task (app.rs:128-130).
+struct TraceDispatcher {
+    struct Request {
+        rl_trace_unit *unit;
+        uint64_t first_photon, n_photons;
+        rl_mapped_photon *out;               // host buffer for the records, or nullptr
+    };
     std::mutex m;
-    ServiceQueue *d_queue = nullptr;
-    cudaStream_t workers = nullptr;
-    int reserved_sms = 0;
-    bool failed = false;
-    // Back-pressure.  render() returns once its batch is queued, so a host that recycles units
-    // faster than the GPU traces them (the scheduler's plot and trace tasks are all asynchronous
-    // here) would queue every unit it owns and then find nothing to do -- and the reference's
-    // idle task sleeps 100 ms (app.rs:128-130).  So a render that finds more than half of the
-    // scene's trace units in flight first waits for the oldest batch: worker threads wait inside
-    // render(), as they do in the reference, instead of in the sleep task.
-    std::mutex flight_m;
-    struct Flight { const volatile uint32_t *flag; uint32_t seq; const void *unit; };
-    std::deque<Flight> in_flight;        // the batches queued, oldest first
-    int units = 0;                       // trace units that have queued a batch to this service
+    std::condition_variable cv_work;         // dispatcher: a request is queued / stop
+    std::condition_variable cv_done;         // callers: requests have been launched
+    std::deque<Request> queue;
+    std::thread thread;
+    bool started = false, stop = false, failed = false;
+    static const int MAX_SLOTS = 8;
+    int slots = 2;                           // launches in flight at once
+    cudaStream_t streams[MAX_SLOTS] = {};
+    cudaEvent_t done[MAX_SLOTS] = {};
+    uint64_t launches = 0, batches = 0;      // statistics (rl_scene_dispatch_stats)
 };
 
 struct rl_scene {
@@ -159,7 +173,7 @@ struct rl_scene {
     // TraceUnit::render takes its photon ids from the scene's batch counter: one scene is one
     // App (app.rs:63), two renders in one process do not share ids
     mutable std::atomic<uint64_t> next_batch{0};
-    mutable TraceService service;
+    mutable TraceDispatcher dispatcher;
 };
 
 struct rl_trace_unit {
@@ -173,16 +187,14 @@ struct rl_trace_unit {
     uint64_t capacity = 0;
     uint64_t n_valid = 0;  // records left on the device by the last render
     unsigned long long *d_rays = nullptr;
-    // trace service: the word a finished batch stores its sequence number to, the number of the
-    // latest batch, and the event behind the latest push
-    volatile uint32_t *h_done = nullptr; // the completion word, in mapped page-locked host memory
-    uint32_t *d_done = nullptr;          // its device address
-    uint32_t done_seq = 0;
-    bool in_service = false;             // the latest batch went to the service and may still be in flight
-    rl_mapped_photon *pending_out = nullptr;   // host buffer the latest batch's records still have to be copied to
-    uint64_t pending_n = 0;
-    cudaEvent_t pushed = nullptr;
-    TraceService *service = nullptr;     // the service this unit is counted in
+    // trace dispatcher: the unit's latest batch sits in a scene's queue until `queued` drops; from
+    // then on everything it needs is ordered on the unit's stream
+    std::atomic<bool> queued{false};
+    TraceDispatcher *dispatcher = nullptr;   // valid while `queued`
+    cudaEvent_t ready = nullptr;             // what the unit's stream held when the batch was queued
+    cudaEvent_t traced = nullptr;            // the latest records are complete (before their copy to the host)
+    int dispatch_rc = RL_OK;                 // outcome of the launch, reported by the unit's next call
+    std::string dispatch_error;
 };
 
 struct rl_plot_unit {
@@ -211,6 +223,8 @@ struct SaveWriter {
     std::thread thread;
     bool started = false, stop = false;
     float *buf[2] = {nullptr, nullptr};
+    cudaEvent_t copied[2] = {nullptr, nullptr};   // the snapshot in buf[i] has arrived (recorded behind its copies)
+    int device = 0;
     size_t floats = 0;
     int pending = -1, writing = -1;
     std::string pending_path, error;
@@ -230,6 +244,7 @@ struct SaveWriter {
         return true;
     }
     void run() {
+        cudaSetDevice(device);
         std::unique_lock<std::mutex> lock(m);
         for (;;) {
             cv.wait(lock, [&] { return pending >= 0 || stop; });
@@ -240,7 +255,11 @@ struct SaveWriter {
             writing = idx;
             lock.unlock();
             std::string err;
-            const bool ok = write_file(path, buf[idx], floats, err);
+            // the snapshot was only queued by save(): wait here, not in the caller, for the copies
+            const cudaError_t ce = cudaEventSynchronize(copied[idx]);
+            bool ok = ce == cudaSuccess;
+            if (!ok) err = std::string("buffer.raw snapshot: ") + cudaGetErrorString(ce);
+            else ok = write_file(path, buf[idx], floats, err);
             lock.lock();
             writing = -1;
             if (!ok && error.empty()) error = err;
@@ -266,6 +285,7 @@ struct SaveWriter {
             started = false;
         }
         for (float *&b : buf) { if (b) cudaFreeHost(b); b = nullptr; }
+        for (cudaEvent_t &e : copied) { if (e) cudaEventDestroy(e); e = nullptr; }
     }
 };
 
@@ -448,103 +468,125 @@ int max_stack(const std::vector<uint32_t> &ops, size_t first, size_t n) {
     return mx;
 }
 
-// ---- trace service plumbing ------------------------------------------------------------------
+// ---- trace dispatcher plumbing ----------------------------------------------------------------
 int env_int(const char *name, int fallback) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : fallback;
 }
 
-// Completion words.  A finished batch stores its sequence number to a word in mapped page-locked
-// host memory; whoever needs the batch (the unit's next call, the plot unit that splats its
-// records, sync) polls that word from the host -- no stream ever waits on the service, so no
-// hardware queue is blocked behind a batch that is still being traced.  (Both device-side
-// alternatives were measured on the scheduler replay: cuStreamWaitValue32 deschedules the channel
-// for milliseconds per wait, 77 Mrays/s; a polling kernel per unit holds its hardware queue,
-// 1 850 Mrays/s; one launch per batch without the service: 2 490.)  The words live in slabs that are
-// never freed, so a thread that still polls a word of a unit that has just been destroyed reads
-// valid memory; a recycled word keeps counting from where its last owner stopped.
-struct FlagPool {
-    std::mutex m;
-    std::vector<volatile uint32_t *> free_words;
-    int take(volatile uint32_t **host, uint32_t **device) {
-        std::lock_guard<std::mutex> lock(m);
-        if (free_words.empty()) {
-            void *slab = nullptr;
-            const size_t words = 1024;
-            RL_CUDA(cudaHostAlloc(&slab, words * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
-            memset(slab, 0, words * sizeof(uint32_t));
-            for (size_t i = 0; i < words; i++) free_words.push_back(static_cast<volatile uint32_t *>(slab) + i);
-        }
-        *host = free_words.back();
-        free_words.pop_back();
-        void *d = nullptr;
-        cudaError_t e = cudaHostGetDevicePointer(&d, const_cast<uint32_t *>(*host), 0);
-        if (e != cudaSuccess) {
-            free_words.push_back(*host);
-            return fail(RL_ERR_CUDA, std::string("cudaHostGetDevicePointer: ") + cudaGetErrorString(e));
-        }
-        *device = static_cast<uint32_t *>(d);
-        return RL_OK;
-    }
-    void give_back(volatile uint32_t *host) {
-        std::lock_guard<std::mutex> lock(m);
-        free_words.push_back(host);
-    }
-};
-FlagPool g_flags;
-
-// Host wait until *flag has reached `seq` (sequence numbers, wrap-around compare).
-int wait_flag(const volatile uint32_t *flag, uint32_t seq, cudaStream_t workers) {
-    const auto reached = [&] { return (int32_t)(*flag - seq) >= 0; };
-    for (int spin = 0; spin < 2000; spin++) {
-        if (reached()) return RL_OK;
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
-    }
-    const auto t0 = std::chrono::steady_clock::now();
-    for (uint64_t polls = 0;; polls++) {
-        if (reached()) return RL_OK;
-        std::this_thread::sleep_for(std::chrono::microseconds(polls < 50 ? 5 : 25));
-        if ((polls & 0x3fff) == 0x3fff) {
-            // a worker that died takes its batches with it: report instead of waiting for ever
-            cudaError_t e = workers ? cudaStreamQuery(workers) : cudaSuccess;
-            if (e != cudaSuccess && e != cudaErrorNotReady)
-                return fail(RL_ERR_CUDA, std::string("trace service: ") + cudaGetErrorString(e));
-            cudaGetLastError();
-            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(env_int("RL_SERVICE_TIMEOUT_S", 300)))
-                return fail(RL_ERR_CUDA, "trace service: a batch did not finish (RL_SERVICE_TIMEOUT_S)");
-        }
-    }
-}
-
-// Batches below this size go through the trace service (0: never).  The same bound as the
-// small-launch rule of launch_trace: fewer than 64 photons per thread of a full grid.
-bool use_service(const rl_scene *scene, uint64_t n_photons) {
-    if (n_photons == 0 || n_photons > (1ull << 28)) return false;
-    if (scene->service.failed || !env_int("RL_TRACE_SERVICE", 1)) return false;
+// Batches below this size are queued to the scene's dispatcher (RL_TRACE_GROUPS=0: never).  The
+// same bound as the small-launch rule of launch_trace: fewer than 64 photons per thread of a
+// full grid -- larger requests fill the GPU on their own.
+bool use_dispatcher(const rl_scene *scene, uint64_t n_photons) {
+    if (n_photons == 0 || n_photons >= (1ull << RL_SEGMENT_INDEX_BITS)) return false;
+    if (scene->dispatcher.failed || !env_int("RL_TRACE_GROUPS", 1)) return false;
     return n_photons < 64ull * (uint64_t)scene->dev.sm_count * 768ull;
 }
 
-int service_get(const rl_scene *scene, TraceService **out) {
-    TraceService &svc = scene->service;
-    std::lock_guard<std::mutex> lock(svc.m);
-    if (!svc.d_queue) {
-        cudaError_t e = cudaMalloc(&svc.d_queue, sizeof(ServiceQueue));
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&svc.workers, cudaStreamNonBlocking);
-        // the ring is cleared before any unit's stream can push to it (a memset is asynchronous,
-        // and the units' non-blocking streams are not ordered behind the default stream)
-        if (e == cudaSuccess) e = cudaMemsetAsync(svc.d_queue, 0, sizeof(ServiceQueue), svc.workers);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(svc.workers);
-        if (e != cudaSuccess) {
-            cudaFree(svc.d_queue); svc.d_queue = nullptr; svc.failed = true;
-            return fail(RL_ERR_CUDA, std::string("trace service: ") + cudaGetErrorString(e));
+void dispatcher_loop(const rl_scene *scene) {
+    TraceDispatcher &d = scene->dispatcher;
+    cudaSetDevice(scene->dev.index);
+    const size_t group_max = (size_t)std::min(RL_MAX_SEGMENTS, std::max(1, env_int("RL_TRACE_GROUP_MAX", RL_MAX_SEGMENTS)));
+    int slot = 0;
+    std::vector<TraceDispatcher::Request> group;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(d.m);
+            d.cv_work.wait(lk, [&] { return d.stop || !d.queue.empty(); });
+            if (d.queue.empty()) return;                          // stop, and nothing left to launch
         }
-        int reserved = env_int("RL_SERVICE_RESERVED_SMS", 2);
-        svc.reserved_sms = reserved < 0 ? 0 : (reserved > scene->dev.sm_count - 1 ? scene->dev.sm_count - 1 : reserved);
+        // at most two launches in flight: wait for the one that last used this slot; what is
+        // queued meanwhile joins this launch
+        cudaEventSynchronize(d.done[slot]);
+        group.clear();
+        {
+            std::lock_guard<std::mutex> lk(d.m);
+            const uint32_t w = d.queue.front().unit->width, h = d.queue.front().unit->height;
+            for (auto it = d.queue.begin(); it != d.queue.end() && group.size() < group_max;) {
+                if (it->unit->width == w && it->unit->height == h) { group.push_back(*it); it = d.queue.erase(it); }
+                else ++it;
+            }
+        }
+        cudaStream_t st = d.streams[slot];
+        TraceLaunch p;
+        memset(&p, 0, sizeof(p));
+        p.width = group[0].unit->width; p.height = group[0].unit->height;
+        p.accum = nullptr;
+        p.n_segments = (uint32_t)group.size();
+        cudaError_t e = cudaSuccess;
+        for (size_t k = 0; k < group.size() && e == cudaSuccess; k++) {
+            rl_trace_unit *u = group[k].unit;
+            p.seg[k].seed = u->seed;
+            p.seg[k].first_photon = group[k].first_photon;
+            p.seg[k].n_photons = group[k].n_photons;
+            p.seg[k].records = u->d_records;
+            p.seg[k].ray_counter = u->d_rays;
+            e = cudaStreamWaitEvent(st, u->ready, 0);
+        }
+        if (e == cudaSuccess) e = launch_trace(scene->ds, p, scene->dev.sm_count, st);
+        if (e == cudaSuccess) e = cudaEventRecord(d.done[slot], st);
+        for (size_t k = 0; k < group.size() && e == cudaSuccess; k++) {
+            rl_trace_unit *u = group[k].unit;
+            e = cudaStreamWaitEvent(u->ss.stream, d.done[slot], 0);
+            if (e == cudaSuccess) e = cudaEventRecord(u->traced, u->ss.stream);
+            if (e == cudaSuccess && group[k].out)
+                e = copy_async(group[k].out, u->d_records, group[k].n_photons * sizeof(rl_mapped_photon),
+                               cudaMemcpyDeviceToHost, u->ss.stream);
+        }
+        if (e != cudaSuccess) cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> lk(d.m);
+            d.launches++; d.batches += group.size();
+            for (auto &r : group) {
+                if (e != cudaSuccess) {
+                    r.unit->dispatch_rc = RL_ERR_CUDA;
+                    r.unit->dispatch_error = std::string("trace dispatcher: ") + cudaGetErrorString(e);
+                }
+                r.unit->queued.store(false, std::memory_order_release);
+            }
+        }
+        d.cv_done.notify_all();
+        slot = (slot + 1) % d.slots;
     }
-    *out = &svc;
+}
+
+int dispatcher_start(const rl_scene *scene) {
+    TraceDispatcher &d = scene->dispatcher;
+    std::lock_guard<std::mutex> lk(d.m);
+    if (d.started) return RL_OK;
+    cudaError_t e = cudaSuccess;
+    d.slots = std::min((int)TraceDispatcher::MAX_SLOTS, std::max(1, env_int("RL_TRACE_SLOTS", 2)));
+    for (int k = 0; k < d.slots && e == cudaSuccess; k++) {
+        e = cudaStreamCreateWithFlags(&d.streams[k], cudaStreamNonBlocking);
+        // blocking sync: the dispatcher thread sleeps while it waits for a slot
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.done[k], cudaEventDisableTiming | cudaEventBlockingSync);
+    }
+    if (e != cudaSuccess) {
+        d.failed = true;
+        return fail(RL_ERR_CUDA, std::string("trace dispatcher: ") + cudaGetErrorString(e));
+    }
+    try {
+        d.thread = std::thread(dispatcher_loop, scene);
+    } catch (...) {
+        d.failed = true;                                  // no thread: batches are launched one by one
+        return fail(RL_ERR_NOMEM, "trace dispatcher: cannot create a thread");
+    }
+    d.started = true;
     return RL_OK;
+}
+
+void dispatcher_stop(rl_scene *scene) {
+    TraceDispatcher &d = scene->dispatcher;
+    {
+        std::lock_guard<std::mutex> lk(d.m);
+        d.stop = true;
+    }
+    d.cv_work.notify_all();
+    if (d.thread.joinable()) d.thread.join();             // launches what is still queued first
+    for (int k = 0; k < TraceDispatcher::MAX_SLOTS; k++) {
+        if (d.streams[k]) { cudaStreamSynchronize(d.streams[k]); cudaStreamDestroy(d.streams[k]); }
+        if (d.done[k]) cudaEventDestroy(d.done[k]);
+    }
 }
 
 template <class T>
@@ -689,8 +731,8 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
             if (R > cluster_rmax) cluster_rmax = R;
             if (mr2 + R * R > fl.cmax2) fl.cmax2 = mr2 + R * R;
         }
-        // the cluster scan takes four records per step: pad with records no ray selects
-        while (clusters.size() % 4 != 0) {
+        // the cluster scan takes eight records per step: pad with records no ray selects
+        while (clusters.size() % 8 != 0) {
             clusters.push_back(make_float4(0.f, 0.f, 0.f, 1.0e30f));
             cluster_range.push_back(0u);
         }
@@ -710,6 +752,31 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     }
     ds.off_compounds = append(blob, fl.compounds);      ds.n_compounds = (uint32_t)fl.compounds.size() / 2;
     ds.off_ops = append(blob, fl.ops);                  ds.n_ops = (uint32_t)fl.ops.size();
+    {
+        // the compounds' bounding spheres once more, in the form the sphere pre-test scans:
+        // {c, |c|^2 - r^2}, centre as stored (f32), padded to eight records; unbounded bodies are
+        // flagged per group of 64 and always evaluated
+        std::vector<float4> body_bounds;
+        std::vector<uint64_t> body_always((fl.compounds.size() / 2 + 63) / 64 + 1, 0ull);
+        double body_rmax = 0.0;
+        for (size_t k = 0; k < fl.compounds.size() / 2; k++) {
+            const float4 b = fl.compounds[2 * k + 1];
+            if (b.w < 0.0f) {
+                body_always[k / 64] |= 1ull << (k % 64);
+                body_bounds.push_back(make_float4(0.f, 0.f, 0.f, 1.0e30f));
+                continue;
+            }
+            const double c2 = (double)b.x * b.x + (double)b.y * b.y + (double)b.z * b.z;
+            const double r2 = (double)b.w * (1.0 + 1e-6);          // the f32 record of |c|^2 - r^2 rounds: keep it outside
+            body_bounds.push_back(make_float4(b.x, b.y, b.z, (float)(c2 - r2)));
+            if (c2 + r2 > fl.cmax2) fl.cmax2 = c2 + r2;
+            if (sqrt(r2) > body_rmax) body_rmax = sqrt(r2);
+        }
+        while (body_bounds.size() % 8 != 0 || body_bounds.empty()) body_bounds.push_back(make_float4(0.f, 0.f, 0.f, 1.0e30f));
+        ds.off_body_bounds = append(blob, body_bounds);
+        ds.off_body_always = append(blob, body_always);
+        ds.body_rmax = (float)(body_rmax * 1.0001);
+    }
     ds.off_sphere_k = append(blob, fl.sphere_k);
     ds.off_clusters = append(blob, clusters);           ds.n_clusters = (uint32_t)clusters.size();
     ds.off_cluster_range = append(blob, cluster_range);
@@ -737,6 +804,12 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     c.kind = cm.kind;
     c.px = cm.fixed.position.x; c.py = cm.fixed.position.y; c.pz = cm.fixed.position.z;
     c.field_of_view = cm.fixed.field_of_view;
+    {
+        // camera.rs:60, in the specified arithmetic the kernels use (1 / tan, tan = sin / cos)
+        float fs, fc;
+        spec_sincos(c.field_of_view * 0.5f, fs, fc);
+        c.screen_distance = 1.0f / (fs / fc);
+    }
     c.focal_distance = cm.fixed.focal_distance;
     c.depth_of_field = cm.fixed.depth_of_field;
     c.chromatic_abberation = cm.fixed.chromatic_abberation;
@@ -770,12 +843,7 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
 int rl_scene_destroy(rl_scene *scene) {
     if (!scene) return RL_OK;
     DeviceGuard guard(scene->dev.index);
-    if (scene->service.workers) {
-        // workers retire by themselves once the ring stays empty
-        cudaStreamSynchronize(scene->service.workers);
-        cudaStreamDestroy(scene->service.workers);
-    }
-    cudaFree(scene->service.d_queue);
+    dispatcher_stop(scene);
     cudaFree(scene->d_blob);
     cudaFree(scene->d_materials);
     delete scene;
@@ -795,37 +863,32 @@ int rl_trace_unit_create(uint64_t id, uint32_t width, uint32_t height, uint64_t 
     cudaError_t e = cudaMalloc(&u->d_rays, sizeof(unsigned long long));
     // cleared on the unit's own stream: everything the unit does later is ordered behind it
     if (e == cudaSuccess) e = cudaMemsetAsync(u->d_rays, 0, sizeof(unsigned long long), u->ss.stream);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&u->pushed, cudaEventDisableTiming);
-    if (e == cudaSuccess && g_flags.take(&u->h_done, &u->d_done) != RL_OK) e = cudaErrorMemoryAllocation;
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&u->ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&u->traced, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         cudaFree(u->d_rays);
-        if (u->pushed) cudaEventDestroy(u->pushed);
+        if (u->ready) cudaEventDestroy(u->ready);
+        if (u->traced) cudaEventDestroy(u->traced);
         u->ss.destroy(); delete u;
         return fail(RL_ERR_CUDA, cudaGetErrorString(e));
     }
-    u->done_seq = *u->h_done;            // a recycled completion word keeps counting
     *out = u;
     return RL_OK;
 }
 
-// The unit's latest batch is finished (host wait on its completion word).
-static int trace_wait_done(rl_trace_unit *u) {
-    if (!u->in_service) return RL_OK;
-    int rc = wait_flag(u->h_done, u->done_seq, u->service ? u->service->workers : nullptr);
-    if (rc != RL_OK) return rc;
-    u->in_service = false;
-    return RL_OK;
-}
-
-// ... and the copy of its records into the host buffer render() was given is queued.
-static int trace_finish(rl_trace_unit *u) {
-    int rc = trace_wait_done(u);
-    if (rc != RL_OK) return rc;
-    if (u->pending_out) {
-        rl_mapped_photon *out = u->pending_out;
-        u->pending_out = nullptr;
-        RL_CUDA(copy_async(out, u->d_records, u->pending_n * sizeof(rl_mapped_photon), cudaMemcpyDeviceToHost,
-                           u->ss.stream));
+// The unit's latest batch has been launched: everything it needs (the launch, the copy of its
+// records to the host) is ordered on the unit's stream from here on.  A short host wait on the
+// dispatcher's condition variable when the batch is still queued.
+static int trace_settle(rl_trace_unit *u) {
+    if (u->queued.load(std::memory_order_acquire)) {
+        TraceDispatcher *d = u->dispatcher;
+        std::unique_lock<std::mutex> lk(d->m);
+        d->cv_done.wait(lk, [&] { return !u->queued.load(std::memory_order_acquire); });
+    }
+    if (u->dispatch_rc != RL_OK) {
+        const int rc = u->dispatch_rc;
+        u->dispatch_rc = RL_OK;
+        return fail(rc, u->dispatch_error);
     }
     return RL_OK;
 }
@@ -833,18 +896,12 @@ static int trace_finish(rl_trace_unit *u) {
 int rl_trace_unit_destroy(rl_trace_unit *u) {
     if (!u) return RL_OK;
     DeviceGuard guard(u->dev.index);
-    trace_finish(u);
+    trace_settle(u);
     if (u->ss.stream) cudaStreamSynchronize(u->ss.stream);
-    if (u->service) {
-        std::lock_guard<std::mutex> lock(u->service->flight_m);
-        auto &q = u->service->in_flight;
-        q.erase(std::remove_if(q.begin(), q.end(), [u](const TraceService::Flight &f) { return f.unit == u; }), q.end());
-        u->service->units--;
-    }
     cudaFree(u->d_records);
     cudaFree(u->d_rays);
-    if (u->h_done) g_flags.give_back(u->h_done);
-    if (u->pushed) cudaEventDestroy(u->pushed);
+    if (u->ready) cudaEventDestroy(u->ready);
+    if (u->traced) cudaEventDestroy(u->traced);
     u->ss.destroy();
     delete u;
     return RL_OK;
@@ -859,7 +916,7 @@ int rl_trace_unit_set_batch_size(rl_trace_unit *u, uint64_t n) {
 int rl_trace_unit_set_stream(rl_trace_unit *u, void *s) {
     if (!u) return fail(RL_ERR_INVALID, "null unit");
     DeviceGuard guard(u->dev.index);
-    int rc = trace_finish(u);
+    int rc = trace_settle(u);
     if (rc != RL_OK) return rc;
     return u->ss.bind(s);
 }
@@ -874,64 +931,38 @@ static int ensure_records(rl_trace_unit *u, uint64_t n) {
     return RL_OK;
 }
 
-// Queue photons [first, first + n) of `scene` on the unit's stream: through the trace service
-// when the batch is small (the reference's 524 288-photon batches) and leaves records, as one
-// launch otherwise.  `*serviced` tells which.
-static int queue_trace(rl_trace_unit *u, const rl_scene *scene, uint64_t first_photon, uint64_t n_photons,
-                       rl_mapped_photon *records, float4 *accum, bool *serviced) {
-    *serviced = false;
+// Photons [first, first + n) of `scene` into the unit's record buffer (and `out`, a host buffer,
+// when given): through the scene's dispatcher when the batch is small (the reference's 524 288
+// photons), as a launch on the unit's stream otherwise.  Returns once the work is queued.
+static int queue_records(rl_trace_unit *u, const rl_scene *scene, uint64_t first_photon, uint64_t n_photons,
+                         rl_mapped_photon *out) {
     if (n_photons == 0) return RL_OK;
-    // a fused batch is consumed by the plot unit's stream: it stays a launch, ordered by events
-    if (!accum && use_service(scene, n_photons)) {
-        TraceService *svc = nullptr;
-        int rc = service_get(scene, &svc);
-        if (rc != RL_OK) return rc;
-        ServiceEntry e;
-        memset(&e, 0, sizeof(e));
-        e.seed = u->seed; e.first_photon = first_photon; e.n_photons = (uint32_t)n_photons;
-        e.records = records; e.accum = nullptr; e.ray_counter = u->d_rays;
-        e.width = u->width; e.height = u->height;
-        e.aspect = (float)u->width / (float)u->height;            // trace_unit.rs:73, plot_unit.rs:49
-        e.done_flag = u->d_done; e.done_value = ++u->done_seq;
-        // the push runs in stream order (after whatever still reads the unit's records); a worker
-        // is launched behind it, so that every queued batch has a worker that starts after it is
-        // visible -- whichever worker is resident when the push lands takes the photons
-        RL_CUDA(launch_service_push(svc->d_queue, e, u->ss.stream));
-        RL_CUDA(cudaEventRecord(u->pushed, u->ss.stream));
-        RL_CUDA(cudaStreamWaitEvent(svc->workers, u->pushed, 0));
-        RL_CUDA(launch_service_worker(scene->ds, svc->d_queue, scene->dev.sm_count, svc->reserved_sms, svc->workers));
-        u->in_service = true;
-        *serviced = true;
-        // back-pressure (see TraceService): at most half of the scene's units in flight
-        if (u->service && u->service != svc) {                   // the unit moved to another scene
-            std::lock_guard<std::mutex> lock(u->service->flight_m);
-            auto &q = u->service->in_flight;
-            q.erase(std::remove_if(q.begin(), q.end(), [u](const TraceService::Flight &f) { return f.unit == u; }), q.end());
-            u->service->units--;
-            u->service = nullptr;
-        }
-        TraceService::Flight oldest{nullptr, 0, nullptr};
+    if (use_dispatcher(scene, n_photons) && dispatcher_start(scene) == RL_OK) {
+        TraceDispatcher &d = scene->dispatcher;
+        // the launch waits for what the unit's stream holds now (the copy and the splat of the
+        // unit's previous records)
+        RL_CUDA(cudaEventRecord(u->ready, u->ss.stream));
         {
-            std::lock_guard<std::mutex> lock(svc->flight_m);
-            if (!u->service) { u->service = svc; svc->units++; }
-            auto &q = svc->in_flight;
-            q.erase(std::remove_if(q.begin(), q.end(), [u](const TraceService::Flight &f) { return f.unit == u; }), q.end());
-            q.push_back(TraceService::Flight{u->h_done, e.done_value, u});
-            const size_t depth = (size_t)env_int("RL_TRACE_DEPTH", 0);
-            const size_t limit = depth ? depth : (size_t)std::max(2, svc->units / 2);
-            if (q.size() > limit) { oldest = q.front(); q.pop_front(); }
+            std::lock_guard<std::mutex> lk(d.m);
+            u->dispatcher = &d;
+            u->queued.store(true, std::memory_order_release);
+            d.queue.push_back(TraceDispatcher::Request{u, first_photon, n_photons, out});
         }
-        if (oldest.flag && oldest.unit != u) {
-            rc = wait_flag(oldest.flag, oldest.seq, svc->workers);
-            if (rc != RL_OK) return rc;
-        }
+        d.cv_work.notify_one();
         return RL_OK;
     }
     TraceLaunch p;
-    p.seed = u->seed; p.first_photon = first_photon; p.n_photons = n_photons;
+    memset(&p, 0, sizeof(p));
     p.width = u->width; p.height = u->height;
-    p.records = records; p.accum = accum; p.ray_counter = u->d_rays;
+    p.accum = nullptr;
+    p.n_segments = 1;
+    p.seg[0].seed = u->seed; p.seg[0].first_photon = first_photon; p.seg[0].n_photons = n_photons;
+    p.seg[0].records = u->d_records; p.seg[0].ray_counter = u->d_rays;
     RL_CUDA(launch_trace(scene->ds, p, u->dev.sm_count, u->ss.stream));
+    RL_CUDA(cudaEventRecord(u->traced, u->ss.stream));
+    if (out)
+        RL_CUDA(copy_async(out, u->d_records, n_photons * sizeof(rl_mapped_photon), cudaMemcpyDeviceToHost,
+                           u->ss.stream));
     return RL_OK;
 }
 
@@ -940,26 +971,15 @@ static int render_range(rl_trace_unit *u, const rl_scene *scene, uint64_t first_
     if (!u || !scene) return fail(RL_ERR_INVALID, "rl_trace_unit_render: null argument");
     if (scene->dev.index != u->dev.index) return fail(RL_ERR_INVALID, "scene and unit on different devices");
     DeviceGuard guard(u->dev.index);
-    int rc = trace_finish(u);                    // the previous batch and the copy of its records
+    int rc = trace_settle(u);                    // the previous batch has been launched
     if (rc == RL_OK) rc = ensure_records(u, n_photons);
-    if (rc != RL_OK) return rc;
-    bool serviced = false;
-    rc = queue_trace(u, scene, first_photon, n_photons, u->d_records, nullptr, &serviced);
+    if (rc == RL_OK) rc = queue_records(u, scene, first_photon, n_photons, out);
     if (rc != RL_OK) return rc;
     u->n_valid = n_photons;
-    if (out && n_photons) {
-        if (serviced) {
-            // the copy is queued once the batch is finished: by the next call on this unit, by the
-            // plot unit that takes its records, or by sync -- `out` is complete after sync
-            u->pending_out = out;
-            u->pending_n = n_photons;
-            if (wait) rc = trace_finish(u);
-            if (rc != RL_OK) return rc;
-        } else {
-            RL_CUDA(copy_async(out, u->d_records, n_photons * sizeof(rl_mapped_photon),
-                               cudaMemcpyDeviceToHost, u->ss.stream));
-        }
-        if (wait) RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    if (wait && out && n_photons) {
+        rc = trace_settle(u);
+        if (rc != RL_OK) return rc;
+        RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     }
     return RL_OK;
 }
@@ -986,7 +1006,7 @@ int rl_trace_unit_download(rl_trace_unit *u, rl_mapped_photon *out, uint64_t cap
     if (u->n_valid > capacity)
         return fail(RL_ERR_INVALID, "rl_trace_unit_download: the last render left more records than `capacity`");
     DeviceGuard guard(u->dev.index);
-    int rc = trace_finish(u);
+    int rc = trace_settle(u);
     if (rc != RL_OK) return rc;
     if (u->n_valid)
         RL_CUDA(copy_async(out, u->d_records, u->n_valid * sizeof(rl_mapped_photon), cudaMemcpyDeviceToHost,
@@ -1004,12 +1024,18 @@ int rl_trace_unit_render_fused(rl_trace_unit *u, const rl_scene *scene, rl_plot_
     if (plot->width != u->width || plot->height != u->height)
         return fail(RL_ERR_INVALID, "trace and plot unit canvas sizes differ");
     DeviceGuard guard(u->dev.index);
-    int rc = trace_finish(u);
+    int rc = trace_settle(u);
     if (rc == RL_OK) rc = order_after(plot->ss, u->ss);
     if (rc != RL_OK) return rc;
-    bool serviced = false;
-    rc = queue_trace(u, scene, first_photon, n_photons, nullptr, plot->d_accum, &serviced);
-    if (rc != RL_OK) return rc;
+    // a fused batch is consumed by the plot unit's stream: always a launch of its own
+    TraceLaunch p;
+    memset(&p, 0, sizeof(p));
+    p.width = u->width; p.height = u->height;
+    p.accum = plot->d_accum;
+    p.n_segments = 1;
+    p.seg[0].seed = u->seed; p.seg[0].first_photon = first_photon; p.seg[0].n_photons = n_photons;
+    p.seg[0].records = nullptr; p.seg[0].ray_counter = u->d_rays;
+    RL_CUDA(launch_trace(scene->ds, p, u->dev.sm_count, u->ss.stream));
     u->n_valid = 0;
     return order_after(u->ss, plot->ss);
 }
@@ -1017,7 +1043,7 @@ int rl_trace_unit_render_fused(rl_trace_unit *u, const rl_scene *scene, rl_plot_
 int rl_trace_unit_ray_count(rl_trace_unit *u, uint64_t *out_rays) {
     if (!u || !out_rays) return fail(RL_ERR_INVALID, "null argument");
     DeviceGuard guard(u->dev.index);
-    int rc = trace_wait_done(u);
+    int rc = trace_settle(u);
     if (rc != RL_OK) return rc;
     unsigned long long v = 0;
     RL_CUDA(copy_async(&v, u->d_rays, sizeof(v), cudaMemcpyDeviceToHost, u->ss.stream));
@@ -1029,7 +1055,7 @@ int rl_trace_unit_ray_count(rl_trace_unit *u, uint64_t *out_rays) {
 int rl_trace_unit_sync(rl_trace_unit *u) {
     if (!u) return fail(RL_ERR_INVALID, "null unit");
     DeviceGuard guard(u->dev.index);
-    int rc = trace_finish(u);
+    int rc = trace_settle(u);
     if (rc != RL_OK) return rc;
     RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     return RL_OK;
@@ -1038,6 +1064,14 @@ int rl_trace_unit_sync(rl_trace_unit *u) {
 int rl_scene_batch_counter_reset(const rl_scene *scene, uint64_t next_batch) {
     if (!scene) return fail(RL_ERR_INVALID, "null scene");
     scene->next_batch.store(next_batch);
+    return RL_OK;
+}
+
+int rl_scene_dispatch_stats(const rl_scene *scene, uint64_t *out_launches, uint64_t *out_batches) {
+    if (!scene) return fail(RL_ERR_INVALID, "null scene");
+    std::lock_guard<std::mutex> lk(scene->dispatcher.m);
+    if (out_launches) *out_launches = scene->dispatcher.launches;
+    if (out_batches) *out_batches = scene->dispatcher.batches;
     return RL_OK;
 }
 
@@ -1128,17 +1162,15 @@ int rl_plot_unit_plot_device(rl_plot_unit *u, rl_trace_unit *trace) {
     if (u->dev.index != trace->dev.index) return fail(RL_ERR_INVALID, "units on different devices");
     if (trace->n_valid == 0) return RL_OK;
     DeviceGuard guard(u->dev.index);
-    // the records are complete (host wait if the batch went through the trace service); the splat
-    // is ordered behind what the trace unit's stream holds NOW, then the copy of the records to the
-    // host is queued on that stream -- it runs beside the splat, and the unit's next batch is
-    // ordered behind both
-    int rc = trace_wait_done(trace);
-    if (rc == RL_OK) rc = order_after(trace->ss, u->ss);
+    // the batch has been launched (short host wait if it is still in the dispatcher's queue): the
+    // trace unit's stream now holds the launch's event and the copy of the records to the host;
+    // the splat is ordered behind the event only -- it runs beside the copy -- and the unit's next
+    // batch behind both
+    int rc = trace_settle(trace);
     if (rc != RL_OK) return rc;
+    RL_CUDA(cudaStreamWaitEvent(u->ss.stream, trace->traced, 0));
     RL_CUDA(launch_splat(trace->d_records, trace->n_valid, u->d_accum, u->width, u->height,
                          u->dev.sm_count, u->ss.stream));
-    rc = trace_finish(trace);
-    if (rc != RL_OK) return rc;
     return order_after(u->ss, trace->ss);
 }
 
@@ -1295,7 +1327,15 @@ int rl_gather_unit_save(rl_gather_unit *u, const char *path) {
         wr.floats = 2 * n;
         RL_CUDA(cudaMallocHost(&wr.buf[0], 2 * n * sizeof(float)));
         cudaError_t e = cudaMallocHost(&wr.buf[1], 2 * n * sizeof(float));
-        if (e != cudaSuccess) { cudaFreeHost(wr.buf[0]); wr.buf[0] = nullptr; return fail(RL_ERR_CUDA, cudaGetErrorString(e)); }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&wr.copied[0], cudaEventDisableTiming | cudaEventBlockingSync);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&wr.copied[1], cudaEventDisableTiming | cudaEventBlockingSync);
+        if (e != cudaSuccess) {
+            cudaFreeHost(wr.buf[0]); wr.buf[0] = nullptr;
+            if (wr.buf[1]) cudaFreeHost(wr.buf[1]);
+            wr.buf[1] = nullptr;
+            return fail(RL_ERR_CUDA, cudaGetErrorString(e));
+        }
+        wr.device = u->dev.index;
     }
     bool proven = false;
     for (const std::string &p : wr.proven) proven |= p == path;
@@ -1322,7 +1362,12 @@ int rl_gather_unit_save(rl_gather_unit *u, const char *path) {
     float *host = wr.buf[idx];
     RL_CUDA(copy_async(host, u->d_acc, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
     RL_CUDA(copy_async(host + n, u->d_comp, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
-    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    // The snapshot is taken in stream order; nobody waits for it here.  The gather task holds the
+    // gather unit and every finished plot unit while it runs (task_scheduler.rs:209-219): a host
+    // wait at this point is as long as the GPU's queue is deep, and the scheduler has no plot
+    // unit to hand out meanwhile.  The writer thread waits for the event instead.
+    RL_CUDA(cudaEventRecord(wr.copied[idx], u->ss.stream));
+    if (!proven) RL_CUDA(cudaStreamSynchronize(u->ss.stream));
     if (!proven) {
         std::string err;
         if (!SaveWriter::write_file(path, host, 2 * n, err)) return fail(RL_ERR_IO, err);
@@ -1347,6 +1392,7 @@ int rl_gather_unit_save(rl_gather_unit *u, const char *path) {
     }
     if (no_thread) {
         // no writer thread to be had: write in the caller, as the first save does
+        RL_CUDA(cudaStreamSynchronize(u->ss.stream));
         std::string err;
         if (!SaveWriter::write_file(path, host, 2 * n, err)) return fail(RL_ERR_IO, err);
         return RL_OK;

@@ -46,29 +46,23 @@ struct PrimTables {
     const float4 *spheres;
     const uint32_t *sphere_obj;
     uint32_t sphere_k, clusters, cluster_range, planes, paraboloids, leaves, compounds, ops;
+    uint32_t body_bounds, body_always;
     uint32_t plane_obj, paraboloid_obj, compound_obj;
     uint32_t scratch;         // per-block scratch behind the blob (see Scratch)
     uint32_t n_spheres, n_clusters, n_planes, n_paraboloids, n_compounds;
-    float sphere_cmax2, cluster_rmax, leaf_off_max;
-    uint32_t class_count[16];  // [parity][class] path counts of the block-wide path sort
+    float sphere_cmax2, cluster_rmax, leaf_off_max, body_rmax;
 };
 
 #define RL_TABLES_VEC4 ((sizeof(PrimTables) + 15) / 16)
-#define RL_PATH_CLASSES 6      // next actions a path can have (block-wide path sort)
-#define RL_PATH_WORDS 20       // words of path state that move in the sort
-#define RL_CLUSTER_SLOTS 16    // candidate clusters a lane queues privately per round
 #define RL_CAND_SLOTS 8        // queued sphere candidates per lane
 #define RL_COMPOUND_SLOTS 4    // body results per lane, and body tasks per thread of the block list
 #define RL_PAIR_CAP 768        // (lane, cluster) or (lane, body) pairs per warp and round
-#define RL_BODIES_PER_ROUND (RL_PAIR_CAP / 32)
-// scratch bytes per thread: ray table 48; one 32-byte area that is the private cluster queue,
-// then the sphere queue (sphere phase), then the body results (body phase); block task list 4 per
-// slot; three counters 12; pair list 2 * RL_PAIR_CAP / 32
+#define RL_BODIES_PER_ROUND 64  // bodies whose bounds one scan covers (one bit each of a lane's candidate mask)
+// scratch bytes per thread: ray table 48; one 32-byte area that is the sphere queue (sphere
+// phase), then the body results (body phase); block task list 4 per slot; three counters 12;
+// pair list 2 * RL_PAIR_CAP / 32
 #define RL_SCRATCH_BYTES_PER_THREAD (48 + 32 + 4 * RL_COMPOUND_SLOTS + 12 + 2 * RL_PAIR_CAP / 32)
-// the path sort of the trace kernel adds its own area behind the scratch: staging of the path
-// state and the permutation table
-#define RL_SORT_BYTES_PER_THREAD (4 * RL_PATH_WORDS + 2 * RL_PATH_CLASSES)
-static_assert(2 * RL_CLUSTER_SLOTS <= 32 && 2 * RL_CAND_SLOTS <= 32 && 8 * RL_COMPOUND_SLOTS <= 32, "shared 32-byte area");
+static_assert(2 * RL_CAND_SLOTS <= 32 && 8 * RL_COMPOUND_SLOTS <= 32, "shared 32-byte area");
 static_assert(RL_PAIR_INDEX_BITS + 5 <= 16, "a pair record is a lane (5 bits) and a table index in 16 bits");
 
 __device__ __forceinline__ const PrimTables &tables() {
@@ -95,6 +89,8 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         t.leaves = base + sc.off_leaves;
         t.compounds = base + sc.off_compounds;
         t.ops = base + sc.off_ops;
+        t.body_bounds = base + sc.off_body_bounds;
+        t.body_always = base + sc.off_body_always;
         t.plane_obj = base + sc.off_plane_obj;
         t.paraboloid_obj = base + sc.off_paraboloid_obj;
         t.compound_obj = base + sc.off_compound_obj;
@@ -107,6 +103,7 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         t.sphere_cmax2 = sc.sphere_cmax2;
         t.cluster_rmax = sc.cluster_rmax;
         t.leaf_off_max = sc.leaf_off_max;
+        t.body_rmax = sc.body_rmax;
         *reinterpret_cast<PrimTables *>(rl_smem) = t;
     }
     // zero the scratch counters (same layout as in intersect_scene)
@@ -116,20 +113,8 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         uint32_t *counters = reinterpret_cast<uint32_t *>(results + RL_COMPOUND_SLOTS * blockDim.x)
                              + RL_COMPOUND_SLOTS * blockDim.x;
         for (uint32_t k = threadIdx.x; k < 3 * blockDim.x; k += blockDim.x) counters[k] = 0u;
-        if (threadIdx.x < 16) const_cast<uint32_t *>(tables().class_count)[threadIdx.x] = 0u;
     }
     __syncthreads();
-}
-
-// The block's photon pool counter (trace_kernel): the second word of the third
-// scratch counter array, whose first word is the task-list length and whose
-// other words are unused (blocks have at least 128 threads).
-__device__ __forceinline__ uint32_t *photon_pool() {
-    float4 *ray_tab = rl_smem + tables().scratch;
-    float2 *results = reinterpret_cast<float2 *>(ray_tab + 3 * blockDim.x);
-    uint32_t *counters = reinterpret_cast<uint32_t *>(results + RL_COMPOUND_SLOTS * blockDim.x)
-                         + RL_COMPOUND_SLOTS * blockDim.x;
-    return counters + 2 * blockDim.x + 1;
 }
 
 // Shared memory a tracing kernel needs with `threads` threads per block.
@@ -238,50 +223,6 @@ __device__ __forceinline__ Ray idle_ray() {
     return r;
 }
 
-// --------------------------------------------------------- path sort by class
-// Optional (RL_SORT_PATHS): per bounce, the paths of a block are re-dealt to its
-// threads in the order of what happens to them next, so that a warp executes
-// one or two of the material code paths instead of all of them.  A path is just
-// its state: 20 words move through shared memory.  One barrier per sort: every
-// warp reserves a run in each class with one shared-memory atomic per class, the
-// threads publish "the path parked by thread tid is number k of class c" in a
-// permutation table; after the barrier thread j works out from the six class
-// totals which (class, k) it serves and fetches that path.  The counters are
-// double-buffered by iteration parity and zeroed one iteration ahead.
-#define RL_CLASS_MISS 0u
-#define RL_CLASS_EMITTER 1u
-#define RL_CLASS_DIFFUSE 2u
-#define RL_CLASS_GLASS 3u
-#define RL_CLASS_SOAP 4u
-#define RL_CLASS_IDLE 5u
-
-__device__ __forceinline__ void path_sort_publish(uint32_t cls, uint32_t parity, uint16_t *perm) {
-    uint32_t *count = const_cast<uint32_t *>(tables().class_count) + 8 * parity;
-    const uint32_t lane = threadIdx.x & 31u, lanes_below = (1u << lane) - 1u;
-    uint32_t rank = 0, run = 0;
-#pragma unroll
-    for (uint32_t c = 0; c < RL_PATH_CLASSES; c++) {
-        const uint32_t mask = __ballot_sync(0xffffffffu, cls == c);
-        if (lane == c && mask) run = atomicAdd(&count[c], (uint32_t)__popc(mask));
-        if (cls == c) rank = __popc(mask & lanes_below);
-    }
-    run = __shfl_sync(0xffffffffu, run, cls);
-    perm[cls * blockDim.x + run + rank] = (uint16_t)threadIdx.x;
-}
-// After the barrier: the thread whose parked path this thread takes over, and that path's class.
-__device__ __forceinline__ uint32_t path_sort_fetch(uint32_t parity, const uint16_t *perm, uint32_t &cls_out) {
-    uint32_t *count = const_cast<uint32_t *>(tables().class_count);
-    uint32_t k = threadIdx.x, cls = 0;
-#pragma unroll
-    for (uint32_t c = 0; c < RL_PATH_CLASSES - 1; c++) {
-        const uint32_t n = count[8 * parity + c];
-        if (cls == c && k >= n) { k -= n; cls = c + 1; }
-    }
-    if (threadIdx.x < RL_PATH_CLASSES) count[8 * (parity ^ 1u) + threadIdx.x] = 0u;   // for the next iteration
-    cls_out = cls;
-    return perm[cls * blockDim.x + k];
-}
-
 // ------------------------------------------------------------------- camera
 // app.rs:327-357 (make_camera) in closed form, camera.rs:94-108 + :47-90.
 __device__ __forceinline__ Ray camera_ray(const DevCamera &cm, float x, float y, float wavelength, float t,
@@ -307,8 +248,9 @@ __device__ __forceinline__ Ray camera_ray(const DevCamera &cm, float x, float y,
     const float dof_radius = rng.unit(key) / cm.depth_of_field;
     const float d = (wavelength - 580.0f) / 200.0f;
     const float chromatic_zoom = 1.0f + d * cm.chromatic_abberation;
-    const float2 fov = sincos_call(cm.field_of_view * 0.5f);
-    const float screen_distance = 1.0f / (fov.x / fov.y);              // 1 / tan, spec_tan = sin / cos
+    // camera.rs:60: 1 / tan(fov / 2) is a constant of the scene, evaluated once on the host with the
+    // same specified functions (rl_api.cu, dev_camera)
+    const float screen_distance = cm.screen_distance;
     const float xs = x * chromatic_zoom;
     const float ys = y * chromatic_zoom;
     const V3 direction = normalise_dev(mk(xs, screen_distance, -ys));
@@ -514,6 +456,62 @@ __device__ __forceinline__ Hit intersect_scene_brute(const Ray &ray) {
     return best;
 }
 
+// Uniform scan of `count` bounding-sphere records {m, |m|^2 - R^2} (count a multiple of 8, at most
+// 64; tables are padded with records no ray selects): bit k of the result is set iff the sphere
+// pre-test keeps record k for this lane's ray -- 8 fused operations, two compares and one
+// predicated OR per record, the candidates of a lane stay in two registers.
+__device__ __forceinline__ uint64_t scan_bounds(const float4 *tab, uint32_t count, V3 d, float ndo, float m2ox,
+                                                float m2oy, float m2oz, float oo, float thr, float bthr) {
+    uint64_t mask = 0ull;
+#pragma unroll 1
+    for (uint32_t g = 0; g < count; g += 8) {
+        uint32_t m8 = 0u;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++) {
+            const float4 s = tab[g + j];
+            const float b = fmaf(d.x, s.x, fmaf(d.y, s.y, fmaf(d.z, s.z, ndo)));
+            const float c = fmaf(m2ox, s.x, fmaf(m2oy, s.y, fmaf(m2oz, s.z, s.w))) + oo;
+            const float disc = fmaf(b, b, -c);
+            if (disc >= thr && b >= bthr) m8 |= 1u << j;
+        }
+        mask |= (uint64_t)m8 << g;
+    }
+    return mask;
+}
+
+// Lists the warp's candidates as (lane, base + bit) records in `pairs` (RL_PAIR_CAP entries) and
+// clears the listed bits of `todo`; returns the number of records (warp-uniform).  When the
+// warp's candidates do not fit, only a window of 24 bit positions is listed (at most 24 x 32
+// records) and the caller comes back for the rest.
+__device__ __forceinline__ uint32_t emit_pairs(uint64_t &todo, uint32_t base, uint16_t *pairs, uint32_t lane) {
+    uint64_t take = todo;
+    uint32_t cnt = (uint32_t)__popcll(take);
+    uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
+    if (total > RL_PAIR_CAP) {                                      // warp-uniform
+        const uint32_t low = __reduce_min_sync(0xffffffffu, take ? (uint32_t)__ffsll((long long)take) - 1u : 64u);
+        take &= 0xffffffull << low;
+        cnt = (uint32_t)__popcll(take);
+        total = __reduce_add_sync(0xffffffffu, cnt);
+    }
+    todo &= ~take;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (uint32_t sh = 1; sh < 32; sh <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, sh);
+        if (lane >= sh) incl += v;
+    }
+    uint16_t *dst = pairs + (incl - cnt);
+    const uint32_t tag = (lane << RL_PAIR_INDEX_BITS) | base;       // base is a multiple of 64: OR = add
+#pragma unroll 1
+    while (take) {
+        const uint32_t bit = (uint32_t)__ffsll((long long)take) - 1u;
+        take &= take - 1ull;
+        *dst++ = (uint16_t)(tag | bit);
+    }
+    __syncwarp();
+    return total;
+}
+
 // Conservative slab test of a convex body against the ray, with every
 // half-space moved outwards by RL_SLAB_INFLATE (evaluated eight lanes per body
 // inside intersect_scene).  A hit the reference returns lies on one leaf plane
@@ -613,7 +611,8 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
     // (rounding of the reference's discriminant, and its use of B^2 - C for a direction that
     // is only unit to rounding), hence dist(line, m) <= R + sqrt(S/2) and
     // R^2 - dist(line, m)^2 >= -(2 R sqrt(S/2) + S/2); B_cluster >= B_i - |d| R.
-    // Kept (lane, cluster) pairs are compacted with a ballot into one list per warp.
+    // A lane's candidates are bits of a register (scan_bounds); the warp's (lane, cluster) pairs
+    // are then listed in shared memory (emit_pairs).
     const float4 *spheres = tb.spheres;
     const float4 *sphere_k = sm_vec(tb.sphere_k);
     const float4 *clusters = sm_vec(tb.clusters);
@@ -623,92 +622,69 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
     const float slack = -2.0f * thr + 2.0f * fabsf(dd - 1.0f) * (tb.sphere_cmax2 + oo);
     const float thr_c = -(2.0f * tb.cluster_rmax * sqrtf(slack) + 2.0f * slack);
     const float bthr_c = bthr - sqrtf(dd) * tb.cluster_rmax;
-    const uint32_t lanes_below = (1u << lane) - 1u;
-    uint16_t *myq = lq_base + tid;                              // private cluster queue, slot k at myq[k * nthreads]
     const bool warp_live = __any_sync(0xffffffffu, live);       // warp-uniform
-    uint32_t i = warp_live ? 0u : n_clusters;
-    if (warp_live) do {
-        // each lane queues its candidate clusters privately (three predicated instructions per
-        // cluster), until any queue could overflow
-        uint32_t mine = 0;
-        for (; i < n_clusters; i += 4) {
-#pragma unroll
-            for (uint32_t j = 0; j < 4; j++) {
-                // the table is padded with never-selected records to a multiple of four
-                const float4 s = clusters[i + j];               // {mx, my, mz, |m|^2 - R^2}
-                const float b = fmaf(d.x, s.x, fmaf(d.y, s.y, fmaf(d.z, s.z, ndo)));
-                const float c = fmaf(m2ox, s.x, fmaf(m2oy, s.y, fmaf(m2oz, s.z, s.w))) + oo;
-                const float disc = fmaf(b, b, -c);
-                if (disc >= thr_c && b >= bthr_c) {
-                    myq[mine * nthreads] = (uint16_t)(i + j);
-                    mine++;
-                }
-            }
-            if (__any_sync(0xffffffffu, mine > RL_CLUSTER_SLOTS - 4)) { i += 4; break; }
-        }
-        // the queues are compacted into one (lane, cluster) list per warp: prefix sum of the counts
-        uint32_t incl = mine;
-#pragma unroll
-        for (uint32_t sh = 1; sh < 32; sh <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, sh);
-            if (lane >= sh) incl += v;
-        }
-        const uint32_t npairs = __shfl_sync(0xffffffffu, incl, 31);    // warp-uniform
-        uint16_t *dst = pairs + (incl - mine);
 #pragma unroll 1
-        for (uint32_t k = 0; k < mine; k++) dst[k] = (uint16_t)((lane << RL_PAIR_INDEX_BITS) | myq[k * nthreads]);
-        __syncwarp();
-        // Level 2, warp-cooperative: eight lanes take one (lane, cluster) pair and test one
-        // member each with the owner's constants, so the work of lanes with many candidate
-        // clusters is spread over the warp; survivors go to the owner's sphere queue.
+    for (uint32_t base = 0; warp_live && base < n_clusters; base += 64) {
+        uint64_t todo = scan_bounds(clusters + base, min(64u, n_clusters - base), d, ndo, m2ox, m2oy, m2oz, oo,
+                                    thr_c, bthr_c);
+        while (__any_sync(0xffffffffu, todo != 0ull)) {
+            const uint32_t npairs = emit_pairs(todo, base, pairs, lane);
+            // Level 2, warp-cooperative: eight lanes take one (lane, cluster) pair and test one
+            // member each with the owner's constants, so the work of lanes with many candidate
+            // clusters is spread over the warp; survivors go to the owner's sphere queue.
 #pragma unroll 1
-        for (uint32_t pb = 0; pb < npairs; pb += 4) {
-            const uint32_t p = pb + (lane >> 3);
-            if (p < npairs) {
-                const uint32_t pair = pairs[p];
-                const uint32_t owner = wbase + (pair >> RL_PAIR_INDEX_BITS);
-                const uint32_t r = cluster_range[pair & RL_PAIR_INDEX_MAX];
-                const uint32_t end = (r & 0xffffu) + (r >> 16);
-                const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1], rt = ray_tab[3 * owner + 2];
+            for (uint32_t pb = 0; pb < npairs; pb += 4) {
+                const uint32_t p = pb + (lane >> 3);
+                if (p < npairs) {
+                    const uint32_t pair = pairs[p];
+                    const uint32_t owner = wbase + (pair >> RL_PAIR_INDEX_BITS);
+                    const uint32_t r = cluster_range[pair & RL_PAIR_INDEX_MAX];
+                    const uint32_t end = (r & 0xffffu) + (r >> 16);
+                    const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1], rt = ray_tab[3 * owner + 2];
 #pragma unroll 1
-                for (uint32_t m = (r & 0xffffu) + (lane & 7u); m < end; m += 8) {
-                    const float4 s = sphere_k[m];               // {cx, cy, cz, |c|^2 - r^2}
-                    const float b = fmaf(rd.x, s.x, fmaf(rd.y, s.y, fmaf(rd.z, s.z, rd.w)));
-                    const float c = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w))) + ro.w;
-                    const float disc = fmaf(b, b, -c);
-                    if (disc >= rt.x && b >= rt.y) {
-                        const uint32_t slot = atomicAdd(&sq_cnt[owner], 1u);
-                        if (slot < RL_CAND_SLOTS) sq_base[slot * nthreads + owner] = (uint16_t)m;
+                    for (uint32_t m = (r & 0xffffu) + (lane & 7u); m < end; m += 8) {
+                        const float4 s = sphere_k[m];               // {cx, cy, cz, |c|^2 - r^2}
+                        const float b = fmaf(rd.x, s.x, fmaf(rd.y, s.y, fmaf(rd.z, s.z, rd.w)));
+                        const float c = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w))) + ro.w;
+                        const float disc = fmaf(b, b, -c);
+                        if (disc >= rt.x && b >= rt.y) {
+                            const uint32_t slot = atomicAdd(&sq_cnt[owner], 1u);
+                            if (slot < RL_CAND_SLOTS) sq_base[slot * nthreads + owner] = (uint16_t)m;
+                        }
                     }
                 }
             }
-        }
-        __syncwarp();
-        // Level 3, per lane: exact Sphere::intersect for the candidates queued for this lane
-        const uint32_t cnt = sq_cnt[tid];
-        if (cnt > RL_CAND_SLOTS) {
-            // more candidates than slots (pathological): evaluate every sphere exactly
+            __syncwarp();
+            // Level 3, per lane: exact Sphere::intersect for the candidates queued for this lane
+            const uint32_t cnt = sq_cnt[tid];
+            if (cnt > RL_CAND_SLOTS) {
+                // more candidates than slots (pathological): evaluate every sphere exactly
 #pragma unroll 1
-            for (uint32_t k = 0; k < tb.n_spheres; k++) {
-                const float t = sphere_t(__ldg(spheres + k), ray);
-                if (t > 0.0f) consider(best, t, (int)__ldg(sphere_obj + k), (RL_HIT_SPHERE << 28) | k);
-            }
-        } else {
+                for (uint32_t k = 0; k < tb.n_spheres; k++) {
+                    const float t = sphere_t(__ldg(spheres + k), ray);
+                    if (t > 0.0f) consider(best, t, (int)__ldg(sphere_obj + k), (RL_HIT_SPHERE << 28) | k);
+                }
+            } else {
 #pragma unroll 1
-            for (uint32_t k = 0; k < cnt; k++) {
-                const uint32_t idx = sq_base[k * nthreads + tid];
-                const float t = sphere_t(__ldg(spheres + idx), ray);
-                if (t > 0.0f) consider(best, t, (int)__ldg(sphere_obj + idx), (RL_HIT_SPHERE << 28) | idx);
+                for (uint32_t k = 0; k < cnt; k++) {
+                    const uint32_t idx = sq_base[k * nthreads + tid];
+                    const float t = sphere_t(__ldg(spheres + idx), ray);
+                    if (t > 0.0f) consider(best, t, (int)__ldg(sphere_obj + idx), (RL_HIT_SPHERE << 28) | idx);
+                }
             }
+            sq_cnt[tid] = 0u;
+            __syncwarp();
         }
-        sq_cnt[tid] = 0u;
-        __syncwarp();
-    } while (__any_sync(0xffffffffu, i < n_clusters));
+    }
 
     if (warp_live) intersect_flat_surfaces(tb, ray, best);
 
     // Compound bodies (block-wide; every thread of the block calls intersect_scene together).
-    //  1. bounding-sphere test in a uniform loop, kept (lane, body) pairs compacted with a ballot;
+    //  1. bounding spheres: the same uniform scan over the bodies' bound records; a hit the
+    //     reference returns lies inside the (host-inflated) bound, so the line passes it:
+    //     exactly B^2 - dd C >= 0, and the evaluated B'^2 - C' can fall short of that by the
+    //     rounding of both (e1) and by |dd - 1| |C| only: threshold -slack; B >= -|d| R.
+    //     Unbounded bodies are flagged in a mask that is OR-ed in;
     //  2. slab test warp-cooperatively: eight lanes per pair, one leaf each, shuffle reduction of
     //     the interval; survivors are appended to ONE task list per block;
     //  3. after a block barrier the threads take one task each -- the reference's recursion
@@ -717,35 +693,23 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
     //  4. after a second barrier every thread merges the results computed for its ray.
     ray_tab[3 * tid + 2].z = best.t;                            // nearest hit so far: bodies beyond it are skipped
     const float4 *compounds = sm_vec(tb.compounds);
+    const float4 *body_bounds = sm_vec(tb.body_bounds);
+    const uint64_t *body_always = reinterpret_cast<const uint64_t *>(rl_smem + tb.body_always);
     const float4 *leaves = sm_vec(tb.leaves);
     const uint32_t *compound_obj = sm_u32(tb.compound_obj);
     const uint32_t n_compounds = tb.n_compounds;
     const uint32_t group = lane >> 3, sub = lane & 7u;
     const uint32_t task_cap = RL_COMPOUND_SLOTS * nthreads;
+    const float thr_b = -slack;
+    const float bthr_b = bthr - sqrtf(dd) * tb.body_rmax;
     for (uint32_t round = 0; round < n_compounds; round += RL_BODIES_PER_ROUND) {   // block-uniform trip count
         const uint32_t round_end = min(round + RL_BODIES_PER_ROUND, n_compounds);
-        uint32_t npairs = 0;                                    // warp-uniform
-#pragma unroll 1
-        for (uint32_t i = warp_live ? round : round_end; i < round_end; i++) {
-            const float4 b4 = compounds[2 * i + 1];             // bounding sphere {c, r^2}
-            bool keep = true;
-            if (b4.w >= 0.0f) {
-                const float cx = b4.x - o.x, cy = b4.y - o.y, cz = b4.z - o.z;
-                const float bq = fmaf(cz, cz, fmaf(cy, cy, cx * cx));
-                const float bb = fmaf(d.z, cz, fmaf(d.y, cy, d.x * cx));
-                const float bc = bq - b4.w;                     // > 0: origin outside the bound
-                // both tests leave room for their own rounding (16 eps of the largest term), so
-                // that a ray far from the body is kept rather than culled on noise
-                const float noise = 9.5367432e-7f * bq;
-                const bool behind = bc > noise && bb < 0.0f;
-                const bool misses = fmaf(bb, bb, -(bc * dd)) < -(noise * dd);
-                keep = !(behind || misses);
-            }
-            const uint32_t mask = __ballot_sync(0xffffffffu, keep);
-            if (keep) pairs[npairs + __popc(mask & lanes_below)] = (uint16_t)((lane << RL_PAIR_INDEX_BITS) | i);
-            npairs += __popc(mask);
-        }
-        __syncwarp();
+        uint64_t todo = 0ull;
+        if (warp_live)
+            todo = scan_bounds(body_bounds + round, (round_end - round + 7u) & ~7u, d, ndo, m2ox, m2oy, m2oz, oo,
+                               thr_b, bthr_b) | body_always[round / RL_BODIES_PER_ROUND];
+        while (__any_sync(0xffffffffu, todo != 0ull)) {
+        const uint32_t npairs = emit_pairs(todo, round, pairs, lane);
 #pragma unroll 1
         for (uint32_t pb = 0; pb < npairs; pb += 4) {
             const uint32_t p = pb + group;
@@ -785,6 +749,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
                 if (slot < task_cap) btasks[slot] = (owner << 16) | body;
                 else atomicAdd(&res_cnt[owner], RL_COMPOUND_SLOTS + 1u);   // no room: the owner evaluates every body
             }
+        }
         }
         __syncthreads();
         const uint32_t ntasks = min(*bcount, task_cap);

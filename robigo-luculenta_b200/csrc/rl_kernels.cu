@@ -24,8 +24,8 @@ void kernel_launches_reset() { g_launches.store(0); }
 #ifndef RL_TRACE_THREADS
 #define RL_TRACE_THREADS 768
 #endif
-#ifndef RL_SORT_PATHS
-#define RL_SORT_PATHS 0          // 1: re-deal the paths of a CTA by next action every bounce (see rl_device.cuh)
+#ifndef RL_RING_STATE_SMEM
+#define RL_RING_STATE_SMEM 0     // 1: the camera-ray ring counters live in shared memory; 0: in registers of every thread (2963 vs 2916 Mrays/s)
 #endif
 #ifndef RL_TRACE_MIN_BLOCKS
 #define RL_TRACE_MIN_BLOCKS 1
@@ -40,409 +40,179 @@ void kernel_launches_reset() { g_launches.store(0); }
 #endif
 
 // ------------------------------------------------------------------ K1 trace
+// One launch traces up to RL_MAX_SEGMENTS batches ("segments": the photon ranges of several
+// TraceUnit::render calls on one scene and canvas, rl_api.cu groups them) as one pool of photons.
 struct TraceArgs {
-    uint64_t seed;
-    uint64_t first_photon;
-    uint64_t n_photons;
+    uint32_t n_seg;
+    uint32_t seg_shift;        // a path remembers its photon as (segment << seg_shift) | index within the segment
+    uint32_t ring_cap;         // camera-ray ring entries per CTA (a power of two)
     int width, height;
     float aspect;
-    rl_mapped_photon *records;
     float4 *accum;
-    unsigned long long *ray_counter;
+    TraceSegment seg[RL_MAX_SEGMENTS];
 };
 
-// Persistent threads with path regeneration: a block owns a contiguous range
-// of the launch's photons and hands them out from a counter in shared memory
-// (one warp-aggregated atomic per warp and iteration); a lane takes its next
-// photon the moment its current path ends, so a warp never idles on its longest
-// path and no lane idles while the block's pool is not empty -- with the
-// reference's 524 288-photon batches a thread sees only a handful of paths and
-// a static deal would leave most lanes waiting for the unluckiest one.  The
-// result of a photon depends on its id alone, so the deal changes nothing but
-// the order of the accumulator atomics.  The primitive tables live in shared
-// memory; each loop iteration is one Scene::intersect plus one material
-// interaction for every live lane.
+// Per-CTA bookkeeping in shared memory, behind the intersection scratch; the camera-ray ring
+// (ring_cap entries of three float4) follows it.
+struct TraceCta {
+    uint64_t seed[RL_MAX_SEGMENTS];
+    uint64_t first_photon[RL_MAX_SEGMENTS];
+    rl_mapped_photon *records[RL_MAX_SEGMENTS];
+    uint32_t seg_start[RL_MAX_SEGMENTS + 1];   // first index of each segment in the launch's concatenated photon range
+    uint32_t seg_rays[RL_MAX_SEGMENTS];        // Scene::intersect calls of the paths this CTA finished, per segment
+    uint32_t warp_dead[2][32];                 // lanes without a path, per warp (double-buffered by iteration parity)
+    // the ring: entries handed out / produced so far, next photon to generate, end of the block's
+    // range.  Double-buffered like warp_dead: every thread reads [parity] behind the loop's
+    // barrier, thread 0 writes [parity ^ 1] for the next iteration.
+    uint4 ring_state[2];
+    uint32_t pad[3];
+};
+// behind TraceCta: the screen position of every thread's current photon (float2 per thread; only
+// read again when the path ends), then the camera-ray ring
+#define RL_TRACE_PARK_BYTES_PER_THREAD 8
+static_assert(sizeof(TraceCta) % 16 == 0, "the ring behind TraceCta holds float4");
+
+__device__ __forceinline__ TraceCta *trace_cta(const DevScene &sc) {
+    char *base = reinterpret_cast<char *>(rl_smem + RL_TABLES_VEC4 + sc.smem_vec4);
+    return reinterpret_cast<TraceCta *>(base + (size_t)RL_SCRATCH_BYTES_PER_THREAD * blockDim.x);
+}
+
+// trace_unit.rs:151-158 and :136-145 for the photon at index `gidx` of the launch: the draws of
+// the wavelength, the screen position and the time, and the camera ray (which draws the lens
+// sample).  Six draws: the second Philox block is half used, its other two words travel with the
+// entry.
+__device__ __forceinline__ void generate_camera_entry(const DevScene &sc, const TraceArgs &a, const TraceCta *cta,
+                                                      float4 *entry, uint32_t gidx) {
+    uint32_t seg = 0;
+    while (seg + 1 < a.n_seg && gidx >= cta->seg_start[seg + 1]) seg++;
+    const uint32_t local = gidx - cta->seg_start[seg];
+    const RngKey key = {cta->seed[seg], cta->first_photon[seg] + local};
+    Rng rng;
+    rng.init();
+    const float wavelength = rng.wavelength(key);
+    const float sx = rng.bi_unit(key);
+    const float sy = rng.bi_unit(key) / a.aspect;
+    const float t = rng.unit(key);
+    const Ray ray = camera_ray(sc.camera, sx, sy, wavelength, t, rng, key);
+    entry[0] = make_float4(ray.origin.x, ray.origin.y, ray.origin.z, ray.direction.x);
+    entry[1] = make_float4(ray.direction.y, ray.direction.z, wavelength, sx);
+    entry[2] = make_float4(sy, __uint_as_float(rng.b0), __uint_as_float(rng.b1),
+                           __uint_as_float((seg << a.seg_shift) | local));
+}
+
+// Persistent threads with path regeneration.  A block owns a contiguous range of the launch's
+// photons.  Camera rays are produced in bulk: whenever the block's ring of ready camera rays
+// cannot serve the lanes whose paths have just ended, EVERY thread of the block generates one
+// (the RNG draws, three sines and cosines, two normalisations and two quaternion rotations of
+// trace_unit.rs:136-145 / camera.rs:47-108 run with full warps instead of for the two lanes in
+// seven that need a new path in a given iteration), and a lane takes its next photon from the ring
+// the moment the path it holds ends -- so a warp never idles on its longest path (1 ... ~150
+// bounces) and no lane idles while the block has photons left.  The result of a photon depends on
+// its id alone, so the deal changes nothing but the order of the accumulator atomics.  The
+// primitive tables live in shared memory; each loop iteration is one Scene::intersect plus one
+// material interaction for every live lane.
 __global__ void __launch_bounds__(RL_TRACE_THREADS, RL_TRACE_MIN_BLOCKS)
 trace_kernel(const DevScene sc, const TraceArgs a) {
     setup_tables(sc);
-
-    // photon indices within the launch fit 32 bits (launch_trace splits larger requests)
-    const uint32_t pool_end = (uint32_t)(a.n_photons * (blockIdx.x + 1ull) / gridDim.x);
-    uint32_t *pool = photon_pool();
-    if (threadIdx.x == 0) *pool = (uint32_t)(a.n_photons * (uint64_t)blockIdx.x / gridDim.x);
+    TraceCta *cta = trace_cta(sc);
+    float2 *park = reinterpret_cast<float2 *>(cta + 1) + threadIdx.x;
+    float4 *ring = reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(cta + 1) + ((blockDim.x + 1u) & ~1u));
+    if (threadIdx.x < RL_MAX_SEGMENTS) {
+        const uint32_t k = threadIdx.x;
+        cta->seg_rays[k] = 0u;
+        if (k < a.n_seg) {
+            cta->seed[k] = a.seg[k].seed;
+            cta->first_photon[k] = a.seg[k].first_photon;
+            cta->records[k] = a.seg[k].records;
+        }
+    }
+    if (threadIdx.x == 0) {
+        uint32_t at = 0;
+        for (uint32_t k = 0; k < a.n_seg; k++) { cta->seg_start[k] = at; at += (uint32_t)a.seg[k].n_photons; }
+        cta->seg_start[a.n_seg] = at;
+    }
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u;
-    bool pool_empty = false;
+
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t parity = 0;
+#if RL_RING_STATE_SMEM
+    if (threadIdx.x == 0) {
+        const uint32_t total = cta->seg_start[a.n_seg];
+        cta->ring_state[0] = make_uint4(0u, 0u, (uint32_t)((uint64_t)total * blockIdx.x / gridDim.x),
+                                        (uint32_t)((uint64_t)total * (blockIdx.x + 1ull) / gridDim.x));
+    }
+    // (the loop's first barrier publishes it)
+#else
+    // the same, kept by every thread in registers
+    uint4 ring_regs = make_uint4(0u, 0u, (uint32_t)((uint64_t)cta->seg_start[a.n_seg] * blockIdx.x / gridDim.x),
+                                 (uint32_t)((uint64_t)cta->seg_start[a.n_seg] * (blockIdx.x + 1ull) / gridDim.x));
+#endif
 
     bool alive = false;
-    uint32_t cur = 0;
+    uint32_t cur = 0;                                               // (segment << seg_shift) | photon index in it
     Ray ray;
     ray.origin = mk(0.f, 0.f, 0.f); ray.direction = mk(0.f, 0.f, 0.f); ray.wavelength = 0.f;
-    float sx = 0.f, sy = 0.f;
     float intensity = 1.0f, continue_chance = 1.0f;
     Rng rng;
     rng.init();
-    uint32_t rays = 0;
-#if RL_SORT_PATHS
-    // staging of the path exchange and the permutation table, behind the intersection scratch
-    uint32_t *stage = reinterpret_cast<uint32_t *>(
-        reinterpret_cast<char *>(rl_smem + tables().scratch) + (size_t)RL_SCRATCH_BYTES_PER_THREAD * blockDim.x);
-    uint16_t *perm = reinterpret_cast<uint16_t *>(stage + RL_PATH_WORDS * blockDim.x);
-    uint32_t parity = 0;
-#endif
+    uint32_t rays = 0;                                              // of the current path
 
     for (;;) {
-        // lanes without a path draw the next photon ids of the block's pool; a warp that has seen
-        // the pool empty never touches the counter again, so it overshoots the end by at most
-        // 32 per warp and cannot wrap
-        uint32_t mine = 0xffffffffu;
-        if (!pool_empty) {
-            const uint32_t want = __ballot_sync(0xffffffffu, !alive);
-            if (want != 0u) {
-                const uint32_t leader = __ffs(want) - 1u;
-                uint32_t base = 0;
-                if (lane == leader) base = atomicAdd(pool, (uint32_t)__popc(want));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (!alive) mine = base + __popc(want & ((1u << lane) - 1u));
-                pool_empty = base + (uint32_t)__popc(want) >= pool_end;      // warp-uniform
-            }
-        }
-        if (mine < pool_end) {
-            // trace_unit.rs:151-158 and :136-145
-            cur = mine;
-            const RngKey key = {a.seed, a.first_photon + cur};
-            rng.init();
-            const float wavelength = rng.wavelength(key);
-            sx = rng.bi_unit(key);
-            sy = rng.bi_unit(key) / a.aspect;
-            const float t = rng.unit(key);
-            ray = camera_ray(sc.camera, sx, sy, wavelength, t, rng, key);
-            intensity = 1.0f;
-            continue_chance = 1.0f;
-            alive = true;
-        }
-        // every thread of the block takes part in the intersection (block barriers and warp
-        // votes inside); idle lanes trace a ray that hits nothing
-        if (!__syncthreads_or(alive)) break;
-        Hit hit = intersect_scene(alive ? ray : idle_ray(), alive);
-        if (alive) rays++;                                              // Scene::intersect calls (scene.rs:39)
-#if RL_SORT_PATHS
-        {
-            uint32_t cls = RL_CLASS_IDLE;
-            if (alive) {
-                cls = RL_CLASS_MISS;
-                if (hit.obj >= 0) {
-                    const uint32_t kind = __float_as_uint(__ldg(sc.materials + hit.obj).x);
-                    cls = kind == RL_MATERIAL_BLACKBODY ? RL_CLASS_EMITTER
-                          : (kind <= RL_MATERIAL_GLOSSY_MIRROR ? RL_CLASS_DIFFUSE
-                             : (kind == RL_MATERIAL_SF10_GLASS ? RL_CLASS_GLASS : RL_CLASS_SOAP));
-                }
-            }
-            path_sort_publish(cls, parity, perm);
-            const uint32_t T = blockDim.x;
-            uint32_t *p = stage + threadIdx.x;
-            p[0 * T] = __float_as_uint(ray.origin.x); p[1 * T] = __float_as_uint(ray.origin.y);
-            p[2 * T] = __float_as_uint(ray.origin.z); p[3 * T] = __float_as_uint(ray.direction.x);
-            p[4 * T] = __float_as_uint(ray.direction.y); p[5 * T] = __float_as_uint(ray.direction.z);
-            p[6 * T] = __float_as_uint(ray.wavelength); p[7 * T] = __float_as_uint(intensity);
-            p[8 * T] = __float_as_uint(continue_chance); p[9 * T] = __float_as_uint(sx);
-            p[10 * T] = __float_as_uint(sy); p[11 * T] = cur;
-            p[12 * T] = (rng.block << 3) | rng.left;
-            p[13 * T] = rng.b0; p[14 * T] = rng.b1; p[15 * T] = rng.b2;
-            p[16 * T] = __float_as_uint(hit.t); p[17 * T] = (uint32_t)hit.obj; p[18 * T] = hit.code;
-            __syncthreads();
-            p = stage + path_sort_fetch(parity, perm, cls);
-            parity ^= 1u;
-            ray.origin = mk(__uint_as_float(p[0 * T]), __uint_as_float(p[1 * T]), __uint_as_float(p[2 * T]));
-            ray.direction = mk(__uint_as_float(p[3 * T]), __uint_as_float(p[4 * T]), __uint_as_float(p[5 * T]));
-            ray.wavelength = __uint_as_float(p[6 * T]); intensity = __uint_as_float(p[7 * T]);
-            continue_chance = __uint_as_float(p[8 * T]); sx = __uint_as_float(p[9 * T]);
-            sy = __uint_as_float(p[10 * T]); cur = p[11 * T];
-            rng.block = p[12 * T] >> 3; rng.left = p[12 * T] & 7u;
-            rng.b0 = p[13 * T]; rng.b1 = p[14 * T]; rng.b2 = p[15 * T];
-            hit.t = __uint_as_float(p[16 * T]); hit.obj = (int)p[17 * T]; hit.code = p[18 * T];
-            alive = cls != RL_CLASS_IDLE;
-            // the staging area is written again only behind the next loop-top barrier
-        }
+        // lanes without a path, per warp and in the block; every thread of the block takes part in
+        // the intersection (block barriers and warp votes inside), and this barrier also
+        // separates two calls of it
+        const uint32_t want = __ballot_sync(0xffffffffu, !alive);
+        if (lane == 0) cta->warp_dead[parity][warp] = (uint32_t)__popc(want);
+        const uint32_t dead = (uint32_t)__syncthreads_count(!alive);
+        const uint32_t T = blockDim.x, cap_mask = a.ring_cap - 1u;
+#if RL_RING_STATE_SMEM
+        const uint4 rs = cta->ring_state[parity];                   // {head, tail, gen_next, gen_end}: block-uniform
+#else
+        const uint4 rs = ring_regs;
 #endif
-        if (alive) {
-            // trace_unit.rs:91-131
-            bool done = false;
-            float result = 0.0f;
-            if (hit.obj < 0) {
-                done = true;                                            // trace_unit.rs:94
-            } else {
-                const float4 m = __ldg(sc.materials + hit.obj);
-                if (__float_as_uint(m.x) == RL_MATERIAL_BLACKBODY) {
-                    result = intensity * blackbody_intensity(m, ray.wavelength);  // :99-101
-                    done = true;
-                } else {
-                    const Surf s = surface_at(ray, hit);
-                    const RngKey key = {a.seed, a.first_photon + cur};
-                    float probability;
-                    const V3 dir = material_bounce(m, ray, hit, s, rng, key, probability);  // :104-107
-                    intensity = intensity * probability;
-                    ray.direction = dir;
-                    ray.origin = s.position + dir * 0.00001f;                      // :114
-                    continue_chance = continue_chance * 0.96f;                    // :117
-                    if (rng.unit(key) * 0.85f
-                        > continue_chance * (1.0f - spec_exp(intensity * -20.0f)))  // :122-125
-                        done = true;
-                }
-            }
-            if (done) {
-                if (a.records) {
-                    rl_mapped_photon ph;
-                    ph.x = sx; ph.y = sy; ph.probability = result; ph.wavelength = ray.wavelength;
-                    *reinterpret_cast<float4 *>(a.records + cur) =
-                        make_float4(ph.x, ph.y, ph.probability, ph.wavelength);
-                }
-                // adding cie * 0 leaves the accumulator unchanged (plot_unit.rs:80-83)
-                if (a.accum && result != 0.0f)
-                    splat_photon(a.accum, a.width, a.height, a.aspect, sx, sy, ray.wavelength, result);
-                alive = false;
-            }
-        }
-    }
-
-    // rays traced = Scene::intersect calls (scene.rs:39)
-    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
-    if ((threadIdx.x & 31) == 0 && a.ray_counter) atomicAdd(a.ray_counter, (unsigned long long)rays);
-}
-
-// --------------------------------------------------------- K1b trace service
-// The reference's host hands the engine 524 288-photon batches from C worker threads
-// (task_scheduler.rs:95-96,127-182; app.rs:104-109): 4.6 photons per thread of a full grid.  One
-// launch per batch spends most of its life in its tail.  The trace service keeps ONE resident
-// kernel busy with whatever batches are queued: render() pushes a {photon range, records,
-// completion flag} entry into a ring in device memory (service_push_kernel, in stream order on
-// the unit's stream) and launches a worker (service_worker_kernel) behind it; a worker's CTAs
-// claim chunks of photons from the oldest entries of the ring, whichever unit they belong to,
-// and leave only when the ring has nothing left to claim -- so while the host keeps batches
-// queued the same CTAs stay resident and go from one batch to the next without a tail, and a
-// worker that finds the ring empty (an older worker took its entry) retires in microseconds.
-// A finished entry stores its sequence number to the unit's completion word; the unit's stream
-// waits on that word (cuStreamWaitValue32) before the copy of the records to the host.
-//
-// Same path code as trace_kernel (camera_ray, intersect_scene, material_bounce, roulette): a
-// photon's record depends on (scene, seed, photon id) only, so which CTA of which worker traces
-// it changes nothing (tests/test_gpu_service.py).
-#define RL_SERVICE_CHUNK 1024u         // photons a CTA claims at a time
-#define RL_SERVICE_OPEN 4u             // entries a CTA can hold paths of at once
-#define RL_SERVICE_POOLS 2u            // chunks a CTA deals photons from
-#ifndef RL_SERVICE_LINGER_CYCLES
-#define RL_SERVICE_LINGER_CYCLES 60000 // a CTA that has worked waits this long for new entries (~30 us)
-#endif
-
-struct ServiceCta {                    // per-CTA bookkeeping in shared memory, behind the intersection scratch
-    struct Open {
-        uint64_t seed, first_photon;
-        rl_mapped_photon *records;
-        float4 *accum;
-        ServiceEntry *slot;
-        float aspect;
-        int width, height;
-        uint32_t ticket;               // ring ticket + 1 of the entry; 0 = free
-        uint32_t n_photons;
-        uint32_t unfinished;           // photons this CTA claimed and has not finished (dealt or not)
-        uint32_t claimed;              // photons claimed since the last flush to the entry
-        uint32_t rays;                 // Scene::intersect calls since the last flush
-    } open[RL_SERVICE_OPEN];
-    struct Pool { uint32_t next, end, open; } pool[RL_SERVICE_POOLS];
-    uint32_t active;                   // some photon of this CTA is alive or waits to be dealt
-    uint32_t done;                     // nothing left and nothing arrived: the CTA retires
-    uint32_t worked;                   // the CTA has claimed at least one chunk
-    long long idle_since;
-};
-
-__device__ __forceinline__ ServiceCta *service_cta(const DevScene &sc) {
-    char *base = reinterpret_cast<char *>(rl_smem + RL_TABLES_VEC4 + sc.smem_vec4);
-    return reinterpret_cast<ServiceCta *>(base + (size_t)RL_SCRATCH_BYTES_PER_THREAD * blockDim.x);
-}
-
-__global__ void service_push_kernel(ServiceQueue *q, ServiceEntry e) {
-    if (threadIdx.x != 0) return;
-    const uint32_t t = atomicAdd(&q->tail, 1u);
-    ServiceEntry *s = &q->slots[t % RL_SERVICE_CAP];
-    // the slot's previous entry (RL_SERVICE_CAP tickets ago) may still be in flight
-    while (atomicCAS(&s->busy, 0u, 1u) != 0u) __nanosleep(200);
-    s->seed = e.seed; s->first_photon = e.first_photon;
-    s->records = e.records; s->accum = e.accum; s->ray_counter = e.ray_counter;
-    s->done_flag = e.done_flag; s->done_value = e.done_value; s->n_photons = e.n_photons;
-    s->width = e.width; s->height = e.height; s->aspect = e.aspect;
-    s->finished = 0u;
-    __threadfence();
-    // publishes the entry: claimers compare the ticket half before they touch the slot
-    atomicExch(&s->ticket_next, (unsigned long long)(t + 1u) << 32);
-}
-
-// Thread 0, between two block barriers: hand finished photons back to their entries, refill the
-// pools from the ring, decide whether the CTA stays.
-__device__ __forceinline__ void service_manage(ServiceQueue *q, ServiceCta *cta) {
-    uint32_t pending = 0;
-#pragma unroll 1
-    for (uint32_t o = 0; o < RL_SERVICE_OPEN; o++) {
-        ServiceCta::Open &op = cta->open[o];
-        if (op.ticket == 0u) continue;
-        if (op.unfinished != 0u) { pending += op.unfinished; continue; }
-        // every photon this CTA took from the entry has ended; the records were written before the
-        // barrier this thread has just passed
-        ServiceEntry *s = op.slot;
-        if (op.rays && s->ray_counter) atomicAdd(s->ray_counter, (unsigned long long)op.rays);
-        __threadfence();
-        const uint32_t before = atomicAdd(&s->finished, op.claimed);
-        if (before + op.claimed == op.n_photons) {
-            // the last photons of the entry: everything the other CTAs wrote is ordered before
-            // their own additions to `finished`
-            // the flag is a word in mapped host memory: the records must be visible to the copy
-            // engine and to peers before the host sees it
-            __threadfence_system();
-            uint32_t *flag = s->done_flag;
-            const uint32_t value = s->done_value;
-            *reinterpret_cast<volatile uint32_t *>(flag) = value;
-            __threadfence();
-            atomicExch(&s->busy, 0u);
-        }
-        op.ticket = 0u; op.claimed = 0u; op.rays = 0u;
-    }
-#pragma unroll 1
-    for (uint32_t p = 0; p < RL_SERVICE_POOLS; p++) {
-        ServiceCta::Pool &pl = cta->pool[p];
-        if (pl.next < pl.end) continue;                         // still dealing
-        pl.next = pl.end = 0u;
-        // claim the next chunk of the oldest entry that has photons left
-        uint32_t h = *reinterpret_cast<volatile uint32_t *>(&q->head);
-#pragma unroll 1
-        for (;;) {
-            const uint32_t t = *reinterpret_cast<volatile uint32_t *>(&q->tail);
-            if (h == t) break;
-            ServiceEntry *s = &q->slots[h % RL_SERVICE_CAP];
-            unsigned long long word = *reinterpret_cast<volatile unsigned long long *>(&s->ticket_next);
-            if ((uint32_t)(word >> 32) != h + 1u) {
-                // not published yet, or the ring has moved on
-                const uint32_t h2 = *reinterpret_cast<volatile uint32_t *>(&q->head);
-                if (h2 == h) break;
-                h = h2;
-                continue;
-            }
-            __threadfence();                                    // the entry's fields were written before its ticket
-            const uint32_t n = *reinterpret_cast<volatile uint32_t *>(&s->n_photons);
-            const uint32_t c = (uint32_t)word;
-            if (c >= n) {                                       // fully claimed: move the head on
-                atomicCAS(&q->head, h, h + 1u);
-                h = *reinterpret_cast<volatile uint32_t *>(&q->head);
-                continue;
-            }
-            // an open record for this entry: the one it already has, else a free one
-            uint32_t o = RL_SERVICE_OPEN, free_o = RL_SERVICE_OPEN;
-            for (uint32_t k = 0; k < RL_SERVICE_OPEN; k++) {
-                if (cta->open[k].ticket == h + 1u) o = k;
-                else if (cta->open[k].ticket == 0u && free_o == RL_SERVICE_OPEN) free_o = k;
-            }
-            if (o == RL_SERVICE_OPEN) o = free_o;
-            if (o == RL_SERVICE_OPEN) break;                    // paths of four entries alive: wait
-            const uint32_t take = n - c < RL_SERVICE_CHUNK ? n - c : RL_SERVICE_CHUNK;
-            if (atomicCAS(&s->ticket_next, word, word + take) != word) continue;   // another CTA was faster
-            ServiceCta::Open &op = cta->open[o];
-            if (op.ticket == 0u) {
-                op.seed = s->seed; op.first_photon = s->first_photon;
-                op.records = s->records; op.accum = s->accum; op.slot = s;
-                op.aspect = s->aspect; op.width = (int)s->width; op.height = (int)s->height;
-                op.n_photons = n;
-                op.ticket = h + 1u; op.unfinished = 0u; op.claimed = 0u; op.rays = 0u;
-            }
-            op.unfinished += take;
-            op.claimed += take;
-            pl.next = c; pl.end = c + take; pl.open = o;
-            pending += take;
-            cta->worked = 1u;
-            break;
-        }
-    }
-    cta->active = pending != 0u;
-    if (pending != 0u) {
-        cta->idle_since = 0;
-    } else if (!cta->worked) {
-        cta->done = 1u;                                         // an older worker took everything
-    } else {
-        const long long now = clock64();
-        if (cta->idle_since == 0) cta->idle_since = now;
-        else if (now - cta->idle_since > RL_SERVICE_LINGER_CYCLES) cta->done = 1u;
-        __nanosleep(500);
-    }
-}
-
-__global__ void __launch_bounds__(RL_TRACE_THREADS, RL_TRACE_MIN_BLOCKS)
-service_worker_kernel(const DevScene sc, ServiceQueue *q) {
-    ServiceCta *cta = service_cta(sc);
-    if (threadIdx.x == 0) {
-        for (uint32_t o = 0; o < RL_SERVICE_OPEN; o++) {
-            cta->open[o].ticket = 0u; cta->open[o].unfinished = 0u; cta->open[o].claimed = 0u; cta->open[o].rays = 0u;
-        }
-        for (uint32_t p = 0; p < RL_SERVICE_POOLS; p++) cta->pool[p].next = cta->pool[p].end = cta->pool[p].open = 0u;
-        cta->active = 0u; cta->done = 0u; cta->worked = 0u; cta->idle_since = 0;
-        service_manage(q, cta);
-    }
-    __syncthreads();
-    if (cta->done) return;                                      // nothing to claim: no table set-up either
-    setup_tables(sc);
-
-    const uint32_t lane = threadIdx.x & 31u;
-    bool alive = false;
-    uint32_t cur = 0;                                           // photon index within its entry | open record << 28
-    Ray ray;
-    ray.origin = mk(0.f, 0.f, 0.f); ray.direction = mk(0.f, 0.f, 0.f); ray.wavelength = 0.f;
-    float sx = 0.f, sy = 0.f;
-    float intensity = 1.0f, continue_chance = 1.0f;
-    Rng rng;
-    rng.init();
-    uint32_t rays = 0;                                          // of the current path
-
-    for (bool first = true;; first = false) {
-        if (!first) {
-            __syncthreads();                                    // the path ends of the last iteration are counted
-            if (threadIdx.x == 0) service_manage(q, cta);
+        uint32_t avail = rs.y - rs.x, tail = rs.y, n_new = 0u;
+        if (avail < dead && rs.z < rs.w) {
+            n_new = a.ring_cap - avail;
+            if (n_new > T) n_new = T;
+            if (n_new > rs.w - rs.z) n_new = rs.w - rs.z;
+            if (threadIdx.x < n_new)
+                generate_camera_entry(sc, a, cta, ring + 3u * ((tail + threadIdx.x) & cap_mask), rs.z + threadIdx.x);
             __syncthreads();
+            tail += n_new; avail += n_new;
         }
-        if (cta->done) break;
-        if (!cta->active) continue;
-        // lanes without a path draw photons from the CTA's pools (one warp-aggregated atomic per pool)
-        uint32_t mine = 0xffffffffu, mine_open = 0;
-#pragma unroll
-        for (uint32_t p = 0; p < RL_SERVICE_POOLS; p++) {
-            const uint32_t want = __ballot_sync(0xffffffffu, !alive && mine == 0xffffffffu);
-            ServiceCta::Pool &pl = cta->pool[p];
-            const uint32_t end = pl.end;
-            if (want != 0u && pl.next < end) {                  // warp-uniform: one address, one load
-                const uint32_t leader = __ffs(want) - 1u;
-                uint32_t base = 0;
-                if (lane == leader) base = atomicAdd(&pl.next, (uint32_t)__popc(want));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                const uint32_t idx = base + __popc(want & ((1u << lane) - 1u));
-                if (!alive && mine == 0xffffffffu && idx < end) { mine = idx; mine_open = pl.open; }
+        if (dead == T && avail == 0u) break;                        // no path alive, no photon left
+#if RL_RING_STATE_SMEM
+        if (threadIdx.x == 0)
+            cta->ring_state[parity ^ 1u] = make_uint4(rs.x + (dead < avail ? dead : avail), tail, rs.z + n_new, rs.w);
+#else
+        ring_regs = make_uint4(rs.x + (dead < avail ? dead : avail), tail, rs.z + n_new, rs.w);
+#endif
+        if (avail != 0u && want != 0u) {
+            // the lanes without a path take the oldest ready camera rays, in thread order: a
+            // warp's first entry is the number of such lanes in the warps before it
+            const uint32_t before = __reduce_add_sync(0xffffffffu, lane < warp ? cta->warp_dead[parity][lane] : 0u);
+            const uint32_t idx = rs.x + before + __popc(want & ((1u << lane) - 1u));
+            if (!alive && idx < tail) {
+                const float4 *e = ring + 3u * (idx & cap_mask);
+                const float4 e0 = e[0], e1 = e[1], e2 = e[2];
+                ray.origin = mk(e0.x, e0.y, e0.z);
+                ray.direction = mk(e0.w, e1.x, e1.y);
+                ray.wavelength = e1.z;
+                *park = make_float2(e1.w, e2.x);                    // MappedPhoton x, y
+                rng.block = 2u; rng.left = 2u;                      // six draws made (generate_camera_entry)
+                rng.b0 = __float_as_uint(e2.y); rng.b1 = __float_as_uint(e2.z); rng.b2 = 0u; rng.b3 = 0u;
+                cur = __float_as_uint(e2.w);
+                intensity = 1.0f;
+                continue_chance = 1.0f;
+                rays = 0;
+                alive = true;
             }
         }
-        if (mine != 0xffffffffu) {
-            // trace_unit.rs:151-158 and :136-145
-            const ServiceCta::Open &op = cta->open[mine_open];
-            cur = mine | (mine_open << 28);
-            const RngKey key = {op.seed, op.first_photon + mine};
-            rng.init();
-            const float wavelength = rng.wavelength(key);
-            sx = rng.bi_unit(key);
-            sy = rng.bi_unit(key) / op.aspect;
-            const float t = rng.unit(key);
-            ray = camera_ray(sc.camera, sx, sy, wavelength, t, rng, key);
-            intensity = 1.0f;
-            continue_chance = 1.0f;
-            rays = 0;
-            alive = true;
-        }
+        parity ^= 1u;
         const Hit hit = intersect_scene(alive ? ray : idle_ray(), alive);
         if (alive) {
-            rays++;
-            ServiceCta::Open &op = cta->open[cur >> 28];
-            const uint32_t index = cur & 0x0fffffffu;
+            rays++;                                                 // Scene::intersect calls (scene.rs:39)
+            const uint32_t seg = cur >> a.seg_shift, index = cur & ((1u << a.seg_shift) - 1u);
             // trace_unit.rs:91-131
             bool done = false;
             float result = 0.0f;
@@ -455,7 +225,7 @@ service_worker_kernel(const DevScene sc, ServiceQueue *q) {
                     done = true;
                 } else {
                     const Surf s = surface_at(ray, hit);
-                    const RngKey key = {op.seed, op.first_photon + index};
+                    const RngKey key = {cta->seed[seg], cta->first_photon[seg] + index};
                     float probability;
                     const V3 dir = material_bounce(m, ray, hit, s, rng, key, probability);  // :104-107
                     intensity = intensity * probability;
@@ -468,26 +238,41 @@ service_worker_kernel(const DevScene sc, ServiceQueue *q) {
                 }
             }
             if (done) {
-                if (op.records)
-                    *reinterpret_cast<float4 *>(op.records + index) = make_float4(sx, sy, result, ray.wavelength);
-                if (op.accum && result != 0.0f)
-                    splat_photon(op.accum, op.width, op.height, op.aspect, sx, sy, ray.wavelength, result);
-                atomicAdd(&op.rays, rays);
-                atomicSub(&op.unfinished, 1u);
+                const float2 screen = *park;
+                rl_mapped_photon *records = cta->records[seg];
+                if (records)
+                    *reinterpret_cast<float4 *>(records + index) = make_float4(screen.x, screen.y, result, ray.wavelength);
+                // adding cie * 0 leaves the accumulator unchanged (plot_unit.rs:80-83)
+                if (a.accum && result != 0.0f)
+                    splat_photon(a.accum, a.width, a.height, a.aspect, screen.x, screen.y, ray.wavelength, result);
+                atomicAdd(&cta->seg_rays[seg], rays);
                 alive = false;
             }
         }
     }
+
+    // rays traced = Scene::intersect calls (scene.rs:39), per segment (= per trace unit)
+    __syncthreads();
+    if (threadIdx.x < a.n_seg) {
+        const uint32_t r = cta->seg_rays[threadIdx.x];
+        unsigned long long *counter = a.seg[threadIdx.x].ray_counter;
+        if (r != 0u && counter) atomicAdd(counter, (unsigned long long)r);
+    }
 }
 
+// camera-ray ring entries for CTAs of `threads` threads: the power of two at or above the CTA
+// size (a refill never has to be cut short), or below it when shared memory is short
+static uint32_t ring_entries(int threads, bool roomy) {
+    uint32_t cap = 128;
+    while ((int)cap < threads) cap <<= 1;
+    if (!roomy && (int)cap > threads && cap > 128) cap >>= 1;
+    return cap;
+}
+static size_t trace_kernel_smem_bytes(const DevScene &sc, int threads, uint32_t ring_cap) {
+    return tracing_smem_bytes(sc, threads) + sizeof(TraceCta) + (size_t)RL_TRACE_PARK_BYTES_PER_THREAD * ((threads + 1) & ~1)
+           + (size_t)ring_cap * 3 * sizeof(float4);
+}
 size_t trace_smem_bytes(const DevScene &sc, int threads) { return tracing_smem_bytes(sc, threads); }
-// the trace kernel proper: plus the path-sort area when enabled
-static size_t service_smem_bytes(const DevScene &sc, int threads) {
-    return tracing_smem_bytes(sc, threads) + sizeof(ServiceCta);
-}
-static size_t trace_kernel_smem_bytes(const DevScene &sc, int threads) {
-    return tracing_smem_bytes(sc, threads) + (RL_SORT_PATHS ? (size_t)RL_SORT_BYTES_PER_THREAD * threads : 0);
-}
 
 // Small launches in flight: one mark per stream, an event re-recorded behind that stream's latest
 // small launch.  launch_trace (under its lock) counts the OTHER streams whose mark has not
@@ -570,42 +355,14 @@ static void set_carveout(Kernel kernel, KernelCache &cached, int per_sm, size_t 
     }
 }
 
-cudaError_t launch_service_push(ServiceQueue *q, const ServiceEntry &e, cudaStream_t st) {
-    if (e.n_photons == 0 || e.n_photons > (1u << 28)) return cudaErrorInvalidValue;
-    service_push_kernel<<<1, 32, 0, st>>>(q, e);
-    g_launches++;
-    return cudaGetLastError();
-}
-
-cudaError_t launch_service_worker(const DevScene &sc, ServiceQueue *q, int sm_count, int reserved_sms,
-                                  cudaStream_t st) {
-    static std::mutex lock;
-    static KernelCache cache[16];
-    int dev = 0;
-    cudaError_t err = cudaGetDevice(&dev);
-    if (err != cudaSuccess) return err;
-    int threads = RL_TRACE_THREADS;
-    size_t smem = 0;
-    {
-        std::lock_guard<std::mutex> guard(lock);
-        KernelCache scratch_entry;
-        KernelCache &cached = dev >= 0 && dev < 16 ? cache[dev] : scratch_entry;
-        err = prepare_kernel(service_worker_kernel, cached, dev);
-        if (err != cudaSuccess) return err;
-        while (threads > 128 && service_smem_bytes(sc, threads) > (size_t)cached.max_smem) threads -= 128;
-        smem = service_smem_bytes(sc, threads);
-        if (smem > (size_t)cached.max_smem) return cudaErrorInvalidValue;
-        set_carveout(service_worker_kernel, cached, 1, smem);
-    }
-    int grid = sm_count - reserved_sms;
-    if (grid < 1) grid = 1;
-    service_worker_kernel<<<(unsigned)grid, threads, smem, st>>>(sc, q);
-    g_launches++;
-    return cudaGetLastError();
-}
-
 cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count, cudaStream_t st) {
-    if (p.n_photons == 0) return cudaSuccess;
+    if (p.n_segments == 0 || p.n_segments > RL_MAX_SEGMENTS) return p.n_segments ? cudaErrorInvalidValue : cudaSuccess;
+    uint64_t n_photons = 0;
+    for (uint32_t k = 0; k < p.n_segments; k++) {
+        if (p.n_segments > 1 && p.seg[k].n_photons >= (1ull << RL_SEGMENT_INDEX_BITS)) return cudaErrorInvalidValue;
+        n_photons += p.seg[k].n_photons;
+    }
+    if (n_photons == 0) return cudaSuccess;
     // the function attributes below are process-wide: launches from the threads of different
     // units (each on its own stream) take turns setting them and launching
     static std::mutex launch_lock;
@@ -621,8 +378,15 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     err = prepare_kernel(trace_kernel, cached, dev);
     if (err != cudaSuccess) return err;
     const int max_smem = cached.max_smem;
-    int threads = RL_TRACE_THREADS;
-    while (threads > 128 && trace_kernel_smem_bytes(sc, threads) > (size_t)max_smem) threads -= 128;
+    int threads = env_int("RL_TRACE_THREADS_MAX", RL_TRACE_THREADS);
+    if (threads > RL_TRACE_THREADS || threads < 128 || threads % 128) threads = RL_TRACE_THREADS;
+    // prefer the full CTA with a short ring to a smaller CTA with a roomy one
+    bool roomy = true;
+    while (trace_kernel_smem_bytes(sc, threads, ring_entries(threads, roomy)) > (size_t)max_smem) {
+        if (roomy) { roomy = false; continue; }
+        if (threads <= 128) return cudaErrorInvalidValue;
+        threads -= 128; roomy = true;
+    }
     // Small batches (the reference's 524 288 photons are 4.6 per thread of a full grid) spend most
     // of their time in the tail, where a block waits for its last paths.  They are launched as
     // small CTAs, several per SM, so that the blocks of a launch retire one by one and the blocks
@@ -636,9 +400,10 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     const int small_cta = env_int("RL_TRACE_SMALL_CTA", RL_TRACE_SMALL_CTA);
     const uint64_t small_paths = (uint64_t)env_int("RL_TRACE_SMALL_PATHS", RL_TRACE_SMALL_PATHS);
     const bool small = small_cta >= 128 && small_cta < threads && small_cta % 32 == 0
-                       && p.n_photons < small_paths * (uint64_t)sm_count * (uint64_t)threads;
-    if (small) threads = small_cta;
-    const size_t smem = trace_kernel_smem_bytes(sc, threads);
+                       && n_photons < small_paths * (uint64_t)sm_count * (uint64_t)threads;
+    if (small) { threads = small_cta; roomy = true; }
+    const uint32_t ring_cap = ring_entries(threads, roomy);
+    const size_t smem = trace_kernel_smem_bytes(sc, threads, ring_cap);
     if (cached.threads != threads || cached.smem != smem) {
         int occ = 0;
         err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_kernel, threads, smem);
@@ -647,7 +412,6 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     }
     const int per_sm = cached.per_sm;
     set_carveout(trace_kernel, cached, per_sm, smem);
-    uint64_t want = (p.n_photons + threads - 1) / threads;
     uint64_t full = (uint64_t)sm_count * per_sm;
     if (small) {
         // RL_TRACE_BLOCKS_PER_SM > 0 fixes the share (experiments); default: by the concurrency seen
@@ -658,20 +422,29 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
         }
         if (share < per_sm) full = (uint64_t)sm_count * (share < 1 ? 1 : share);
     }
-    unsigned grid = (unsigned)(want < full ? want : full);
-    // the kernel indexes photons of a launch with 32 bits: larger requests take several launches
+    TraceArgs a;
+    a.n_seg = p.n_segments;
+    a.seg_shift = p.n_segments > 1 ? RL_SEGMENT_INDEX_BITS : 31u;
+    a.ring_cap = ring_cap;
+    a.width = (int)p.width;
+    a.height = (int)p.height;
+    a.aspect = (float)p.width / (float)p.height;      // trace_unit.rs:73, plot_unit.rs:49
+    a.accum = p.accum;
+    for (uint32_t k = 0; k < RL_MAX_SEGMENTS; k++) a.seg[k] = p.seg[k < p.n_segments ? k : 0];
+    // a launch indexes the photons of a segment with seg_shift bits: a larger single request takes several launches
     const uint64_t chunk = 1ull << 31;
-    for (uint64_t done = 0; done < p.n_photons; done += chunk) {
-        TraceArgs a;
-        a.seed = p.seed;
-        a.first_photon = p.first_photon + done;
-        a.n_photons = p.n_photons - done < chunk ? p.n_photons - done : chunk;
-        a.width = (int)p.width;
-        a.height = (int)p.height;
-        a.aspect = (float)p.width / (float)p.height;  // trace_unit.rs:73, plot_unit.rs:49
-        a.records = p.records ? p.records + done : nullptr;
-        a.accum = p.accum;
-        a.ray_counter = p.ray_counter;
+    const uint64_t passes = p.n_segments > 1 ? 1 : (n_photons + chunk - 1) / chunk;
+    for (uint64_t pass = 0; pass < passes; pass++) {
+        uint64_t n_launch = n_photons;
+        if (p.n_segments == 1) {
+            const uint64_t done = pass * chunk;
+            n_launch = n_photons - done < chunk ? n_photons - done : chunk;
+            a.seg[0].first_photon = p.seg[0].first_photon + done;
+            a.seg[0].n_photons = n_launch;
+            a.seg[0].records = p.seg[0].records ? p.seg[0].records + done : nullptr;
+        }
+        const uint64_t want = (n_launch + threads - 1) / threads;
+        const unsigned grid = (unsigned)(want < full ? want : full);
         trace_kernel<<<grid, threads, smem, st>>>(sc, a);
         g_launches++;
         cudaError_t e = cudaGetLastError();

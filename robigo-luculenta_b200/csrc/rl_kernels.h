@@ -9,43 +9,25 @@
 
 namespace rl {
 
-struct TraceLaunch {
+// One batch of photons: the ids [first_photon, first_photon + n_photons) of the stream `seed`
+// (one TraceUnit::render call, trace_unit.rs:151-168).
+struct TraceSegment {
     uint64_t seed;
     uint64_t first_photon;
     uint64_t n_photons;
+    rl_mapped_photon *records;        // device, n_photons entries, or nullptr
+    unsigned long long *ray_counter;  // device, or nullptr
+};
+// Batches traced by one launch share the canvas and the accumulator.  Several segments: each
+// fewer than 2^RL_SEGMENT_INDEX_BITS photons; one segment: any size (split into launches of 2^31).
+#define RL_MAX_SEGMENTS 32
+#define RL_SEGMENT_INDEX_BITS 27
+struct TraceLaunch {
     uint32_t width, height;
-    rl_mapped_photon *records;  // device, n_photons entries, or nullptr
-    float4 *accum;              // device, width*height float4, or nullptr (fused splat)
-    unsigned long long *ray_counter;  // device
+    float4 *accum;                    // device, width*height float4, or nullptr (fused splat)
+    uint32_t n_segments;
+    TraceSegment seg[RL_MAX_SEGMENTS];
 };
-
-// ---- trace service: a ring of batches in device memory that resident worker CTAs drain
-#define RL_SERVICE_CAP 1024u           // ring slots (entries in flight at once)
-struct ServiceEntry {
-    uint64_t seed, first_photon;
-    rl_mapped_photon *records;         // device, n_photons entries, or nullptr
-    float4 *accum;                     // device accumulator for a fused splat, or nullptr
-    unsigned long long *ray_counter;   // device
-    uint32_t *done_flag;               // word (mapped host memory) that receives done_value when the entry is finished
-    uint32_t done_value, n_photons;    // 0 < n_photons <= 2^28
-    uint32_t width, height;
-    float aspect;
-    uint32_t finished;                 // photons whose paths have ended
-    uint32_t busy;                     // the slot holds an entry that is not finished yet
-    unsigned long long ticket_next;    // (ring ticket + 1) << 32 | photons claimed so far
-};
-struct ServiceQueue {
-    uint32_t tail;                     // tickets handed out
-    uint32_t head;                     // oldest ticket that may have unclaimed photons
-    uint32_t pad[2];
-    ServiceEntry slots[RL_SERVICE_CAP];
-};
-// Queue one batch (in stream order on `st`); n_photons must be in (0, 2^28].
-cudaError_t launch_service_push(ServiceQueue *q, const ServiceEntry &e, cudaStream_t st);
-// One worker: CTAs that drain the ring and retire when it stays empty.  `reserved_sms` SMs are
-// left to the other kernels of the pipeline (splat, gather, pack).
-cudaError_t launch_service_worker(const DevScene &sc, ServiceQueue *q, int sm_count, int reserved_sms,
-                                  cudaStream_t st);
 
 // Dynamic shared memory the trace kernels need for a scene.
 size_t trace_smem_bytes(const DevScene &sc, int threads);

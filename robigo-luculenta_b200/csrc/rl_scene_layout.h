@@ -17,6 +17,7 @@ struct DevCamera {
     uint32_t kind;
     float px, py, pz;
     float field_of_view, focal_distance, depth_of_field, chromatic_abberation;
+    float screen_distance;    // 1 / tan(field_of_view / 2) (camera.rs:60), specified arithmetic
     float qx, qy, qz, qw;
     float phi_base, phi_rate, alpha_base, alpha_rate, distance_base, distance_rate, focal_factor;
 };
@@ -33,12 +34,15 @@ struct DevScene {
     uint32_t off_compounds, n_compounds;
     uint32_t off_ops, n_ops;
     uint32_t off_sphere_obj, off_plane_obj, off_paraboloid_obj, off_compound_obj, off_sphere_k;
-    uint32_t off_clusters, n_clusters, off_cluster_range;
+    uint32_t off_clusters, n_clusters, off_cluster_range;   // clusters padded to a multiple of 8 records
+    uint32_t off_body_bounds, off_body_always;              // bounding spheres of the compounds in the pre-test's form
+                                                            // (padded to 8), and per 64 bodies the mask of unbounded ones
     const float4 *materials;  // per object
     uint32_t n_objects;
     float sphere_cmax2;       // max (|centre|^2 + r^2) over spheres and clusters (error bound of the pre-test)
     float cluster_rmax;       // largest cluster bounding radius
     float leaf_off_max;       // largest |offset| over the half-spaces of compound surfaces (slab-test inflation)
+    float body_rmax;          // largest bounding radius of a compound
     DevCamera camera;
 };
 

@@ -283,14 +283,16 @@ int main(int argc, char **argv) {
             fclose(f);
         }
         const uint64_t rays = scheduler.rays();
+        uint64_t launches = 0, grouped = 0;
+        rl_scene_dispatch_stats(scene.handle(), &launches, &grouped);
         printf("{\"mode\": \"%s\", \"pinned\": %s, \"lazy\": %s, \"async_render\": %s, \"records\": \"%s\", \"consume\": \"%s\", \"sleep_ms\": %d, \"width\": %u, \"height\": %u, \"threads\": %zu, \"batches\": %llu, \"batch\": %llu, \"seconds\": %.6f, \"setup_seconds\": %.6f, "
-               "\"batches_per_s\": %.3f, \"rays\": %llu, \"mrays_per_s\": %.3f, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"worker_seconds\": {\"sleep\": [%llu, %.3f], "
+               "\"batches_per_s\": %.3f, \"dispatch\": {\"launches\": %llu, \"batches\": %llu}, \"rays\": %llu, \"mrays_per_s\": %.3f, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"worker_seconds\": {\"sleep\": [%llu, %.3f], "
                "\"trace\": [%llu, %.3f], \"plot\": [%llu, %.3f], \"gather\": [%llu, %.3f], \"tonemap\": [%llu, %.3f]}}\n",
                device ? "device" : "strict", pin_host_buffers() ? "true" : "false",
                lazy_host_mirrors() ? "true" : "false", async_render() ? "true" : "false",
                deferred_records() ? "deferred" : "host", consume_on_device() ? "device" : "host", g_sleep_ms, w, h, threads, (unsigned long long)scheduler.traces_completed(),
                (unsigned long long)batch, seconds, setup_seconds, scheduler.traces_completed() / seconds,
-               (unsigned long long)rays, rays / seconds / 1e6, (unsigned long long)h2d, (unsigned long long)d2h,
+               (unsigned long long)launches, (unsigned long long)grouped, (unsigned long long)rays, rays / seconds / 1e6, (unsigned long long)h2d, (unsigned long long)d2h,
                (unsigned long long)g_stats[0].calls, g_stats[0].ns * 1e-9, (unsigned long long)g_stats[1].calls,
                g_stats[1].ns * 1e-9, (unsigned long long)g_stats[2].calls, g_stats[2].ns * 1e-9,
                (unsigned long long)g_stats[3].calls, g_stats[3].ns * 1e-9, (unsigned long long)g_stats[4].calls,

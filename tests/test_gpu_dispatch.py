@@ -1,8 +1,9 @@
-"""The trace service (csrc/rl_kernels.cu K1b): batches of the reference's size are queued to a
-ring in device memory and traced by resident worker CTAs instead of one launch each
-(task_scheduler.rs:95-96,127-182 is the caller that produces them).  Whichever CTA of whichever
-worker traces a photon, its record is a function of (scene, seed, photon id): everything here is
-compared bit for bit with the oracle, and with the one-launch-per-batch path."""
+"""Group launches (csrc/rl_api.cu TraceDispatcher, csrc/rl_kernels.cu K1): batches of the
+reference's size are queued to the scene's dispatcher and traced several to a launch, each batch
+one segment of the launch's photon pool (task_scheduler.rs:95-96,127-182 is the caller that
+produces them).  Whichever launch, CTA and lane traces a photon, its record is a function of
+(scene, seed, photon id): everything here is compared bit for bit with the oracle, and with the
+one-launch-per-batch path."""
 import threading
 
 import numpy as np
@@ -13,7 +14,7 @@ from test_gpu_parity import SEED, assert_records_equal, image_tolerance
 pytestmark = pytest.mark.gpu
 
 
-def test_service_batches_bit_equal_and_counted(gpu, orc):
+def test_grouped_batches_bit_equal_and_counted(gpu, orc):
     b = gpu.SceneBuilder(2)
     sc = gpu.Scene(b)
     w, h, n, rounds = 320, 200, 5000, 6
@@ -22,7 +23,7 @@ def test_service_batches_bit_equal_and_counted(gpu, orc):
     got = {}
     for r in range(rounds):
         for u in units:
-            u.render(sc, wait=False)                # 7 batches in flight on the ring
+            u.render(sc, wait=False)                # 7 batches queued: they share launches
         for i, u in enumerate(units):
             u.sync()
             got[3 + r * len(units) + i] = u.mapped_photons.copy()
@@ -32,10 +33,12 @@ def test_service_batches_bit_equal_and_counted(gpu, orc):
     for k in range(total):
         assert_records_equal(got[3 + k], want[k * n:(k + 1) * n], f"batch {3 + k}")
     assert sum(u.ray_count() for u in units) == ct.rays
+    launches, batches = sc.dispatch_stats()
+    assert batches == total and 1 <= launches <= total
 
 
 @pytest.mark.parametrize("n", [1, 7, 1023, 1024, 1025, 4097])
-def test_service_ragged_batch_sizes(gpu, orc, n):
+def test_dispatched_ragged_batch_sizes(gpu, orc, n):
     b = gpu.SceneBuilder(3)
     sc = gpu.Scene(b)
     tu = gpu.TraceUnit(0, 64, 48, seed=11, batch=n)
@@ -44,22 +47,24 @@ def test_service_ragged_batch_sizes(gpu, orc, n):
         assert_records_equal(got, orc.trace(b.desc(), 11, 64, 48, first, n), f"n={n} first={first}")
 
 
-def test_service_equals_one_launch_per_batch(gpu, monkeypatch):
+def test_group_launch_equals_one_launch_per_batch(gpu, monkeypatch):
     b = gpu.SceneBuilder(2)
     sc = gpu.Scene(b)
     n = 40000
     tu = gpu.TraceUnit(0, 512, 512, seed=SEED, batch=n)
-    through_service = tu.render_range(sc, 77 * n, n).copy()
-    rays_service = tu.ray_count()
-    monkeypatch.setenv("RL_TRACE_SERVICE", "0")
+    through_dispatcher = tu.render_range(sc, 77 * n, n).copy()
+    rays_dispatcher = tu.ray_count()
+    assert sc.dispatch_stats() == (1, 1)
+    monkeypatch.setenv("RL_TRACE_GROUPS", "0")
     tu2 = gpu.TraceUnit(1, 512, 512, seed=SEED, batch=n)
     direct = tu2.render_range(sc, 77 * n, n)
-    assert_records_equal(through_service, direct, "service vs launch")
-    assert rays_service == tu2.ray_count()
+    assert sc.dispatch_stats() == (1, 1)                # the second render was a launch of its own
+    assert_records_equal(through_dispatcher, direct, "dispatcher vs launch")
+    assert rays_dispatcher == tu2.ray_count()
 
 
-def test_service_ring_wraps(gpu, orc):
-    # more batches than the ring has slots (1024), from several units and two host threads
+def test_many_batches_from_two_host_threads(gpu, orc):
+    # 1400 batches from several units and two host threads
     b = gpu.SceneBuilder(1)
     sc = gpu.Scene(b)
     n, per_thread = 96, 700
@@ -88,8 +93,8 @@ def test_service_ring_wraps(gpu, orc):
             assert_records_equal(rec, want[first:first + n], f"batch at {first}")
 
 
-def test_two_scenes_keep_separate_rings(gpu, orc):
-    # two scenes (two Apps) in one process: records through each scene's own service, splatted
+def test_two_scenes_keep_separate_dispatchers(gpu, orc):
+    # two scenes (two Apps) in one process: records through each scene's own dispatcher, splatted
     # from the device copy, and small fused batches (which stay launches) beside them
     w, h, n = 96, 64, 20000
     b2, b3 = gpu.SceneBuilder(2), gpu.SceneBuilder(3)
@@ -108,3 +113,35 @@ def test_two_scenes_keep_separate_rings(gpu, orc):
     for scene_b, plot in ((b2, p2), (b3, p3)):
         ref = orc.plot(w, h, orc.trace(scene_b.desc(), SEED, w, h, 0, 4 * n))
         assert float(np.abs(plot.tristimulus_buffer - ref).max()) <= image_tolerance(ref)
+
+
+def test_group_of_units_with_different_seeds_and_sizes(gpu, orc):
+    # one launch carries segments of different RNG streams and lengths; units on another canvas
+    # are grouped separately
+    b = gpu.SceneBuilder(2)
+    sc = gpu.Scene(b)
+    spec = [(0, 64, 48, 5, 3000), (1, 64, 48, 6, 1), (2, 64, 48, 7, 4097), (3, 32, 32, 8, 2500),
+            (4, 64, 48, 5, 777), (5, 32, 32, 9, 1024)]
+    units = [gpu.TraceUnit(i, w, h, seed=seed, batch=n) for i, w, h, seed, n in spec]
+    for rounds in range(3):
+        sc.reset_batch_counter(10 * rounds)
+        for u in units:
+            u.render(sc, wait=False)
+        for k, (u, (i, w, h, seed, n)) in enumerate(zip(units, spec)):
+            u.sync()
+            want = orc.trace(b.desc(), seed, w, h, (10 * rounds + k) * n, n)
+            assert_records_equal(u.mapped_photons, want, f"round {rounds} unit {i}")
+
+
+def test_scene_destroyed_before_its_units(gpu):
+    # the Python wrappers are collected in any order: a unit outliving the scene it rendered is fine
+    b = gpu.SceneBuilder(1)
+    sc = gpu.Scene(b)
+    units = [gpu.TraceUnit(i, 32, 32, seed=3, batch=512) for i in range(5)]
+    for u in units:
+        u.render(sc, wait=False)
+    del sc                                              # launches what is queued, stops the dispatcher
+    for u in units:
+        u.sync()
+        assert np.isfinite(u.mapped_photons["x"]).all()
+    del units

@@ -211,18 +211,31 @@ def test_c1_trace_statistics(pkg, orc, mode):
 
 
 def test_spec_and_libm_modes_agree_statistically(pkg, orc):
-    # Same estimator, different libm: per-photon results agree except where a 1-ulp
-    # difference flips a branch; image-level statistics agree.
+    # Same estimator, different libm.  The RNG-only fields are bit-equal; the probabilities differ
+    # where an ulp of libm moved a direction or flipped a branch (measured: 1.5 % of the photons,
+    # 18 % of the lit ones -- paths are chaotic); the images agree within the stated fraction of
+    # the Monte-Carlo noise (tests/stat_parity.py; the GPU-sized version is in
+    # tests/test_gpu_parity.py::test_image_matches_reference_arithmetic).
+    import stat_parity
     d = pkg.SceneBuilder(pkg.SCENE_C2).desc()
-    n = 30000
-    a = orc.trace(d, 11, 64, 64, 0, n, 0)
-    b = orc.trace(d, 11, 64, 64, 0, n, 1)
-    for f in ("x", "y", "wavelength"):
-        assert np.array_equal(a[f], b[f])          # RNG only: bit-equal
-    pa, pb = a["probability"], b["probability"]
-    close = np.isclose(pa, pb, rtol=1e-4, atol=1e-7)
-    assert close.mean() > 0.97, f"only {close.mean():.4f} of photons agree"
-    assert abs(pa.mean() - pb.mean()) < 0.05 * pa.mean()
+    w = h = 64
+    k, n = 8, 12000
+    subs, differ = [], 0
+    whole_libm = np.zeros((h, w, 3), dtype=np.float32)
+    for i in range(k):
+        spec = orc.trace(d, 11, w, h, i * n, n, orc.MATH_SPEC)
+        libm = orc.trace(d, 11, w, h, i * n, n, orc.MATH_LIBM)
+        for f in ("x", "y", "wavelength"):
+            assert np.array_equal(spec[f], libm[f])    # RNG only: bit-equal
+        differ += int(np.count_nonzero(~np.isclose(spec["probability"], libm["probability"], rtol=1e-4, atol=1e-7)))
+        subs.append(orc.plot(w, h, spec))
+        orc.plot(w, h, libm, whole_libm)
+    assert differ / (k * n) < 0.03, f"{differ / (k * n):.4f} of the photons differ"
+    stat_parity.check(subs, whole_libm, "oracle SPEC vs LIBM")
+    # and the statistic does tell two independent renders apart
+    other = orc.plot(w, h, orc.trace(d, 12, w, h, 0, k * n, orc.MATH_SPEC))
+    rms, _, _ = stat_parity.compare(subs, other)
+    assert rms > 1.0
 
 
 # ------------------------------------------------------------------------ plot

@@ -1,0 +1,29 @@
+#!/bin/bash
+# One GPU visit: GPU tests, replay sweep, one ncu capture of the trace kernel, the bench line.
+# usage (under gpurun): bash tools/gpu_round.sh <tag> [tests|sweep|ncu|bench ...]   (default: all four)
+TAG=${1:-round}; shift
+WHAT=${@:-tests sweep ncu bench}
+mkdir -p gpurun_out
+for w in $WHAT; do
+  case $w in
+    tests) timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/${TAG}_gputest.log 2>&1; tail -4 gpurun_out/${TAG}_gputest.log ;;
+    sweep) bash tools/e2e_sweep.sh 2048 16 > gpurun_out/${TAG}_sweep.txt 2>&1; mv gpurun_out/e2e_sweep.jsonl gpurun_out/${TAG}_sweep.jsonl; cat gpurun_out/${TAG}_sweep.txt ;;
+    ncu) timeout 600 ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_trace python tools/profile_trace.py > gpurun_out/${TAG}_ncu.log 2>&1; tail -2 gpurun_out/${TAG}_ncu.log ;;
+    bench) timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -3 gpurun_out/${TAG}_bench.err; python - <<PY
+import json
+try:
+    l = json.loads(open("gpurun_out/${TAG}_bench.json").read().strip().splitlines()[-1])
+    print("value", l["value"], "ms/step", l["ms_per_step"], "launches", l["gpu_launches"])
+    for k in ("e2e", "e2e_deferred_records", "e2e_device"):
+        e = l.get(k) or {}
+        print(k, e.get("value"), e.get("seconds"), e.get("note"))
+    for o in l.get("other_configs") or []:
+        print(o["config"], round(o["mrays_per_s"], 1))
+    for a in l["roofline"].get("also", []):
+        print(a["kernel"][:30], round(a["frac"], 3))
+except Exception as e:
+    print("bench line unreadable:", e)
+PY
+    ;;
+  esac
+done
