@@ -566,7 +566,7 @@ def main():
         if "note" not in e2e:
             e2e["path"] = ("strict mode: the reference host's call pattern replayed against the C ABI "
                            "(host/rl_replay.cpp; app.rs:95-164, task_scheduler.rs:91-182): 524 288-photon "
-                           "TraceUnit::render calls queued to the resident trace service, every batch of records copied "
+                           "TraceUnit::render calls, each a launch that shares the SMs with the other units' launches, every batch of records copied "
                            "into the unit's host Vec, PlotUnit::plot / GatherUnit::accumulate consuming the units' "
                            "device copies, buffer.raw saved after every gather, tonemap at the end"
                            + ("; ranks' frames summed onto rank 0" if world > 1 else ""))

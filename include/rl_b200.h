@@ -67,8 +67,8 @@ typedef struct rl_mapped_photon {
  * A surface node is the state of one reference geometry struct after its
  * constructor ran (geometry.rs); compound nodes reference two children by
  * index into the same node array (geometry.rs:361-407).  Leaves of a compound
- * must be half-spaces (the only Surface + Volume type the built-in scene
- * combines, geometry.rs:409-416).
+ * are the reference's two Surface + Volume types: half-spaces (geometry.rs:
+ * 90-128) and spheres (geometry.rs:186-267).
  */
 typedef enum rl_surface_kind {
     RL_SURFACE_PLANE = 1,      /* geometry.rs:35-87    a = normal, b = offset                    */

@@ -25,7 +25,8 @@ typedef enum rl_builtin_scene {
     RL_SCENE_C1_SPHERE_PLANE = 1,  /* 1 diffuse sphere + emissive plane, static camera     */
     RL_SCENE_C2_BUILTIN = 2,       /* app.rs:166-363, 339 objects, orbit camera            */
     RL_SCENE_C3_PRISM = 3,         /* SF10 prism + emissive circle + grey floor            */
-    RL_SCENE_C4_SPHERES = 4        /* 4096 random spheres (param = sphere count, 0 = 4096) */
+    RL_SCENE_C4_SPHERES = 4,       /* 4096 random spheres (param = sphere count, 0 = 4096) */
+    RL_SCENE_C6_LENSES = 6         /* compounds over spheres and half-spaces (lens, dome, ...) */
 } rl_builtin_scene;
 
 int rl_scene_builder_create(rl_scene_builder **out);
@@ -35,6 +36,10 @@ int rl_scene_builder_builtin(rl_scene_builder *b, int which, uint32_t param);
 int rl_scene_builder_plane(rl_scene_builder *b, rl_vec3 normal, rl_vec3 offset);
 int rl_scene_builder_circle(rl_scene_builder *b, rl_vec3 normal, rl_vec3 position, float radius);
 int rl_scene_builder_sphere(rl_scene_builder *b, rl_vec3 position, float radius);
+/* SpacePartitioning::new (geometry.rs:99-106) and Compound::new (geometry.rs:369-378): the
+ * children of a compound are Volumes -- half-spaces, spheres or compounds of those. */
+int rl_scene_builder_halfspace(rl_scene_builder *b, rl_vec3 normal, rl_vec3 offset);
+int rl_scene_builder_compound(rl_scene_builder *b, uint32_t surface1, uint32_t surface2);
 int rl_scene_builder_paraboloid(rl_scene_builder *b, rl_vec3 normal, rl_vec3 offset,
                                 float focal_distance);
 int rl_scene_builder_prism(rl_scene_builder *b, rl_vec3 axis, rl_vec3 offset, float edge_length,

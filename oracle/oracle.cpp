@@ -307,10 +307,11 @@ struct SceneView {
     rl_camera_model camera;
 };
 
-// Volume::lies_inside: geometry.rs:124-128 (half-space), :403-407 (compound)
+// Volume::lies_inside: geometry.rs:124-128 (half-space), :263-267 (sphere), :403-407 (compound)
 bool lies_inside(const SceneView &sc, uint32_t node, V3 p) {
     const rl_surface &s = sc.surfaces[node];
     if (s.kind == RL_SURFACE_HALFSPACE) return dot(p - v3(s.b), v3(s.a)) < 0.0f;
+    if (s.kind == RL_SURFACE_SPHERE) return magnitude_squared(p - v3(s.a)) < s.s;
     return lies_inside(sc, s.child[0], p) && lies_inside(sc, s.child[1], p);
 }
 
@@ -764,7 +765,7 @@ void tonemap(const float *xyz, uint32_t width, uint32_t height, float max_intens
 bool is_volume(const SceneView &sc, uint32_t node, int depth) {
     if (node >= sc.n_surfaces || depth > 16) return false;
     const rl_surface &s = sc.surfaces[node];
-    if (s.kind == RL_SURFACE_HALFSPACE) return true;
+    if (s.kind == RL_SURFACE_HALFSPACE || s.kind == RL_SURFACE_SPHERE) return true;    // the two Volume leaves
     if (s.kind == RL_SURFACE_COMPOUND)
         return is_volume(sc, s.child[0], depth + 1) && is_volume(sc, s.child[1], depth + 1);
     return false;

@@ -83,6 +83,7 @@ SURFACE_PLANE, SURFACE_HALFSPACE, SURFACE_CIRCLE, SURFACE_SPHERE, SURFACE_PARABO
  MATERIAL_SF10_GLASS, MATERIAL_SOAP_BUBBLE) = range(1, 7)
 CAMERA_STATIC, CAMERA_ORBIT = 1, 2
 SCENE_C1, SCENE_C2, SCENE_C3, SCENE_C4 = 1, 2, 3, 4
+SCENE_C6 = 6        # compounds over spheres and half-spaces
 
 RL_OK, RL_ERR_INVALID, RL_ERR_UNSUPPORTED, RL_ERR_CUDA, RL_ERR_IO, RL_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 
@@ -168,6 +169,8 @@ HOST_SYMBOLS = {
     "rl_scene_builder_plane": (_I, [_P, Vec3, Vec3]),
     "rl_scene_builder_circle": (_I, [_P, Vec3, Vec3, C.c_float]),
     "rl_scene_builder_sphere": (_I, [_P, Vec3, C.c_float]),
+    "rl_scene_builder_halfspace": (_I, [_P, Vec3, Vec3]),
+    "rl_scene_builder_compound": (_I, [_P, _U32, _U32]),
     "rl_scene_builder_paraboloid": (_I, [_P, Vec3, Vec3, C.c_float]),
     "rl_scene_builder_prism": (_I, [_P, Vec3, Vec3, C.c_float, C.c_float, C.c_float]),
     "rl_scene_builder_hexagonal_prism": (_I, [_P, Vec3, Vec3, C.c_float, C.c_float, C.c_float, C.c_float]),
@@ -286,6 +289,12 @@ class SceneBuilder:
 
     def sphere(self, position, radius):
         return self._idx(host_lib().rl_scene_builder_sphere(self._h, vec3(*position), radius))
+
+    def halfspace(self, normal, offset):
+        return self._idx(host_lib().rl_scene_builder_halfspace(self._h, vec3(*normal), vec3(*offset)))
+
+    def compound(self, surface1, surface2):
+        return self._idx(host_lib().rl_scene_builder_compound(self._h, surface1, surface2))
 
     def paraboloid(self, normal, offset, focal_distance):
         return self._idx(host_lib().rl_scene_builder_paraboloid(self._h, vec3(*normal), vec3(*offset), focal_distance))

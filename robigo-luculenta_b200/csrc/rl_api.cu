@@ -316,6 +316,7 @@ namespace {
 struct Flat {
     std::vector<float4> spheres, sphere_k, planes, paraboloids, leaves, compounds;
     double cmax2 = 0.0, leaf_off_max = 0.0;
+    bool sphere_leaves = false;
     std::vector<uint32_t> ops, sphere_obj, plane_obj, paraboloid_obj, compound_obj;
 };
 
@@ -341,6 +342,16 @@ bool emit_compound(const rl_scene_desc *d, uint32_t node, Flat &fl, uint32_t fir
         lo = rel; hi = rel + 1;
         return true;
     }
+    if (s.kind == RL_SURFACE_SPHERE) {                      // the other Volume leaf (geometry.rs:263-267)
+        uint32_t rel = (uint32_t)(fl.leaves.size() / 2) - first_leaf;
+        if (rel > 254) return false;
+        fl.leaves.push_back(make_float4(0.f, 0.f, 0.f, 0.f));   // w == 0 marks a sphere leaf; n = 0 keeps it out of the slab test
+        fl.leaves.push_back(f4(s.a, s.s));
+        fl.sphere_leaves = true;
+        fl.ops.push_back(0u | (rel << 8));
+        lo = rel; hi = rel + 1;
+        return true;
+    }
     if (s.kind != RL_SURFACE_COMPOUND) return false;
     uint32_t lo1, hi1, lo2, hi2;
     if (!emit_compound(d, s.child[0], fl, first_leaf, depth + 1, lo1, hi1)) return false;
@@ -360,12 +371,15 @@ bool convex_bound(const std::vector<float4> &leaves, size_t first, size_t n, flo
     struct D3 { double x, y, z; };
     auto dot3 = [](D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; };
     auto cross3 = [](D3 a, D3 b) { return D3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; };
-    std::vector<D3> nrm(n), off(n);
-    for (size_t i = 0; i < n; i++) {
+    std::vector<D3> nrm, off;
+    const size_t n_all = n;
+    for (size_t i = 0; i < n_all; i++) {
         const float4 a = leaves[2 * (first + i)], b = leaves[2 * (first + i) + 1];
-        nrm[i] = D3{a.x, a.y, a.z};
-        off[i] = D3{b.x, b.y, b.z};
+        if (a.w == 0.0f) continue;                          // sphere leaves bound the body by themselves (sphere_leaf_bound)
+        nrm.push_back(D3{a.x, a.y, a.z});
+        off.push_back(D3{b.x, b.y, b.z});
     }
+    n = nrm.size();
     // unbounded iff the recession cone {u : n_i.u <= 0} is non-trivial; its extreme rays are
     // cross products of normal pairs (a cone containing a line leaves no vertices at all)
     for (size_t i = 0; i < n; i++)
@@ -413,6 +427,18 @@ bool convex_bound(const std::vector<float4> &leaves, size_t first, size_t n, flo
     r = r * 1.01 + 0.05;
     out = make_float4((float)c.x, (float)c.y, (float)c.z, (float)(r * r));
     return true;
+}
+
+// A body with sphere leaves lies inside each of them: the smallest (inflated like the polytope
+// bound) replaces `out` when it is tighter or when the half-spaces alone leave the body unbounded.
+void sphere_leaf_bound(const std::vector<float4> &leaves, size_t first, size_t n, float4 &out) {
+    for (size_t i = 0; i < n; i++) {
+        const float4 a = leaves[2 * (first + i)], b = leaves[2 * (first + i) + 1];
+        if (a.w != 0.0f) continue;
+        const double r = sqrt(fmax(0.0, (double)b.w)) * 1.01 + 0.05;
+        if (!std::isfinite(r)) continue;
+        if (out.w < 0.0f || r * r < (double)out.w) out = make_float4(b.x, b.y, b.z, (float)(r * r));
+    }
 }
 
 // Sphere clusters for the two-level pre-test: recursive median split of the
@@ -474,12 +500,16 @@ int env_int(const char *name, int fallback) {
     return v && *v ? atoi(v) : fallback;
 }
 
-// Batches below this size are queued to the scene's dispatcher (RL_TRACE_GROUPS=0: never).  The
-// same bound as the small-launch rule of launch_trace: fewer than 64 photons per thread of a
-// full grid -- larger requests fill the GPU on their own.
+// With RL_TRACE_GROUPS=1, batches below this size are queued to the scene's dispatcher.  The same
+// bound as the small-launch rule of launch_trace: fewer than 64 photons per thread of a full
+// grid -- larger requests fill the GPU on their own.  Off by default: measured on the scheduler
+// replay (profiles/r2_dispatch_sweep*.txt), one launch per batch with the launches sharing the
+// SMs' block slots (launch_trace) keeps the pipeline finer-grained -- a batch's records start
+// their way to the host the moment ITS launch ends, not when the whole group's does -- and
+// reaches 98.7 % of the one-launch rate in the steady state, against 75-90 % with groups.
 bool use_dispatcher(const rl_scene *scene, uint64_t n_photons) {
     if (n_photons == 0 || n_photons >= (1ull << RL_SEGMENT_INDEX_BITS)) return false;
-    if (scene->dispatcher.failed || !env_int("RL_TRACE_GROUPS", 1)) return false;
+    if (scene->dispatcher.failed || !env_int("RL_TRACE_GROUPS", 0)) return false;
     return n_photons < 64ull * (uint64_t)scene->dev.sm_count * 768ull;
 }
 
@@ -661,7 +691,7 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
             uint32_t lo, hi;
             if (!emit_compound(desc, o.surface, fl, first_leaf, 0, lo, hi))
                 return fail(RL_ERR_UNSUPPORTED,
-                            "compound surfaces must be trees of half-spaces (<= 255 leaves)");
+                            "compound surfaces must be trees of half-spaces and spheres (<= 255 leaves)");
             uint32_t n_ops = (uint32_t)fl.ops.size() - first_op;
             if (max_stack(fl.ops, first_op, n_ops) > RL_MAX_COMPOUND_STACK)
                 return fail(RL_ERR_UNSUPPORTED, "compound tree too deep");
@@ -669,6 +699,7 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
                                                as_float(first_op), as_float(n_ops)));
             float4 bound = make_float4(0.f, 0.f, 0.f, -1.0f);          // r^2 < 0: unbounded, never culled
             convex_bound(fl.leaves, first_leaf, hi - lo, bound);
+            sphere_leaf_bound(fl.leaves, first_leaf, hi - lo, bound);
             fl.compounds.push_back(bound);
             fl.compound_obj.push_back(i);
             break;
@@ -703,6 +734,7 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
         // per cluster, more for large scenes (balances the uniform cluster scan against it)
         size_t leaf = (size_t)(0.45 * sqrt((double)n) + 0.5);
         leaf = leaf < 8 ? 8 : (leaf > 32 ? 32 : leaf);
+        if (env_int("RL_CLUSTER_LEAF", 0) > 0) leaf = (size_t)env_int("RL_CLUSTER_LEAF", 0);   // experiments
         if (leaf < (n + 999) / 1000) leaf = (n + 999) / 1000;   // pair records index clusters with 11 bits
         if (n) split_spheres(fl.spheres, idx, 0, n, leaf, cl);
         std::vector<float4> spheres(n), sphere_k(n);
@@ -783,6 +815,7 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     ds.sphere_cmax2 = (float)(fl.cmax2 * 1.0001);
     ds.cluster_rmax = (float)(cluster_rmax * 1.0001);
     ds.leaf_off_max = (float)(fl.leaf_off_max * 1.0001);
+    ds.sphere_leaves = fl.sphere_leaves ? 1u : 0u;
     ds.off_plane_obj = append(blob, fl.plane_obj);
     ds.off_paraboloid_obj = append(blob, fl.paraboloid_obj);
     ds.off_compound_obj = append(blob, fl.compound_obj);

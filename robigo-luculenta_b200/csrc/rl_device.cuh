@@ -50,19 +50,29 @@ struct PrimTables {
     uint32_t plane_obj, paraboloid_obj, compound_obj;
     uint32_t scratch;         // per-block scratch behind the blob (see Scratch)
     uint32_t n_spheres, n_clusters, n_planes, n_paraboloids, n_compounds;
+    uint32_t sphere_leaves;   // some compound has a sphere leaf
     float sphere_cmax2, cluster_rmax, leaf_off_max, body_rmax;
 };
 
 #define RL_TABLES_VEC4 ((sizeof(PrimTables) + 15) / 16)
+#ifndef RL_TASK_STEAL
+#define RL_TASK_STEAL 0      // 1: body tasks are taken 32 at a time by whichever warp gets there; 0: dealt by thread index (no difference measured)
+#endif
+#ifndef RL_BODIES_FIRST
+// 1: the bodies' bound scan and slab tests run before the sphere phase, which then runs beside
+// the body evaluation (between the two block barriers); 0: sphere phase first, so that sphere
+// hits prune the bodies too.  Measured on the built-in scene: 2770 vs 2971 Mrays/s.
+#define RL_BODIES_FIRST 0
+#endif
 #define RL_CAND_SLOTS 8        // queued sphere candidates per lane
 #define RL_COMPOUND_SLOTS 4    // body results per lane, and body tasks per thread of the block list
 #define RL_PAIR_CAP 768        // (lane, cluster) or (lane, body) pairs per warp and round
 #define RL_BODIES_PER_ROUND 64  // bodies whose bounds one scan covers (one bit each of a lane's candidate mask)
-// scratch bytes per thread: ray table 48; one 32-byte area that is the sphere queue (sphere
-// phase), then the body results (body phase); block task list 4 per slot; three counters 12;
-// pair list 2 * RL_PAIR_CAP / 32
-#define RL_SCRATCH_BYTES_PER_THREAD (48 + 32 + 4 * RL_COMPOUND_SLOTS + 12 + 2 * RL_PAIR_CAP / 32)
-static_assert(2 * RL_CAND_SLOTS <= 32 && 8 * RL_COMPOUND_SLOTS <= 32, "shared 32-byte area");
+// scratch bytes per thread: ray table 48; sphere queue 2 per slot; three counters 12; pair list
+// 2 * RL_PAIR_CAP / 32; body results 8 per slot; block task list 4 per slot.  (The sphere queue
+// and the body results are separate areas: one warp's sphere phase runs beside another warp's
+// body evaluation.)
+#define RL_SCRATCH_BYTES_PER_THREAD (48 + 2 * RL_CAND_SLOTS + 12 + 2 * RL_PAIR_CAP / 32 + 8 * RL_COMPOUND_SLOTS + 4 * RL_COMPOUND_SLOTS)
 static_assert(RL_PAIR_INDEX_BITS + 5 <= 16, "a pair record is a lane (5 bits) and a table index in 16 bits");
 
 __device__ __forceinline__ const PrimTables &tables() {
@@ -100,6 +110,7 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         t.n_planes = sc.n_planes;
         t.n_paraboloids = sc.n_paraboloids;
         t.n_compounds = sc.n_compounds;
+        t.sphere_leaves = sc.sphere_leaves;
         t.sphere_cmax2 = sc.sphere_cmax2;
         t.cluster_rmax = sc.cluster_rmax;
         t.leaf_off_max = sc.leaf_off_max;
@@ -109,18 +120,23 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
     // zero the scratch counters (same layout as in intersect_scene)
     {
         float4 *ray_tab = rl_smem + base + sc.smem_vec4;
-        float2 *results = reinterpret_cast<float2 *>(ray_tab + 3 * blockDim.x);
-        uint32_t *counters = reinterpret_cast<uint32_t *>(results + RL_COMPOUND_SLOTS * blockDim.x)
-                             + RL_COMPOUND_SLOTS * blockDim.x;
+        uint16_t *sq_base = reinterpret_cast<uint16_t *>(ray_tab + 3 * blockDim.x);
+        uint32_t *counters = reinterpret_cast<uint32_t *>(sq_base + RL_CAND_SLOTS * blockDim.x);
         for (uint32_t k = threadIdx.x; k < 3 * blockDim.x; k += blockDim.x) counters[k] = 0u;
     }
     __syncthreads();
 }
 
+// A scene without compound bodies never touches the body results and the task list, which are
+// the last two areas of the scratch: it does not pay for them (4096 spheres keep 768 threads).
+__host__ __device__ __forceinline__ uint32_t scratch_bytes_per_thread(uint32_t n_compounds) {
+    return RL_SCRATCH_BYTES_PER_THREAD - (n_compounds ? 0u : 12u * RL_COMPOUND_SLOTS);
+}
+
 // Shared memory a tracing kernel needs with `threads` threads per block.
 inline size_t tracing_smem_bytes(const DevScene &sc, int threads) {
     return (RL_TABLES_VEC4 + (size_t)sc.smem_vec4) * sizeof(float4)
-           + (size_t)RL_SCRATCH_BYTES_PER_THREAD * threads;
+           + (size_t)scratch_bytes_per_thread(sc.n_compounds) * threads;
 }
 
 // ---------------------------------------------------------------------- RNG
@@ -336,11 +352,23 @@ __device__ __forceinline__ float paraboloid_t(const float4 *p, const Ray &ray) {
     return -1.0f;
 }
 
-// geometry.rs:380-407 for trees whose leaves are half-spaces: the post-order
-// program replays the reference's recursion with an explicit stack.
+// geometry.rs:380-407 for trees whose leaves are the reference's two Volume
+// types, half-spaces (geometry.rs:90-128) and spheres (geometry.rs:186-267): the
+// post-order program replays the reference's recursion with an explicit stack.
+// A leaf is two float4: half-space {n, max(1, |n|)} {offset, 0}; sphere
+// {0, 0, 0, 0} {centre, r^2} -- the w of the first record tells them apart, and
+// the zero "normal" makes a sphere leaf drop out of the slab test by itself.
 // op word: bits 0-1 kind (0 = leaf, 1 = compound); leaf: bits 8.. = leaf index
 // relative to the compound's first leaf; compound: lo = bits 8-15, mid = bits
 // 16-23, hi = bits 24-31 (children own leaves [lo, mid) and [mid, hi)).
+// Volume::lies_inside of a leaf: geometry.rs:124-128 (half-space), :263-267 (sphere)
+template <bool SPHERES>
+__device__ __forceinline__ bool leaf_contains(float4 n4, float4 o4, V3 pos) {
+    if (SPHERES && n4.w == 0.0f) return magnitude_squared(pos - mk(o4.x, o4.y, o4.z)) < o4.w;
+    return dot(pos - mk(o4.x, o4.y, o4.z), mk(n4.x, n4.y, n4.z)) < 0.0f;
+}
+
+template <bool SPHERES>
 static __device__ __forceinline__ float2 compound_call(uint32_t first_leaf, uint32_t first_op, uint32_t n_ops,
                                                     float ox, float oy, float oz, float dx, float dy, float dz) {
     Ray ray;
@@ -361,7 +389,8 @@ static __device__ __forceinline__ float2 compound_call(uint32_t first_leaf, uint
             const uint32_t leaf = first_leaf + (op >> 8);
             const float4 n4 = leaves[2 * leaf], o4 = leaves[2 * leaf + 1];
             float d;
-            const float t = plane_t(mk(n4.x, n4.y, n4.z), mk(o4.x, o4.y, o4.z), ray, d);
+            const float t = (SPHERES && n4.w == 0.0f) ? sphere_t(o4, ray)
+                                         : plane_t(mk(n4.x, n4.y, n4.z), mk(o4.x, o4.y, o4.z), ray, d);
             t4 = t3; l4 = l3; t3 = t2; l3 = l2; t2 = t1; l2 = l1; t1 = t0; l1 = l0;
             t0 = t; l0 = leaf;
         } else {
@@ -374,16 +403,14 @@ static __device__ __forceinline__ float2 compound_call(uint32_t first_leaf, uint
                 const V3 pos = ray.origin + ray.direction * b1;
 #pragma unroll 1
                 for (uint32_t k = mid; k < hi; k++) {
-                    const float4 n4 = leaves[2 * k], o4 = leaves[2 * k + 1];
-                    if (!(dot(pos - mk(o4.x, o4.y, o4.z), mk(n4.x, n4.y, n4.z)) < 0.0f)) { b1 = -1.0f; break; }
+                    if (!leaf_contains<SPHERES>(leaves[2 * k], leaves[2 * k + 1], pos)) { b1 = -1.0f; break; }
                 }
             }
             if (b2 > 0.0f) {  // surface1.lies_inside(i2.position)
                 const V3 pos = ray.origin + ray.direction * b2;
 #pragma unroll 1
                 for (uint32_t k = lo; k < mid; k++) {
-                    const float4 n4 = leaves[2 * k], o4 = leaves[2 * k + 1];
-                    if (!(dot(pos - mk(o4.x, o4.y, o4.z), mk(n4.x, n4.y, n4.z)) < 0.0f)) { b2 = -1.0f; break; }
+                    if (!leaf_contains<SPHERES>(leaves[2 * k], leaves[2 * k + 1], pos)) { b2 = -1.0f; break; }
                 }
             }
             // both valid: the nearer, ties to surface2 (geometry.rs:391-396); else whichever is valid
@@ -395,11 +422,18 @@ static __device__ __forceinline__ float2 compound_call(uint32_t first_leaf, uint
     return make_float2(t0, __uint_as_float(l0));
 }
 
-// One shared out-of-line copy of the interpreter (three call sites).
-__device__ __forceinline__ float compound_t(uint32_t first_leaf, uint32_t first_op, uint32_t n_ops,
-                                            const Ray &ray, uint32_t &leaf_out) {
-    const float2 r = compound_call(first_leaf, first_op, n_ops, ray.origin.x, ray.origin.y, ray.origin.z,
-                                   ray.direction.x, ray.direction.y, ray.direction.z);
+// Compound::intersect for the body described by the record c4 = {first_leaf, n_leaves, first_op,
+// n_ops}.  The evaluation sits on the critical path of the whole block (every warp waits at a
+// barrier for the threads that evaluate bodies), and the leaf-kind tests cost 4 % of the kernel's
+// time on the built-in scene when they are compiled in: a scene without sphere leaves (block-
+// uniform flag) runs the copy without them.
+__device__ __forceinline__ float compound_t(float4 c4, const Ray &ray, uint32_t &leaf_out) {
+    const uint32_t first_leaf = __float_as_uint(c4.x), first_op = __float_as_uint(c4.z), n_ops = __float_as_uint(c4.w);
+    const float2 r = tables().sphere_leaves
+                         ? compound_call<true>(first_leaf, first_op, n_ops, ray.origin.x, ray.origin.y, ray.origin.z,
+                                               ray.direction.x, ray.direction.y, ray.direction.z)
+                         : compound_call<false>(first_leaf, first_op, n_ops, ray.origin.x, ray.origin.y, ray.origin.z,
+                                                ray.direction.x, ray.direction.y, ray.direction.z);
     leaf_out = __float_as_uint(r.y);
     return r.x;
 }
@@ -450,7 +484,7 @@ __device__ __forceinline__ Hit intersect_scene_brute(const Ray &ray) {
     for (uint32_t i = 0; i < tb.n_compounds; i++) {
         const float4 c4 = compounds[2 * i];
         uint32_t leaf;
-        const float t = compound_t(__float_as_uint(c4.x), __float_as_uint(c4.z), __float_as_uint(c4.w), ray, leaf);
+        const float t = compound_t(c4, ray, leaf);
         if (t > 0.0f) consider(best, t, (int)compound_obj[i], (RL_HIT_LEAF << 28) | leaf);
     }
     return best;
@@ -561,6 +595,16 @@ __device__ __forceinline__ uint32_t emit_pairs(uint64_t &todo, uint32_t base, ui
 // side by side in full warps.  Unbounded bodies carry r^2 < 0 and always pass
 // the bounding test.
 //
+// Order of the work, chosen for the block barriers of the body evaluation: flat surfaces
+// first (their hit bounds the bodies worth evaluating), then the bodies' bound scan and slab
+// tests, which fill the block's task list; behind the first barrier every warp runs its sphere
+// phase and THEN takes tasks from the list, 32 at a time, until it is empty -- the warps with the
+// least sphere work (or no live lane at all) arrive first and take the tasks, so the two phases
+// balance each other and the second barrier, behind which the body results are merged, is
+// reached by all warps at about the same time.  (With the tasks dealt statically to the first
+// warps and the sphere phase in front of the first barrier, 21 % of all warp cycles were spent
+// waiting at these two barriers.)
+//
 // Must be called by every thread of the block together (block barriers and
 // warp votes inside), with a block barrier between two consecutive calls;
 // threads without a live path pass idle_ray() and
@@ -581,30 +625,33 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
     const float thr = -7.6293945e-6f * scale;                                          // -2^-17 * scale
     const float bthr = -1.9073486e-6f * sqrtf((tb.sphere_cmax2 + oo) * dd) - 1.0e-30f;  // -2^-19 * ...
 
-    // Scratch views (per block): ray table [3 float4 per thread]; a 32-byte-per-thread area used
-    // in turn as private cluster queue [slot][thread], sphere queue [slot][thread] and body
-    // results [slot][thread] (distance, code); block task list [RL_COMPOUND_SLOTS per thread];
-    // counters [3][thread]; pair list [RL_PAIR_CAP per warp].
+    // Scratch views (per block, see RL_SCRATCH_BYTES_PER_THREAD): ray table [3 float4 per
+    // thread]; sphere queue [slot][thread]; counters [3][thread]; pair list [RL_PAIR_CAP per warp];
+    // body results [slot][thread] (distance, code) and the block's task list.
     const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
     const uint32_t lane = tid & 31u, wbase = tid & ~31u;
     float4 *ray_tab = rl_smem + tb.scratch;
-    float2 *results = reinterpret_cast<float2 *>(ray_tab + 3 * nthreads);
-    uint16_t *lq_base = reinterpret_cast<uint16_t *>(results);  // same area, sphere phase
-    uint16_t *sq_base = lq_base;                                // same area, after the cluster queues are drained
-    uint32_t *btasks = reinterpret_cast<uint32_t *>(results + RL_COMPOUND_SLOTS * nthreads);
-    uint32_t *sq_cnt = btasks + RL_COMPOUND_SLOTS * nthreads;
+    uint16_t *sq_base = reinterpret_cast<uint16_t *>(ray_tab + 3 * nthreads);
+    uint32_t *sq_cnt = reinterpret_cast<uint32_t *>(sq_base + RL_CAND_SLOTS * nthreads);
     uint16_t *pairs = reinterpret_cast<uint16_t *>(sq_cnt + 3 * nthreads) + (wbase >> 5) * RL_PAIR_CAP;
-    // publish this lane's pre-test constants so that any lane of the warp can test a sphere for it
+    float2 *results = reinterpret_cast<float2 *>(reinterpret_cast<uint16_t *>(sq_cnt + 3 * nthreads)
+                                                 + (nthreads >> 5) * RL_PAIR_CAP);
+    uint32_t *btasks = reinterpret_cast<uint32_t *>(results + RL_COMPOUND_SLOTS * nthreads);
+    // publish this lane's pre-test constants so that any lane of the block can test for it
     ray_tab[3 * tid + 0] = make_float4(m2ox, m2oy, m2oz, oo);
     ray_tab[3 * tid + 1] = make_float4(d.x, d.y, d.z, ndo);
-    ray_tab[3 * tid + 2] = make_float4(thr, bthr, 0.0f,
-                                       fmaf(RL_SLAB_INFLATE_REL, sqrtf(oo) + tb.leaf_off_max, RL_SLAB_INFLATE));
     uint32_t *res_cnt = sq_cnt + nthreads;                      // results other threads computed for this one
-    uint32_t *bcount = sq_cnt + 2 * nthreads;                   // [0]: entries in the block task list
+    uint32_t *bcount = sq_cnt + 2 * nthreads;                   // [0]: entries in the block task list, [1]: entries taken
     sq_cnt[tid] = 0u;
-    res_cnt[tid] = 0u;
 
-    // Two-level scan.  Level 1, uniform over the warp: the same pre-test against the bounding
+    const float slack = -2.0f * thr + 2.0f * fabsf(dd - 1.0f) * (tb.sphere_cmax2 + oo);
+    const bool warp_live = __any_sync(0xffffffffu, live);       // warp-uniform
+
+    if (warp_live) intersect_flat_surfaces(tb, ray, best);
+    ray_tab[3 * tid + 2] = make_float4(thr, bthr, best.t,       // .z: nearest hit so far, bodies beyond it are skipped
+                                       fmaf(RL_SLAB_INFLATE_REL, sqrtf(oo) + tb.leaf_off_max, RL_SLAB_INFLATE));
+
+    // Two-level sphere scan.  Level 1, uniform over the warp: the same pre-test against the bounding
     // sphere {m, R} of each cluster of spheres, with thresholds widened so that a cluster is
     // kept whenever the reference could accept one of its members: a member i the reference
     // accepts has r_i^2 - dist(line, c_i)^2 >= -S/2 with S = 2 e1 + 2 |dd - 1| (cmax2 + |o|^2)
@@ -613,71 +660,81 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
     // R^2 - dist(line, m)^2 >= -(2 R sqrt(S/2) + S/2); B_cluster >= B_i - |d| R.
     // A lane's candidates are bits of a register (scan_bounds); the warp's (lane, cluster) pairs
     // are then listed in shared memory (emit_pairs).
-    const float4 *spheres = tb.spheres;
-    const float4 *sphere_k = sm_vec(tb.sphere_k);
-    const float4 *clusters = sm_vec(tb.clusters);
-    const uint32_t *cluster_range = sm_u32(tb.cluster_range);
-    const uint32_t *sphere_obj = tb.sphere_obj;
-    const uint32_t n_clusters = tb.n_clusters;
-    const float slack = -2.0f * thr + 2.0f * fabsf(dd - 1.0f) * (tb.sphere_cmax2 + oo);
-    const float thr_c = -(2.0f * tb.cluster_rmax * sqrtf(slack) + 2.0f * slack);
-    const float bthr_c = bthr - sqrtf(dd) * tb.cluster_rmax;
-    const bool warp_live = __any_sync(0xffffffffu, live);       // warp-uniform
+    auto sphere_phase = [&]() {
+        const float4 *spheres = tb.spheres;
+        const float4 *sphere_k = sm_vec(tb.sphere_k);
+        const float4 *clusters = sm_vec(tb.clusters);
+        const uint32_t *cluster_range = sm_u32(tb.cluster_range);
+        const uint32_t *sphere_obj = tb.sphere_obj;
+        const uint32_t n_clusters = tb.n_clusters;
+        const float thr_c = -(2.0f * tb.cluster_rmax * sqrtf(slack) + 2.0f * slack);
+        const float bthr_c = bthr - sqrtf(dd) * tb.cluster_rmax;
 #pragma unroll 1
-    for (uint32_t base = 0; warp_live && base < n_clusters; base += 64) {
-        uint64_t todo = scan_bounds(clusters + base, min(64u, n_clusters - base), d, ndo, m2ox, m2oy, m2oz, oo,
-                                    thr_c, bthr_c);
-        while (__any_sync(0xffffffffu, todo != 0ull)) {
-            const uint32_t npairs = emit_pairs(todo, base, pairs, lane);
-            // Level 2, warp-cooperative: eight lanes take one (lane, cluster) pair and test one
-            // member each with the owner's constants, so the work of lanes with many candidate
-            // clusters is spread over the warp; survivors go to the owner's sphere queue.
+        for (uint32_t base = 0; warp_live && base < n_clusters; base += 64) {
+            uint64_t todo = scan_bounds(clusters + base, min(64u, n_clusters - base), d, ndo, m2ox, m2oy, m2oz, oo,
+                                        thr_c, bthr_c);
+            while (__any_sync(0xffffffffu, todo != 0ull)) {
+                const uint32_t npairs = emit_pairs(todo, base, pairs, lane);
+                // Level 2, warp-cooperative: eight lanes take one (lane, cluster) pair and test one
+                // member each with the owner's constants, so the work of lanes with many candidate
+                // clusters is spread over the warp; survivors go to the owner's sphere queue.
 #pragma unroll 1
-            for (uint32_t pb = 0; pb < npairs; pb += 4) {
-                const uint32_t p = pb + (lane >> 3);
-                if (p < npairs) {
-                    const uint32_t pair = pairs[p];
-                    const uint32_t owner = wbase + (pair >> RL_PAIR_INDEX_BITS);
-                    const uint32_t r = cluster_range[pair & RL_PAIR_INDEX_MAX];
-                    const uint32_t end = (r & 0xffffu) + (r >> 16);
-                    const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1], rt = ray_tab[3 * owner + 2];
+                for (uint32_t pb = 0; pb < npairs; pb += 4) {
+                    const uint32_t p = pb + (lane >> 3);
+                    if (p < npairs) {
+                        const uint32_t pair = pairs[p];
+                        const uint32_t owner = wbase + (pair >> RL_PAIR_INDEX_BITS);
+                        const uint32_t r = cluster_range[pair & RL_PAIR_INDEX_MAX];
+                        const uint32_t end = (r & 0xffffu) + (r >> 16);
+                        const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1];
+                        const float2 rt = *reinterpret_cast<const float2 *>(&ray_tab[3 * owner + 2]);
 #pragma unroll 1
-                    for (uint32_t m = (r & 0xffffu) + (lane & 7u); m < end; m += 8) {
-                        const float4 s = sphere_k[m];               // {cx, cy, cz, |c|^2 - r^2}
-                        const float b = fmaf(rd.x, s.x, fmaf(rd.y, s.y, fmaf(rd.z, s.z, rd.w)));
-                        const float c = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w))) + ro.w;
-                        const float disc = fmaf(b, b, -c);
-                        if (disc >= rt.x && b >= rt.y) {
-                            const uint32_t slot = atomicAdd(&sq_cnt[owner], 1u);
-                            if (slot < RL_CAND_SLOTS) sq_base[slot * nthreads + owner] = (uint16_t)m;
+                        for (uint32_t m = (r & 0xffffu) + (lane & 7u); m < end; m += 8) {
+                            const float4 s = sphere_k[m];               // {cx, cy, cz, |c|^2 - r^2}
+                            const float b = fmaf(rd.x, s.x, fmaf(rd.y, s.y, fmaf(rd.z, s.z, rd.w)));
+                            const float c = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w))) + ro.w;
+                            const float disc = fmaf(b, b, -c);
+                            if (disc >= rt.x && b >= rt.y) {
+                                const uint32_t slot = atomicAdd(&sq_cnt[owner], 1u);
+                                if (slot < RL_CAND_SLOTS) sq_base[slot * nthreads + owner] = (uint16_t)m;
+                            }
                         }
                     }
                 }
-            }
-            __syncwarp();
-            // Level 3, per lane: exact Sphere::intersect for the candidates queued for this lane
-            const uint32_t cnt = sq_cnt[tid];
-            if (cnt > RL_CAND_SLOTS) {
-                // more candidates than slots (pathological): evaluate every sphere exactly
+                __syncwarp();
+                // Level 3, per lane: exact Sphere::intersect for the candidates queued for this lane
+                const uint32_t cnt = sq_cnt[tid];
+                if (cnt > RL_CAND_SLOTS) {
+                    // more candidates than slots (pathological): evaluate every sphere exactly
 #pragma unroll 1
-                for (uint32_t k = 0; k < tb.n_spheres; k++) {
-                    const float t = sphere_t(__ldg(spheres + k), ray);
-                    if (t > 0.0f) consider(best, t, (int)__ldg(sphere_obj + k), (RL_HIT_SPHERE << 28) | k);
-                }
-            } else {
+                    for (uint32_t k = 0; k < tb.n_spheres; k++) {
+                        const float t = sphere_t(__ldg(spheres + k), ray);
+                        if (t > 0.0f) consider(best, t, (int)__ldg(sphere_obj + k), (RL_HIT_SPHERE << 28) | k);
+                    }
+                } else {
 #pragma unroll 1
-                for (uint32_t k = 0; k < cnt; k++) {
-                    const uint32_t idx = sq_base[k * nthreads + tid];
-                    const float t = sphere_t(__ldg(spheres + idx), ray);
-                    if (t > 0.0f) consider(best, t, (int)__ldg(sphere_obj + idx), (RL_HIT_SPHERE << 28) | idx);
+                    for (uint32_t k = 0; k < cnt; k++) {
+                        const uint32_t idx = sq_base[k * nthreads + tid];
+                        const float t = sphere_t(__ldg(spheres + idx), ray);
+                        if (t > 0.0f) consider(best, t, (int)__ldg(sphere_obj + idx), (RL_HIT_SPHERE << 28) | idx);
+                    }
                 }
+                sq_cnt[tid] = 0u;
+                __syncwarp();
             }
-            sq_cnt[tid] = 0u;
-            __syncwarp();
         }
-    }
+    };
 
-    if (warp_live) intersect_flat_surfaces(tb, ray, best);
+    const uint32_t n_compounds = tb.n_compounds;
+    if (n_compounds == 0u) {                                    // block-uniform: a scene without bodies has no barrier here
+        sphere_phase();
+        return best;
+    }
+    res_cnt[tid] = 0u;
+#if !RL_BODIES_FIRST
+    sphere_phase();
+    ray_tab[3 * tid + 2].z = best.t;                            // sphere hits bound the bodies worth evaluating too
+#endif
 
     // Compound bodies (block-wide; every thread of the block calls intersect_scene together).
     //  1. bounding spheres: the same uniform scan over the bodies' bound records; a hit the
@@ -687,17 +744,15 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
     //     Unbounded bodies are flagged in a mask that is OR-ed in;
     //  2. slab test warp-cooperatively: eight lanes per pair, one leaf each, shuffle reduction of
     //     the interval; survivors are appended to ONE task list per block;
-    //  3. after a block barrier the threads take one task each -- the reference's recursion
+    //  3. after a block barrier the warps take the tasks 32 at a time -- the reference's recursion
     //     (compound_t) for the owner's ray -- so the few rays of a block that really meet a body
     //     are evaluated side by side in full warps instead of two or three lanes per warp;
     //  4. after a second barrier every thread merges the results computed for its ray.
-    ray_tab[3 * tid + 2].z = best.t;                            // nearest hit so far: bodies beyond it are skipped
     const float4 *compounds = sm_vec(tb.compounds);
     const float4 *body_bounds = sm_vec(tb.body_bounds);
     const uint64_t *body_always = reinterpret_cast<const uint64_t *>(rl_smem + tb.body_always);
     const float4 *leaves = sm_vec(tb.leaves);
     const uint32_t *compound_obj = sm_u32(tb.compound_obj);
-    const uint32_t n_compounds = tb.n_compounds;
     const uint32_t group = lane >> 3, sub = lane & 7u;
     const uint32_t task_cap = RL_COMPOUND_SLOTS * nthreads;
     const float thr_b = -slack;
@@ -709,66 +764,79 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
             todo = scan_bounds(body_bounds + round, (round_end - round + 7u) & ~7u, d, ndo, m2ox, m2oy, m2oz, oo,
                                thr_b, bthr_b) | body_always[round / RL_BODIES_PER_ROUND];
         while (__any_sync(0xffffffffu, todo != 0ull)) {
-        const uint32_t npairs = emit_pairs(todo, round, pairs, lane);
+            const uint32_t npairs = emit_pairs(todo, round, pairs, lane);
 #pragma unroll 1
-        for (uint32_t pb = 0; pb < npairs; pb += 4) {
-            const uint32_t p = pb + group;
-            const bool valid = p < npairs;                      // uniform within a group of eight
-            const uint32_t pair = valid ? pairs[p] : 0u;
-            const uint32_t owner = wbase + (pair >> RL_PAIR_INDEX_BITS), body = pair & RL_PAIR_INDEX_MAX;
-            const float4 c4 = compounds[2 * body];
-            const uint32_t first_leaf = __float_as_uint(c4.x);
-            const uint32_t n_leaves = valid ? __float_as_uint(c4.y) : 0u;
-            const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1];
-            const float2 bi = *reinterpret_cast<const float2 *>(&ray_tab[3 * owner + 2].z);
-            const float best_t = bi.x, inflate = bi.y;
-            const float ox = -0.5f * ro.x, oy = -0.5f * ro.y, oz = -0.5f * ro.z;   // ro = -2 o, exactly
-            // the slab test, one leaf per lane
-            float t_enter = 0.0f, t_exit = 3.0e38f;
-            bool outside_parallel = false;
+            for (uint32_t pb = 0; pb < npairs; pb += 4) {
+                const uint32_t p = pb + group;
+                const bool valid = p < npairs;                      // uniform within a group of eight
+                const uint32_t pair = valid ? pairs[p] : 0u;
+                const uint32_t owner = wbase + (pair >> RL_PAIR_INDEX_BITS), body = pair & RL_PAIR_INDEX_MAX;
+                const float4 c4 = compounds[2 * body];
+                const uint32_t first_leaf = __float_as_uint(c4.x);
+                const uint32_t n_leaves = valid ? __float_as_uint(c4.y) : 0u;
+                const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1];
+                const float2 bi = *reinterpret_cast<const float2 *>(&ray_tab[3 * owner + 2].z);
+                const float best_t = bi.x, inflate = bi.y;
+                const float ox = -0.5f * ro.x, oy = -0.5f * ro.y, oz = -0.5f * ro.z;   // ro = -2 o, exactly
+                // the slab test, one leaf per lane
+                float t_enter = 0.0f, t_exit = 3.0e38f;
+                bool outside_parallel = false;
 #pragma unroll 1
-            for (uint32_t k = first_leaf + sub; k < first_leaf + n_leaves; k += 8) {
-                const float4 n4 = leaves[2 * k], o4 = leaves[2 * k + 1];
-                const float dn = fmaf(n4.z, rd.z, fmaf(n4.y, rd.y, n4.x * rd.x));
-                const float s0 = fmaf(n4.z, oz - o4.z, fmaf(n4.y, oy - o4.y, n4.x * (ox - o4.x))) - inflate * n4.w;
-                const float tk = __fdividef(-s0, dn);
-                if (dn < 0.0f) t_enter = fmaxf(t_enter, tk);
-                else if (dn > 0.0f) t_exit = fminf(t_exit, tk);
-                else if (s0 > 0.0f) outside_parallel = true;
-            }
+                for (uint32_t k = first_leaf + sub; k < first_leaf + n_leaves; k += 8) {
+                    const float4 n4 = leaves[2 * k], o4 = leaves[2 * k + 1];
+                    const float dn = fmaf(n4.z, rd.z, fmaf(n4.y, rd.y, n4.x * rd.x));
+                    const float s0 = fmaf(n4.z, oz - o4.z, fmaf(n4.y, oy - o4.y, n4.x * (ox - o4.x))) - inflate * n4.w;
+                    const float tk = __fdividef(-s0, dn);
+                    if (dn < 0.0f) t_enter = fmaxf(t_enter, tk);
+                    else if (dn > 0.0f) t_exit = fminf(t_exit, tk);
+                    else if (s0 > 0.0f) outside_parallel = true;
+                }
 #pragma unroll
-            for (uint32_t sh = 1; sh < 8; sh <<= 1) {
-                t_enter = fmaxf(t_enter, __shfl_xor_sync(0xffffffffu, t_enter, sh));
-                t_exit = fminf(t_exit, __shfl_xor_sync(0xffffffffu, t_exit, sh));
-                outside_parallel |= (__shfl_xor_sync(0xffffffffu, (int)outside_parallel, sh) != 0);
+                for (uint32_t sh = 1; sh < 8; sh <<= 1) {
+                    t_enter = fmaxf(t_enter, __shfl_xor_sync(0xffffffffu, t_enter, sh));
+                    t_exit = fminf(t_exit, __shfl_xor_sync(0xffffffffu, t_exit, sh));
+                    outside_parallel |= (__shfl_xor_sync(0xffffffffu, (int)outside_parallel, sh) != 0);
+                }
+                const float start = t_enter * 0.9999f - 1.0e-3f;
+                const bool may_hit = !outside_parallel && !(t_exit < 0.0f) && !(start > t_exit) && !(start > best_t);
+                if (valid && sub == 0u && may_hit) {
+                    const uint32_t slot = atomicAdd(bcount, 1u);
+                    if (slot < task_cap) btasks[slot] = (owner << 16) | body;
+                    else atomicAdd(&res_cnt[owner], RL_COMPOUND_SLOTS + 1u);   // no room: the owner evaluates every body
+                }
             }
-            const float start = t_enter * 0.9999f - 1.0e-3f;
-            const bool may_hit = !outside_parallel && !(t_exit < 0.0f) && !(start > t_exit) && !(start > best_t);
-            if (valid && sub == 0u && may_hit) {
-                const uint32_t slot = atomicAdd(bcount, 1u);
-                if (slot < task_cap) btasks[slot] = (owner << 16) | body;
-                else atomicAdd(&res_cnt[owner], RL_COMPOUND_SLOTS + 1u);   // no room: the owner evaluates every body
-            }
-        }
         }
         __syncthreads();
-        const uint32_t ntasks = min(*bcount, task_cap);
+#if RL_BODIES_FIRST
+        if (round == 0u) sphere_phase();
+#endif
+        const uint32_t ntasks = min(bcount[0], task_cap);
 #pragma unroll 1
-        for (uint32_t q = tid; q < ntasks; q += nthreads) {
-            const uint32_t task = btasks[q];
-            const uint32_t owner = task >> 16, body = task & 0xffffu;
-            const float4 c4 = compounds[2 * body];
-            const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1];
-            Ray oray;                                           // the owner's ray, bit for bit
-            oray.origin = mk(-0.5f * ro.x, -0.5f * ro.y, -0.5f * ro.z);
-            oray.direction = mk(rd.x, rd.y, rd.z);
-            oray.wavelength = 0.0f;
-            uint32_t leaf;
-            const float t = compound_t(__float_as_uint(c4.x), __float_as_uint(c4.z), __float_as_uint(c4.w), oray, leaf);
-            if (t > 0.0f) {
-                const uint32_t slot = atomicAdd(&res_cnt[owner], 1u);
-                if (slot < RL_COMPOUND_SLOTS)
-                    results[slot * nthreads + owner] = make_float2(t, __uint_as_float((body << 16) | leaf));
+#if RL_TASK_STEAL
+        for (;;) {
+            uint32_t q = 0;
+            if (lane == 0) q = atomicAdd(bcount + 1, 32u);
+            q = __shfl_sync(0xffffffffu, q, 0) + lane;
+            if (q - lane >= ntasks) break;                      // warp-uniform
+#else
+        for (uint32_t q = tid; q - lane < ntasks; q += nthreads) {
+#endif
+            if (q < ntasks) {
+                const uint32_t task = btasks[q];
+                const uint32_t owner = task >> 16, body = task & 0xffffu;
+                const float4 c4 = compounds[2 * body];
+                const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1];
+                Ray oray;                                           // the owner's ray, bit for bit
+                oray.origin = mk(-0.5f * ro.x, -0.5f * ro.y, -0.5f * ro.z);
+                oray.direction = mk(rd.x, rd.y, rd.z);
+                oray.wavelength = 0.0f;
+                uint32_t leaf;
+                const float t = compound_t(c4, oray, leaf);
+                if (t > 0.0f) {
+                    const uint32_t slot = atomicAdd(&res_cnt[owner], 1u);
+                    if (slot < RL_COMPOUND_SLOTS)
+                        results[slot * nthreads + owner] = make_float2(t, __uint_as_float((body << 16) | leaf));
+                }
             }
         }
         __syncthreads();
@@ -779,7 +847,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
             for (uint32_t k = round; k < round_end; k++) {
                 const float4 c4 = compounds[2 * k];
                 uint32_t leaf;
-                const float t = compound_t(__float_as_uint(c4.x), __float_as_uint(c4.z), __float_as_uint(c4.w), ray, leaf);
+                const float t = compound_t(c4, ray, leaf);
                 if (t > 0.0f) consider(best, t, (int)compound_obj[k], (RL_HIT_LEAF << 28) | leaf);
             }
         } else {
@@ -791,11 +859,10 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
             }
         }
         res_cnt[tid] = 0u;
-        if (tid == 0) *bcount = 0u;
+        if (tid == 0) { bcount[0] = 0u; bcount[1] = 0u; }
         // the next round is behind the barrier below; the next CALL must be behind a block barrier
         // of the caller's (every kernel that loops over intersect_scene has one per iteration),
-        // which also orders these resets and the aliasing of the result slots with the next
-        // call's cluster queues
+        // which also orders these resets
         if (round + RL_BODIES_PER_ROUND < n_compounds) __syncthreads();
     }
     return best;
@@ -832,9 +899,14 @@ __device__ __forceinline__ Surf surface_at(const Ray &ray, const Hit &hit) {
         const V3 local_pos = s.position - offset;
         const V3 plane_pr = local_pos - normal * dot(local_pos, normal);
         s.normal = normalise_dev(focal_point - plane_pr);
-    } else {                                                           // geometry.rs:115
+    } else {
         const float4 n4 = sm_vec(tb.leaves)[2 * idx];
-        s.normal = mk(n4.x, n4.y, n4.z);
+        if (n4.w == 0.0f) {                                            // a sphere leaf, geometry.rs:243-248
+            const float4 o4 = sm_vec(tb.leaves)[2 * idx + 1];
+            s.normal = normalise_dev(s.position - mk(o4.x, o4.y, o4.z));
+        } else {
+            s.normal = mk(n4.x, n4.y, n4.z);                           // geometry.rs:115
+        }
     }
     return s;
 }
@@ -842,7 +914,10 @@ __device__ __forceinline__ Surf surface_at(const Ray &ray, const Hit &hit) {
 // Sphere::intersect's tangent, normalise(cross((0,1,0), normal)) (geometry.rs:250-251); every
 // other surface leaves it zero.  Computed where it is read (SoapBubbleMaterial, material.rs:297).
 __device__ __forceinline__ V3 sphere_tangent(const Hit &hit, const Surf &s) {
-    if ((hit.code >> 28) != RL_HIT_SPHERE) return mk(0.0f, 0.0f, 0.0f);
+    const uint32_t type = hit.code >> 28;
+    const bool sphere = type == RL_HIT_SPHERE
+                        || (type == RL_HIT_LEAF && sm_vec(tables().leaves)[2 * (hit.code & 0x0fffffffu)].w == 0.0f);
+    if (!sphere) return mk(0.0f, 0.0f, 0.0f);
     return normalise_dev(cross(mk(0.0f, 1.0f, 0.0f), s.normal));
 }
 

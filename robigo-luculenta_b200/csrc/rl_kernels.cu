@@ -7,6 +7,7 @@
 //   K4 tonemap_*       TonemapUnit::tonemap (tonemap_unit.rs:55-100, srgb.rs:20-41)
 //
 // Compile with -fmad=false: see rl_math.cuh.
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
@@ -74,7 +75,7 @@ static_assert(sizeof(TraceCta) % 16 == 0, "the ring behind TraceCta holds float4
 
 __device__ __forceinline__ TraceCta *trace_cta(const DevScene &sc) {
     char *base = reinterpret_cast<char *>(rl_smem + RL_TABLES_VEC4 + sc.smem_vec4);
-    return reinterpret_cast<TraceCta *>(base + (size_t)RL_SCRATCH_BYTES_PER_THREAD * blockDim.x);
+    return reinterpret_cast<TraceCta *>(base + (size_t)scratch_bytes_per_thread(sc.n_compounds) * blockDim.x);
 }
 
 // trace_unit.rs:151-158 and :136-145 for the photon at index `gidx` of the launch: the draws of
@@ -261,12 +262,21 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
 }
 
 // camera-ray ring entries for CTAs of `threads` threads: the power of two at or above the CTA
-// size (a refill never has to be cut short), or below it when shared memory is short
-static uint32_t ring_entries(int threads, bool roomy) {
+// size (a refill is never cut short), or a half / a quarter of it (at least 128) when shared
+// memory is short -- lanes that find the ring empty wait one iteration for the next refill
+static uint32_t ring_entries(int threads, int shrink) {
     uint32_t cap = 128;
     while ((int)cap < threads) cap <<= 1;
-    if (!roomy && (int)cap > threads && cap > 128) cap >>= 1;
+    for (int k = 0; k < shrink && cap > 128; k++) cap >>= 1;
     return cap;
+}
+// CTAs of `threads` threads that fit an SM with that ring (228 KB of shared memory, 1 KB reserved
+// per CTA; 2048 threads; 64 K registers at 80 per thread)
+static size_t trace_ctas_per_sm(size_t smem, int threads) {
+    const size_t by_smem = (228u * 1024u) / (smem + 1024u);
+    const size_t by_threads = 2048u / (size_t)threads, by_regs = 65536u / (80u * (size_t)threads);
+    const size_t cap = by_threads < by_regs ? by_threads : by_regs;
+    return by_smem < cap ? by_smem : cap;
 }
 static size_t trace_kernel_smem_bytes(const DevScene &sc, int threads, uint32_t ring_cap) {
     return tracing_smem_bytes(sc, threads) + sizeof(TraceCta) + (size_t)RL_TRACE_PARK_BYTES_PER_THREAD * ((threads + 1) & ~1)
@@ -380,12 +390,23 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     const int max_smem = cached.max_smem;
     int threads = env_int("RL_TRACE_THREADS_MAX", RL_TRACE_THREADS);
     if (threads > RL_TRACE_THREADS || threads < 128 || threads % 128) threads = RL_TRACE_THREADS;
-    // prefer the full CTA with a short ring to a smaller CTA with a roomy one
-    bool roomy = true;
-    while (trace_kernel_smem_bytes(sc, threads, ring_entries(threads, roomy)) > (size_t)max_smem) {
-        if (roomy) { roomy = false; continue; }
+    // the largest CTA that fits, with the roomiest ring that does not cost a resident CTA
+    auto pick_ring = [&](int t) {
+        int best = -1;
+        size_t best_ctas = 0;
+        for (int shrink = 0; shrink <= 2; shrink++) {
+            const size_t bytes = trace_kernel_smem_bytes(sc, t, ring_entries(t, shrink));
+            if (bytes > (size_t)max_smem) continue;
+            const size_t ctas = trace_ctas_per_sm(bytes, t);
+            if (ctas > best_ctas) { best_ctas = ctas; best = shrink; }
+        }
+        return best;
+    };
+    int shrink = pick_ring(threads);
+    while (shrink < 0) {
         if (threads <= 128) return cudaErrorInvalidValue;
-        threads -= 128; roomy = true;
+        threads -= 128;
+        shrink = pick_ring(threads);
     }
     // Small batches (the reference's 524 288 photons are 4.6 per thread of a full grid) spend most
     // of their time in the tail, where a block waits for its last paths.  They are launched as
@@ -401,8 +422,12 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     const uint64_t small_paths = (uint64_t)env_int("RL_TRACE_SMALL_PATHS", RL_TRACE_SMALL_PATHS);
     const bool small = small_cta >= 128 && small_cta < threads && small_cta % 32 == 0
                        && n_photons < small_paths * (uint64_t)sm_count * (uint64_t)threads;
-    if (small) { threads = small_cta; roomy = true; }
-    const uint32_t ring_cap = ring_entries(threads, roomy);
+    if (small) {
+        threads = small_cta;
+        shrink = pick_ring(threads);
+        if (shrink < 0) return cudaErrorInvalidValue;
+    }
+    const uint32_t ring_cap = ring_entries(threads, shrink);
     const size_t smem = trace_kernel_smem_bytes(sc, threads, ring_cap);
     if (cached.threads != threads || cached.smem != smem) {
         int occ = 0;
@@ -414,13 +439,22 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     set_carveout(trace_kernel, cached, per_sm, smem);
     uint64_t full = (uint64_t)sm_count * per_sm;
     if (small) {
-        // RL_TRACE_BLOCKS_PER_SM > 0 fixes the share (experiments); default: by the concurrency seen
-        int share = env_int("RL_TRACE_BLOCKS_PER_SM", 0);
-        if (share <= 0) {
-            const int others = other_streams_in_flight(dev, st, per_sm - 1 > 1 ? per_sm - 1 : 1);
-            share = (per_sm + others) / (others + 1);
+        // The launch's share of the GPU's block slots, by the concurrency seen: with k other
+        // streams' small launches queued or running it asks for 1 / (k + 1) of the slots, counting
+        // up to RL_TRACE_SHARE_MAX launches.  The host's worker threads run far ahead of the GPU,
+        // so in the steady state a batch goes out as a few dozen blocks with tens of photons per
+        // thread, a dozen batches side by side on every SM: a block then spends most of its life
+        // with full warps, and its tail is covered by the blocks of other batches beside it.
+        // RL_TRACE_BLOCKS_PER_SM > 0 fixes the share per SM instead (experiments).
+        const int fixed = env_int("RL_TRACE_BLOCKS_PER_SM", 0);
+        if (fixed > 0) {
+            if (fixed < per_sm) full = (uint64_t)sm_count * fixed;
+        } else {
+            const int share_max = std::max(1, env_int("RL_TRACE_SHARE_MAX", 12));
+            const int others = share_max > 1 ? other_streams_in_flight(dev, st, share_max - 1) : 0;
+            full = (full + others) / (uint64_t)(others + 1);
+            if (full < 1) full = 1;
         }
-        if (share < per_sm) full = (uint64_t)sm_count * (share < 1 ? 1 : share);
     }
     TraceArgs a;
     a.n_seg = p.n_segments;

@@ -43,6 +43,7 @@ struct DevScene {
     float cluster_rmax;       // largest cluster bounding radius
     float leaf_off_max;       // largest |offset| over the half-spaces of compound surfaces (slab-test inflation)
     float body_rmax;          // largest bounding radius of a compound
+    uint32_t sphere_leaves;   // 1: some compound has a sphere leaf (geometry.rs:263-267)
     DevCamera camera;
 };
 

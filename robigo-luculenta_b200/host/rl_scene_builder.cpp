@@ -347,6 +347,29 @@ void scene_c4(rl_scene_builder *b, uint32_t n) {
     b->camera = orbit_camera();
 }
 
+// C6: compounds over the reference's other Volume, the sphere (geometry.rs:263-267, :361-407):
+// a biconvex SF10 lens = Compound<Sphere, Sphere>, a soap-bubble dome = Compound<Sphere,
+// SpacePartitioning> (its spherical face carries the tangent of geometry.rs:250-251), a glossy
+// lens cut by a slab = Compound<Compound<Sphere, Sphere>, ThickPlane>, a diffuse sphere clipped to
+// a prism = Compound<Prism, Sphere>; grey floor, emissive circle and sphere, static camera.
+void scene_c6(rl_scene_builder *b) {
+    add_object(b, add_plane(b, mk(0.f, 0.f, 1.f), mk(0.f, 0.f, 0.f)), material(RL_MATERIAL_DIFFUSE_GREY, 0.8f));
+    add_object(b, compound(b, add_sphere(b, mk(-1.2f, 0.f, 2.f), 2.0f), add_sphere(b, mk(1.2f, 0.f, 2.f), 2.0f)),
+               material(RL_MATERIAL_SF10_GLASS));
+    add_object(b, compound(b, add_sphere(b, mk(5.f, 1.f, 0.5f), 2.0f), halfspace(b, mk(0.f, 0.f, -1.f), mk(0.f, 0.f, 0.5f))),
+               material(RL_MATERIAL_SOAP_BUBBLE));
+    add_object(b, compound(b, compound(b, add_sphere(b, mk(-5.f, 0.f, 1.f), 2.5f), add_sphere(b, mk(-5.f, 0.f, 4.f), 2.5f)),
+                           thick_plane(b, mk(1.f, 0.f, 0.f), mk(-5.5f, 0.f, 0.f), 1.0f)),
+               material(RL_MATERIAL_GLOSSY_MIRROR, 0.1f));
+    add_object(b, compound(b, prism(b, mk(0.f, 0.f, 1.f), mk(0.f, 5.f, 0.2f), 4.0f, 0.7f, 3.0f),
+                           add_sphere(b, mk(0.f, 5.f, 1.5f), 1.8f)),
+               material(RL_MATERIAL_DIFFUSE_COLOURED, 0.9f, 620.0f, 60.0f));
+    add_object(b, add_circle(b, mk(0.f, 0.f, -1.f), mk(0.f, 2.f, 9.f), 4.0f), blackbody(7600.0f, 1.0f));
+    add_object(b, add_sphere(b, mk(2.f, -3.f, 0.8f), 0.8f), blackbody(5000.0f, 0.5f));
+    const rl::Quat q = rl::rotation(1.0f, 0.0f, 0.0f, -0.3f);
+    b->camera = static_camera(mk(0.f, -14.f, 6.f), q, PI * 0.35f, 14.0f, 40.0f, 0.01f);
+}
+
 }  // namespace
 
 extern "C" {
@@ -374,6 +397,7 @@ int rl_scene_builder_builtin(rl_scene_builder *b, int which, uint32_t param) {
     case RL_SCENE_C2_BUILTIN: scene_c2(b); break;
     case RL_SCENE_C3_PRISM: scene_c3(b); break;
     case RL_SCENE_C4_SPHERES: scene_c4(b, param); break;
+    case RL_SCENE_C6_LENSES: scene_c6(b); break;
     default: return RL_ERR_INVALID;
     }
     return RL_OK;
@@ -387,6 +411,16 @@ int rl_scene_builder_circle(rl_scene_builder *b, rl_vec3 normal, rl_vec3 positio
     if (!b) return RL_ERR_INVALID;
     return add_circle(b, vr(normal), vr(position), radius);
 }
+int rl_scene_builder_halfspace(rl_scene_builder *b, rl_vec3 normal, rl_vec3 offset) {
+    if (!b) return RL_ERR_INVALID;
+    return halfspace(b, vr(normal), vr(offset));
+}
+
+int rl_scene_builder_compound(rl_scene_builder *b, uint32_t surface1, uint32_t surface2) {
+    if (!b || surface1 >= b->surfaces.size() || surface2 >= b->surfaces.size()) return RL_ERR_INVALID;
+    return compound(b, (int)surface1, (int)surface2);
+}
+
 int rl_scene_builder_sphere(rl_scene_builder *b, rl_vec3 position, float radius) {
     if (!b) return RL_ERR_INVALID;
     return add_sphere(b, vr(position), radius);

@@ -1,6 +1,6 @@
-"""Group launches (csrc/rl_api.cu TraceDispatcher, csrc/rl_kernels.cu K1): batches of the
-reference's size are queued to the scene's dispatcher and traced several to a launch, each batch
-one segment of the launch's photon pool (task_scheduler.rs:95-96,127-182 is the caller that
+"""Group launches (csrc/rl_api.cu TraceDispatcher, csrc/rl_kernels.cu K1; RL_TRACE_GROUPS=1):
+batches of the reference's size are queued to the scene's dispatcher and traced several to a
+launch, each batch one segment of the launch's photon pool (task_scheduler.rs:95-96,127-182 is the caller that
 produces them).  Whichever launch, CTA and lane traces a photon, its record is a function of
 (scene, seed, photon id): everything here is compared bit for bit with the oracle, and with the
 one-launch-per-batch path."""
@@ -12,6 +12,12 @@ import pytest
 from test_gpu_parity import SEED, assert_records_equal, image_tolerance
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def group_launches(monkeypatch):
+    """The dispatcher is opt-in (one launch per batch measured faster on the scheduler replay)."""
+    monkeypatch.setenv("RL_TRACE_GROUPS", "1")
 
 
 def test_grouped_batches_bit_equal_and_counted(gpu, orc):

@@ -95,7 +95,7 @@ def compare_hits(got, want, what):
         assert_bit_equal(got[f], want[f], f"{what}.{f}")
 
 
-@pytest.mark.parametrize("which,param,extent", [(1, 0, 8.0), (2, 0, 60.0), (3, 0, 15.0), (4, 512, 30.0)])
+@pytest.mark.parametrize("which,param,extent", [(1, 0, 8.0), (2, 0, 60.0), (3, 0, 15.0), (4, 512, 30.0), (6, 0, 12.0)])
 def test_scene_intersect_bit_equal(gpu, orc, which, param, extent):
     b = gpu.SceneBuilder(which, param)
     sc = gpu.Scene(b)
@@ -144,6 +144,7 @@ def test_intersect_edge_cases(gpu, orc):
     (2, 0, 1280, 720, 20000),       # the reference's own default canvas (main.rs:47-48)
     (3, 0, 1024, 1024, 60000),      # dispersive prism (configs[2] scene)
     (4, 256, 512, 512, 20000),      # random spheres (configs[3] family, reduced)
+    (6, 0, 640, 480, 60000),        # compounds over spheres: lens, dome, clipped sphere (geometry.rs:263-267,361-407)
 ])
 def test_trace_records_bit_equal(gpu, orc, which, param, w, h, n):
     b = gpu.SceneBuilder(which, param)
@@ -640,22 +641,17 @@ def test_error_behaviour(gpu):
     assert e.value.code == gpu.RL_ERR_INVALID
     with pytest.raises(gpu.RlError):
         gpu.TraceUnit(0, 0, 32)
-    # a compound with a non-half-space leaf is outside what the engine flattens
+    # the children of a compound are Volumes (geometry.rs:379): a plane is a Surface only
     bad = gpu.SceneBuilder()
-    s1, s2 = bad.sphere((0, 0, 0), 1.0), bad.sphere((0.5, 0, 0), 1.0)
-    d = bad.desc()
-    surfaces = (gpu.Surface * 3)(d.surfaces[0], d.surfaces[1], gpu.Surface())
-    surfaces[2].kind = gpu.SURFACE_COMPOUND
-    surfaces[2].child[0], surfaces[2].child[1] = s1, s2
-    objects = (gpu.Object * 1)(gpu.Object(2, gpu.SceneBuilder.material(gpu.MATERIAL_SF10_GLASS)))
-    desc = gpu.SceneDesc(surfaces, 3, objects, 1, d.camera)
+    bad.object(bad.compound(bad.sphere((0, 0, 0), 1.0), bad.plane((0, 0, 1), (0, 0, 0))),
+               gpu.SceneBuilder.material(gpu.MATERIAL_SF10_GLASS))
     with pytest.raises(gpu.RlError) as e:
-        gpu.Scene(desc)
+        gpu.Scene(bad)
     assert e.value.code == gpu.RL_ERR_UNSUPPORTED
 
 
 # --------------------------------------------------------------------- culling
-@pytest.mark.parametrize("which,param,w,h,n", [(2, 0, 1024, 1024, 1 << 21), (3, 0, 1024, 1024, 1 << 20),
+@pytest.mark.parametrize("which,param,w,h,n", [(2, 0, 1024, 1024, 1 << 21), (3, 0, 1024, 1024, 1 << 20), (6, 0, 640, 480, 1 << 19),
                                                (4, 0, 2048, 2048, 1 << 17), (1, 0, 256, 256, 1 << 18)])
 def test_culls_are_result_preserving(gpu, which, param, w, h, n):
     # every ray of n traced paths: culled Scene::intersect == brute force over all primitives

@@ -326,3 +326,32 @@ def test_closed_draw_is_successor_of_scaled_integer():
     succ = (n.astype(np.float32) * np.float32(2.0 ** -24)).view(np.uint32) + np.uint32(1)
     succ[0] = 0
     assert np.array_equal(quotient.view(np.uint32), succ)
+
+
+def test_compound_of_spheres(pkg, orc):
+    # Sphere is the reference's other Volume (geometry.rs:263-267): Compound<Sphere, Sphere> is a
+    # lens, Compound<Sphere, SpacePartitioning> a dome.  geometry.rs:380-401: each child's own hit,
+    # kept iff it lies inside the other child; Sphere::intersect misses from inside (:236-240), so
+    # a ray that starts inside the lens never sees its far face.
+    b = pkg.SceneBuilder()
+    grey = pkg.SceneBuilder.material(pkg.MATERIAL_DIFFUSE_GREY, 0.5)
+    b.object(b.compound(b.sphere((-1.2, 0, 2), 2.0), b.sphere((1.2, 0, 2), 2.0)), grey)           # lens, 0
+    b.object(b.compound(b.sphere((5, 6, 0.5), 2.0), b.halfspace((0, 0, -1), (0, 0, 0.5))), grey)  # dome, 1
+    rays = np.zeros(7, dtype=orc.RAY)
+    rays["origin"] = [(-10, 0, 2), (10, 0, 2), (0, 0, 2), (0, -10, 2), (5, 6, 10), (5, 6, -10), (5, -10, 0.4)]
+    rays["direction"] = [(1, 0, 0), (-1, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1), (0, 1, 0)]
+    rays["wavelength"], rays["probability"] = 550.0, 1.0
+    hit = orc.intersect(b.desc(), rays)
+    # from -x: the first sphere's near face (x = -3.2) lies outside the second sphere; the second
+    # sphere's near face (x = -0.8) lies inside the first: that is the lens's face
+    assert hit["object"][0] == 0 and abs(hit["distance"][0] - 9.2) < 1e-5
+    assert np.allclose(hit["normal"][0], (-1, 0, 0)) and np.allclose(hit["tangent"][0], (0, 0, 1))
+    assert hit["object"][1] == 0 and abs(hit["distance"][1] - 9.2) < 1e-5 and np.allclose(hit["normal"][1], (1, 0, 0))
+    assert hit["object"][2] == -1                       # from inside: both spheres miss
+    # along y through the lens's rim region: |x| = 0 plane, the lens's half-height is sqrt(4 - 1.44) = 1.6
+    assert hit["object"][3] == 0 and abs(hit["distance"][3] - (10 - 1.6)) < 1e-5
+    # dome from above: the spherical cap at z = 2.5; from below: the flat face at z = 0.5
+    assert hit["object"][4] == 1 and abs(hit["distance"][4] - 7.5) < 1e-5 and np.allclose(hit["normal"][4], (0, 0, 1))
+    assert hit["object"][5] == 1 and abs(hit["distance"][5] - 10.5) < 1e-5 and np.allclose(hit["normal"][5], (0, 0, -1))
+    assert np.allclose(hit["tangent"][5], 0.0)          # only spheres set a tangent (geometry.rs:250-251)
+    assert hit["object"][6] == -1                       # below the cut: the sphere's faces there are outside the half-space

@@ -13,6 +13,8 @@ out = {}
 for name, which, w, h, n in (("C1 sphere+plane 256^2", 1, 256, 256, 1 << 24), ("C2 built-in 1024^2", 2, 1024, 1024, 1 << 26),
                              ("C3 prism 1024^2", 3, 1024, 1024, 1 << 26), ("C4 4096 spheres 2048^2", 4, 2048, 2048, 1 << 24),
                              ("C5 built-in 4096^2 (one GPU's share)", 2, 4096, 4096, 1 << 26)):
+    if os.environ.get("RL_RATES_ONLY") and not name.startswith(os.environ["RL_RATES_ONLY"]):
+        continue
     sc = pkg.Scene(pkg.SceneBuilder(which))
     tu = pkg.TraceUnit(0, w, h, seed=0x5EED, batch=n); pl = pkg.PlotUnit(0, w, h)
     tu.set_stream(side.cuda_stream); pl.set_stream(side.cuda_stream)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU visit: GPU tests, replay sweep, one ncu capture of the trace kernel, the bench line.
-# usage (under gpurun): bash tools/gpu_round.sh <tag> [tests|sweep|ncu|bench ...]   (default: all four)
+# usage (under gpurun): bash tools/gpu_round.sh <tag> [tests|sweep|dsweep|ssweep|ab|ncu|ncu4|traffic|launches|leaf|bench ...]   (default: tests sweep ncu bench)
 TAG=${1:-round}; shift
 WHAT=${@:-tests sweep ncu bench}
 mkdir -p gpurun_out
@@ -9,6 +9,13 @@ for w in $WHAT; do
     tests) timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/${TAG}_gputest.log 2>&1; tail -4 gpurun_out/${TAG}_gputest.log ;;
     sweep) bash tools/e2e_sweep.sh 2048 16 > gpurun_out/${TAG}_sweep.txt 2>&1; mv gpurun_out/e2e_sweep.jsonl gpurun_out/${TAG}_sweep.jsonl; cat gpurun_out/${TAG}_sweep.txt ;;
     ncu) timeout 600 ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_trace python tools/profile_trace.py > gpurun_out/${TAG}_ncu.log 2>&1; tail -2 gpurun_out/${TAG}_ncu.log ;;
+    ncu4) RL_PROFILE_SCENE=4 RL_PROFILE_CANVAS=2048 RL_PROFILE_TRACE_ONLY=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_trace_c4 python tools/profile_trace.py > gpurun_out/${TAG}_ncu4.log 2>&1; tail -2 gpurun_out/${TAG}_ncu4.log ;;
+    dsweep) bash tools/dispatch_sweep.sh ${TAG} ;;
+    ssweep) bash tools/share_sweep.sh ${TAG} ;;
+    ab) bash tools/kernel_ab.sh ${TAG} ;;
+    traffic) timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_traffic.csv python tools/profile_trace.py > gpurun_out/${TAG}_traffic.log 2>&1; tail -1 gpurun_out/${TAG}_traffic.log ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_launches.log 2>&1; tail -1 gpurun_out/${TAG}_launches.log | cut -c1-200 ;;
+    leaf) for L in 12 16 20 24 29 40; do echo "RL_CLUSTER_LEAF=$L"; RL_CLUSTER_LEAF=$L RL_RATES_ONLY=C4 timeout 200 python tools/config_rates.py 2>&1 | tail -1; done | tee gpurun_out/${TAG}_leaf.txt ;;
     bench) timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -3 gpurun_out/${TAG}_bench.err; python - <<PY
 import json
 try:

@@ -14,3 +14,11 @@ for v in variants/*.so; do
   timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee -a gpurun_out/${TAG}_ab.txt
 done
 cp /tmp/librl_b200.keep $LIB; touch $LIB
+# the library in place under the environment settings of variants/env.txt (one per line)
+if [ -f variants/env.txt ]; then
+  while read -r setting; do
+    [ -z "$setting" ] && continue
+    echo "== in-place library, $setting" | tee -a gpurun_out/${TAG}_ab.txt
+    env $setting RL_RATES_ONLY=${RL_RATES_ONLY:-C2} timeout 300 python tools/config_rates.py 2>&1 | tail -1 | tee -a gpurun_out/${TAG}_ab.txt
+  done < variants/env.txt
+fi

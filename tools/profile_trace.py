@@ -13,14 +13,18 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as entry
 
 pkg = entry.load_package()
-W = H = 1024
-scene = pkg.Scene(pkg.SceneBuilder(pkg.SCENE_C2))
+# RL_PROFILE_SCENE=4 RL_PROFILE_CANVAS=2048: the same launches on another BASELINE config
+W = H = int(os.environ.get("RL_PROFILE_CANVAS", "1024"))
+scene = pkg.Scene(pkg.SceneBuilder(int(os.environ.get("RL_PROFILE_SCENE", str(pkg.SCENE_C2)))))
 tu = pkg.TraceUnit(0, W, H, seed=0x5EED, batch=1 << 24)
 pl = pkg.PlotUnit(0, W, H)
 tu.render_fused(scene, pl, 0, 1 << 22)
 tu.sync()
 tu.render_fused(scene, pl, 1 << 24, 1 << 24)
 tu.sync()
+if os.environ.get("RL_PROFILE_TRACE_ONLY"):
+    print("rays", tu.ray_count())
+    sys.exit(0)
 tu.render_range(scene, 1 << 26, 524288, download=False)
 tu.sync()
 pl.plot(tu)
