@@ -35,8 +35,12 @@
  *       bit-for-bit against this mode; LIBM vs SPEC is compared statistically.
  *
  * RNG.  rand::random has no seed, so both modes draw from Philox4x32-10
- * (Salmon et al., SC'11) keyed by (seed, photon id): draw i of a photon is
- * word i%4 of block i/4 with counter (id_lo, id_hi, block, 0).  The two
+ * (Salmon et al., SC'11) keyed by (seed, photon id), counter (id_lo, id_hi,
+ * block, 0): the six draws in front of the first bounce (wavelength, x, y, t,
+ * lens angle, lens radius) are the words of blocks 0 and 1 in order; the draws
+ * of bounce j (the material's, then the roulette's -- at most three) are the
+ * first words of block 2 + j.  A bounce therefore needs exactly one block,
+ * known before the ray is traced.  The two
  * distributions are rand 0.3.11's: f32 = (u32 >> 8) * 2^-24 in [0,1);
  * Closed01<f32> = that * 2^24 / (2^24 - 1) in [0,1].
  */
@@ -268,6 +272,10 @@ struct Philox {
         if (idx == 4) { block4x32_10(key0, key1, c0, c1, block, 0u, buf); block++; idx = 0; }
         return buf[idx++];
     }
+    // The draws of bounce j (the material's, then the roulette's: at most three) are the first
+    // words of block 2 + j; the six draws in front of the first bounce (wavelength, x, y, t, lens
+    // angle and radius) are blocks 0 and 1.  Unused words of a block are dropped.
+    inline void begin_bounce(uint32_t j) { block = 2u + j; idx = 4; }
     // monte_carlo.rs:25-28 -- Closed01<f32> of rand 0.3.11
     inline float unit() { return (float)(next_u32() >> 8) / 16777215.0f; }
     // monte_carlo.rs:37 -- rand::random::<f32>()
@@ -598,6 +606,7 @@ float render_ray(const SceneView &sc, Ray ray, Philox &rng, Counters &ct, bool c
     float intensity = 1.0f;
     uint64_t bounces = 0;
     for (;;) {
+        rng.begin_bounce((uint32_t)bounces);
         Isect is;
         ct.rays++;
         int obj = scene_intersect(sc, ray, is, count_tests ? &ct.tests : nullptr);
@@ -1029,7 +1038,8 @@ int orc_dump_rays(const rl_scene_desc *desc, uint64_t seed, uint32_t width, uint
         Camera cam = camera_at_time<SpecMath>(sc.camera, t);
         Ray ray = camera_get_ray<SpecMath>(cam, x, y, wavelength, rng);
         float continue_chance = 1.0f, intensity = 1.0f;
-        for (;;) {
+        for (uint32_t bounce = 0;; bounce++) {
+            rng.begin_bounce(bounce);
             if (k < cap) {
                 out[k].origin = to_rl(ray.origin); out[k].direction = to_rl(ray.direction);
                 out[k].wavelength = ray.wavelength; out[k].probability = intensity; k++;

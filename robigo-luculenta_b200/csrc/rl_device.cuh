@@ -55,24 +55,14 @@ struct PrimTables {
 };
 
 #define RL_TABLES_VEC4 ((sizeof(PrimTables) + 15) / 16)
-#ifndef RL_TASK_STEAL
-#define RL_TASK_STEAL 0      // 1: body tasks are taken 32 at a time by whichever warp gets there; 0: dealt by thread index (no difference measured)
-#endif
-#ifndef RL_BODIES_FIRST
-// 1: the bodies' bound scan and slab tests run before the sphere phase, which then runs beside
-// the body evaluation (between the two block barriers); 0: sphere phase first, so that sphere
-// hits prune the bodies too.  Measured on the built-in scene: 2770 vs 2971 Mrays/s.
-#define RL_BODIES_FIRST 0
-#endif
 #define RL_CAND_SLOTS 8        // queued sphere candidates per lane
 #define RL_COMPOUND_SLOTS 4    // body results per lane, and body tasks per thread of the block list
 #define RL_PAIR_CAP 768        // (lane, cluster) or (lane, body) pairs per warp and round
 #define RL_BODIES_PER_ROUND 64  // bodies whose bounds one scan covers (one bit each of a lane's candidate mask)
-// scratch bytes per thread: ray table 48; sphere queue 2 per slot; three counters 12; pair list
-// 2 * RL_PAIR_CAP / 32; body results 8 per slot; block task list 4 per slot.  (The sphere queue
-// and the body results are separate areas: one warp's sphere phase runs beside another warp's
-// body evaluation.)
-#define RL_SCRATCH_BYTES_PER_THREAD (48 + 2 * RL_CAND_SLOTS + 12 + 2 * RL_PAIR_CAP / 32 + 8 * RL_COMPOUND_SLOTS + 4 * RL_COMPOUND_SLOTS)
+// scratch bytes per thread: ray table 48; sphere queue 2 per slot; two counters 8; pair list
+// 2 * RL_PAIR_CAP / 32; body results 8 per slot.  All of it is private to a warp (its threads'
+// columns, its pair list): the warps of a block never exchange anything in Scene::intersect.
+#define RL_SCRATCH_BYTES_PER_THREAD (48 + 2 * RL_CAND_SLOTS + 8 + 2 * RL_PAIR_CAP / 32 + 8 * RL_COMPOUND_SLOTS)
 static_assert(RL_PAIR_INDEX_BITS + 5 <= 16, "a pair record is a lane (5 bits) and a table index in 16 bits");
 
 __device__ __forceinline__ const PrimTables &tables() {
@@ -122,15 +112,15 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         float4 *ray_tab = rl_smem + base + sc.smem_vec4;
         uint16_t *sq_base = reinterpret_cast<uint16_t *>(ray_tab + 3 * blockDim.x);
         uint32_t *counters = reinterpret_cast<uint32_t *>(sq_base + RL_CAND_SLOTS * blockDim.x);
-        for (uint32_t k = threadIdx.x; k < 3 * blockDim.x; k += blockDim.x) counters[k] = 0u;
+        for (uint32_t k = threadIdx.x; k < 2 * blockDim.x; k += blockDim.x) counters[k] = 0u;
     }
     __syncthreads();
 }
 
-// A scene without compound bodies never touches the body results and the task list, which are
-// the last two areas of the scratch: it does not pay for them (4096 spheres keep 768 threads).
+// A scene without compound bodies never touches the body results, the last area of the
+// scratch: it does not pay for them (4096 spheres keep 768 threads).
 __host__ __device__ __forceinline__ uint32_t scratch_bytes_per_thread(uint32_t n_compounds) {
-    return RL_SCRATCH_BYTES_PER_THREAD - (n_compounds ? 0u : 12u * RL_COMPOUND_SLOTS);
+    return RL_SCRATCH_BYTES_PER_THREAD - (n_compounds ? 0u : 8u * RL_COMPOUND_SLOTS);
 }
 
 // Shared memory a tracing kernel needs with `threads` threads per block.
@@ -142,7 +132,7 @@ inline size_t tracing_smem_bytes(const DevScene &sc, int threads) {
 // ---------------------------------------------------------------------- RNG
 // Philox4x32-10, counter (photon_lo, photon_hi, block, 0), key (seed_lo,
 // seed_hi).  Stands in for rand::random (monte_carlo.rs:22-28).
-// One block is computed out of line so that the ten draw sites share it.
+// One block is computed out of line so that the call sites share it.
 static __device__ __noinline__ uint4 philox_block(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
                                                   uint32_t block) {
     uint32_t x0 = c0, x1 = c1, x2 = block, x3 = 0u;
@@ -196,6 +186,32 @@ struct Rng {
     __device__ __forceinline__ float bi_unit(const RngKey &k) { return unit(k) * 2.0f - 1.0f; }             // monte_carlo.rs:31-33
     __device__ __forceinline__ float longitude(const RngKey &k) { return half_open(k) * RL_PI * 2.0f; }     // monte_carlo.rs:36-38
     __device__ __forceinline__ float wavelength(const RngKey &k) { return unit(k) * 400.0f + 380.0f; }      // monte_carlo.rs:41-43
+};
+
+// The draws of one bounce: the material's, then the roulette's (at most three), are the first
+// words of block 2 + j of the path's stream (j = bounces so far; blocks 0 and 1 belong to the
+// draws in front of the first bounce, see Rng).  One block per bounce, known before the ray is
+// traced: the trace loop computes it for all its live lanes at one place, with full warps,
+// instead of inside whichever material code happens to run out of words.
+struct BounceRng {
+    uint32_t d0, d1, d2;
+    __device__ __forceinline__ void load(const RngKey &k, uint32_t bounce) {
+        const uint4 v = philox_block((uint32_t)k.seed, (uint32_t)(k.seed >> 32), (uint32_t)k.photon,
+                                     (uint32_t)(k.photon >> 32), 2u + bounce);
+        d0 = v.x; d1 = v.y; d2 = v.z;
+    }
+    __device__ __forceinline__ uint32_t next_u32() {
+        const uint32_t v = d0;
+        d0 = d1; d1 = d2;
+        return v;
+    }
+    __device__ __forceinline__ float unit() {                       // Closed01<f32>, see Rng::unit
+        const uint32_t n = next_u32() >> 8;
+        const float scaled = (float)n * 5.9604644775390625e-8f;
+        return n == 0u ? 0.0f : __uint_as_float(__float_as_uint(scaled) + 1u);
+    }
+    __device__ __forceinline__ float half_open() { return (float)(next_u32() >> 8) * 5.9604644775390625e-8f; }
+    __device__ __forceinline__ float longitude() { return half_open() * RL_PI * 2.0f; }     // monte_carlo.rs:36-38
 };
 
 // sin and cos through one shared out-of-line copy (eight call sites).
@@ -546,6 +562,57 @@ __device__ __forceinline__ uint32_t emit_pairs(uint64_t &todo, uint32_t base, ui
     return total;
 }
 
+// Compound::intersect (geometry.rs:380-401) of a tree of at most eight half-spaces, decided by
+// eight lanes at once (lane `sub` of its group of eight holds leaf `sub`), without walking the tree.
+//
+// What the recursion returns.  A leaf's own hit (plane_t > 0) moves up the tree; at every
+// compound node each child's surviving hit is first FILTERED -- kept iff its position lies
+// inside every leaf of the other child (lies_inside, geometry.rs:403-407) -- and then the nearer
+// of the two survivors is kept (ties: the second child's).  So (a) a hit that reaches the root
+// has passed the containment test of every other leaf; (b) a hit that fails the test of some
+// leaf m is dropped at the lowest common ancestor with m at the latest, BEFORE it is compared
+// with the survivor of m's side.  Let "sound" mean: valid and inside every other leaf (the
+// reference's own f32 predicates, evaluated here on the same operands).  Then:
+//   - no sound leaf: nothing reaches the root -- a miss;
+//   - otherwise let L be the nearest sound leaf.  If every other valid leaf k with t_k <= t_L
+//     fails the test of L's half-space, k is dropped no later than where it would meet L's
+//     survivor, so L wins every comparison on its way up (the survivors it is compared with are
+//     farther) and passes every filter (it is sound): the recursion returns L's hit.
+//   - anything else (a leaf at or before t_L that lies inside L's half-space: ties, or hits within
+//     rounding of an edge) is not decided here: the caller runs the recursion itself.
+// Returns t_L (> 0), -1 for a miss, -2 for "undecided"; leaf_out = L (relative to the body's first
+// leaf).  Called by all 32 lanes; `valid` and the body are uniform within a group of eight.
+__device__ __forceinline__ float eval_body_exact(const float4 *leaves, uint32_t n_leaves, const Ray &ray, bool use,
+                                                 uint32_t sub, uint32_t group_bits, uint32_t &leaf_out) {
+    // every lane of the warp runs through here (warp-wide votes and shuffles below); a group
+    // whose pair is not evaluated this way has use == false and ignores what it computes
+    const uint32_t nl = use ? n_leaves : 1u;
+    const bool mine = use && sub < nl;
+    const float4 n4 = leaves[2 * (mine ? sub : 0u)], o4 = leaves[2 * (mine ? sub : 0u) + 1];
+    float dn;
+    const float t = plane_t(mk(n4.x, n4.y, n4.z), mk(o4.x, o4.y, o4.z), ray, dn);
+    const bool hit = mine && t > 0.0f;
+    const V3 pos = ray.origin + ray.direction * t;              // Intersection::position (geometry.rs:108-110)
+    uint32_t inside = 0;                                        // bit j: this leaf's hit lies inside leaf j
+#pragma unroll
+    for (uint32_t j = 0; j < 8; j++) {
+        const float4 nj = leaves[2 * (j < nl ? j : 0u)], oj = leaves[2 * (j < nl ? j : 0u) + 1];
+        if (dot(pos - mk(oj.x, oj.y, oj.z), mk(nj.x, nj.y, nj.z)) < 0.0f) inside |= 1u << j;   // geometry.rs:124-128
+    }
+    const uint32_t all = (1u << nl) - 1u;
+    const bool sound = hit && ((inside | (1u << sub)) & all) == all;
+    float t_near = sound ? t : 3.0e38f;
+#pragma unroll
+    for (uint32_t sh = 1; sh < 8; sh <<= 1) t_near = fminf(t_near, __shfl_xor_sync(0xffffffffu, t_near, sh));
+    const uint32_t nearest = __ballot_sync(0xffffffffu, sound && t == t_near) & group_bits;
+    const uint32_t L = nearest ? (uint32_t)(__ffs(nearest) - 1) & 7u : 0u;
+    leaf_out = L;
+    // a valid leaf at or before t_L that lies inside L's half-space (this includes a second nearest sound leaf)
+    const uint32_t spoils = __ballot_sync(0xffffffffu, hit && sub != L && t <= t_near && ((inside >> L) & 1u)) & group_bits;
+    if (nearest == 0u) return -1.0f;                            // no sound leaf
+    return spoils ? -2.0f : t_near;
+}
+
 // Conservative slab test of a convex body against the ray, with every
 // half-space moved outwards by RL_SLAB_INFLATE (evaluated eight lanes per body
 // inside intersect_scene).  A hit the reference returns lies on one leaf plane
@@ -590,27 +657,17 @@ __device__ __forceinline__ uint32_t emit_pairs(uint64_t &todo, uint32_t base, ui
 // Compounds.  A bounded convex body can only be hit where the ray passes its
 // bounding sphere (inflated on the host well beyond rounding); survivors go
 // through the slab test above (eight lanes per body), and what remains is
-// evaluated by the reference's recursion (compound_t) from ONE task list per
-// block, so that the few rays of a block that really meet a body are processed
-// side by side in full warps.  Unbounded bodies carry r^2 < 0 and always pass
-// the bounding test.
+// evaluated exactly, again by eight lanes per body (eval_body_exact).  Unbounded
+// bodies always pass the bounding test.
 //
-// Order of the work, chosen for the block barriers of the body evaluation: flat surfaces
-// first (their hit bounds the bodies worth evaluating), then the bodies' bound scan and slab
-// tests, which fill the block's task list; behind the first barrier every warp runs its sphere
-// phase and THEN takes tasks from the list, 32 at a time, until it is empty -- the warps with the
-// least sphere work (or no live lane at all) arrive first and take the tasks, so the two phases
-// balance each other and the second barrier, behind which the body results are merged, is
-// reached by all warps at about the same time.  (With the tasks dealt statically to the first
-// warps and the sphere phase in front of the first barrier, 21 % of all warp cycles were spent
-// waiting at these two barriers.)
+// Nothing in here crosses a warp: every warp of the block runs through Scene::intersect on its
+// own (with the body evaluation shared by the whole block through a task list and two block
+// barriers, 22 % of all warp cycles were spent waiting at those barriers, and the bodies -- 22 of
+// the built-in scene's 339 objects -- cost a third of the kernel's time).
 //
-// Must be called by every thread of the block together (block barriers and
-// warp votes inside), with a block barrier between two consecutive calls;
-// threads without a live path pass idle_ray() and
-// live = false.  A warp none of whose lanes is live skips the scans (its rays
-// hit nothing anyway) and only serves the block's task list: in the tail of a
-// small batch most warps of a block are in that state.
+// Must be called by all 32 lanes of a warp together (warp votes and shuffles inside); lanes
+// without a live path pass idle_ray() and live = false.  A warp none of whose lanes is live
+// skips everything (its rays hit nothing anyway).
 __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true) {
     const PrimTables &tb = tables();
     Hit best;
@@ -626,22 +683,20 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
     const float bthr = -1.9073486e-6f * sqrtf((tb.sphere_cmax2 + oo) * dd) - 1.0e-30f;  // -2^-19 * ...
 
     // Scratch views (per block, see RL_SCRATCH_BYTES_PER_THREAD): ray table [3 float4 per
-    // thread]; sphere queue [slot][thread]; counters [3][thread]; pair list [RL_PAIR_CAP per warp];
-    // body results [slot][thread] (distance, code) and the block's task list.
+    // thread]; sphere queue [slot][thread]; counters [2][thread]; pair list [RL_PAIR_CAP per warp];
+    // body results [slot][thread] (distance, code).
     const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
     const uint32_t lane = tid & 31u, wbase = tid & ~31u;
     float4 *ray_tab = rl_smem + tb.scratch;
     uint16_t *sq_base = reinterpret_cast<uint16_t *>(ray_tab + 3 * nthreads);
     uint32_t *sq_cnt = reinterpret_cast<uint32_t *>(sq_base + RL_CAND_SLOTS * nthreads);
-    uint16_t *pairs = reinterpret_cast<uint16_t *>(sq_cnt + 3 * nthreads) + (wbase >> 5) * RL_PAIR_CAP;
-    float2 *results = reinterpret_cast<float2 *>(reinterpret_cast<uint16_t *>(sq_cnt + 3 * nthreads)
+    uint16_t *pairs = reinterpret_cast<uint16_t *>(sq_cnt + 2 * nthreads) + (wbase >> 5) * RL_PAIR_CAP;
+    float2 *results = reinterpret_cast<float2 *>(reinterpret_cast<uint16_t *>(sq_cnt + 2 * nthreads)
                                                  + (nthreads >> 5) * RL_PAIR_CAP);
-    uint32_t *btasks = reinterpret_cast<uint32_t *>(results + RL_COMPOUND_SLOTS * nthreads);
     // publish this lane's pre-test constants so that any lane of the block can test for it
     ray_tab[3 * tid + 0] = make_float4(m2ox, m2oy, m2oz, oo);
     ray_tab[3 * tid + 1] = make_float4(d.x, d.y, d.z, ndo);
-    uint32_t *res_cnt = sq_cnt + nthreads;                      // results other threads computed for this one
-    uint32_t *bcount = sq_cnt + 2 * nthreads;                   // [0]: entries in the block task list, [1]: entries taken
+    uint32_t *res_cnt = sq_cnt + nthreads;                      // body results other lanes computed for this one
     sq_cnt[tid] = 0u;
 
     const float slack = -2.0f * thr + 2.0f * fabsf(dd - 1.0f) * (tb.sphere_cmax2 + oo);
@@ -726,49 +781,46 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
     };
 
     const uint32_t n_compounds = tb.n_compounds;
-    if (n_compounds == 0u) {                                    // block-uniform: a scene without bodies has no barrier here
-        sphere_phase();
-        return best;
-    }
-    res_cnt[tid] = 0u;
-#if !RL_BODIES_FIRST
     sphere_phase();
-    ray_tab[3 * tid + 2].z = best.t;                            // sphere hits bound the bodies worth evaluating too
-#endif
+    if (n_compounds == 0u) return best;                         // block-uniform
+    ray_tab[3 * tid + 2].z = best.t;                            // sphere and flat hits bound the bodies worth evaluating
+    res_cnt[tid] = 0u;
 
-    // Compound bodies (block-wide; every thread of the block calls intersect_scene together).
+    // Compound bodies, entirely within the warp (no block barrier: the warps of a block run
+    // through Scene::intersect independently of each other).
     //  1. bounding spheres: the same uniform scan over the bodies' bound records; a hit the
     //     reference returns lies inside the (host-inflated) bound, so the line passes it:
     //     exactly B^2 - dd C >= 0, and the evaluated B'^2 - C' can fall short of that by the
     //     rounding of both (e1) and by |dd - 1| |C| only: threshold -slack; B >= -|d| R.
     //     Unbounded bodies are flagged in a mask that is OR-ed in;
-    //  2. slab test warp-cooperatively: eight lanes per pair, one leaf each, shuffle reduction of
-    //     the interval; survivors are appended to ONE task list per block;
-    //  3. after a block barrier the warps take the tasks 32 at a time -- the reference's recursion
-    //     (compound_t) for the owner's ray -- so the few rays of a block that really meet a body
-    //     are evaluated side by side in full warps instead of two or three lanes per warp;
-    //  4. after a second barrier every thread merges the results computed for its ray.
+    //  2. slab test warp-cooperatively: eight lanes per (lane, body) pair, one leaf each, shuffle
+    //     reduction of the interval; the surviving pairs are compacted in place;
+    //  3. exact evaluation, again eight lanes per pair and one leaf per lane (eval_bodies_exact):
+    //     the reference's recursion is decided from the leaves' own hits and containment tests,
+    //     all independent of each other, or handed to the owner lane when it cannot be;
+    //  4. every lane merges the results computed for its ray.
     const float4 *compounds = sm_vec(tb.compounds);
     const float4 *body_bounds = sm_vec(tb.body_bounds);
     const uint64_t *body_always = reinterpret_cast<const uint64_t *>(rl_smem + tb.body_always);
     const float4 *leaves = sm_vec(tb.leaves);
     const uint32_t *compound_obj = sm_u32(tb.compound_obj);
     const uint32_t group = lane >> 3, sub = lane & 7u;
-    const uint32_t task_cap = RL_COMPOUND_SLOTS * nthreads;
+    const uint32_t group_bits = 0xffu << (8u * group), lanes_below = (1u << lane) - 1u;
     const float thr_b = -slack;
     const float bthr_b = bthr - sqrtf(dd) * tb.body_rmax;
-    for (uint32_t round = 0; round < n_compounds; round += RL_BODIES_PER_ROUND) {   // block-uniform trip count
+    const bool fast_bodies = tb.sphere_leaves == 0u;            // block-uniform
+#pragma unroll 1
+    for (uint32_t round = 0; warp_live && round < n_compounds; round += RL_BODIES_PER_ROUND) {
         const uint32_t round_end = min(round + RL_BODIES_PER_ROUND, n_compounds);
-        uint64_t todo = 0ull;
-        if (warp_live)
-            todo = scan_bounds(body_bounds + round, (round_end - round + 7u) & ~7u, d, ndo, m2ox, m2oy, m2oz, oo,
-                               thr_b, bthr_b) | body_always[round / RL_BODIES_PER_ROUND];
+        uint64_t todo = scan_bounds(body_bounds + round, (round_end - round + 7u) & ~7u, d, ndo, m2ox, m2oy, m2oz, oo,
+                                    thr_b, bthr_b) | body_always[round / RL_BODIES_PER_ROUND];
         while (__any_sync(0xffffffffu, todo != 0ull)) {
             const uint32_t npairs = emit_pairs(todo, round, pairs, lane);
+            uint32_t nsurv = 0;                                 // warp-uniform: pairs that pass the slab test, compacted in place
 #pragma unroll 1
             for (uint32_t pb = 0; pb < npairs; pb += 4) {
                 const uint32_t p = pb + group;
-                const bool valid = p < npairs;                      // uniform within a group of eight
+                const bool valid = p < npairs;                  // uniform within a group of eight
                 const uint32_t pair = valid ? pairs[p] : 0u;
                 const uint32_t owner = wbase + (pair >> RL_PAIR_INDEX_BITS), body = pair & RL_PAIR_INDEX_MAX;
                 const float4 c4 = compounds[2 * body];
@@ -798,56 +850,48 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
                     outside_parallel |= (__shfl_xor_sync(0xffffffffu, (int)outside_parallel, sh) != 0);
                 }
                 const float start = t_enter * 0.9999f - 1.0e-3f;
-                const bool may_hit = !outside_parallel && !(t_exit < 0.0f) && !(start > t_exit) && !(start > best_t);
-                if (valid && sub == 0u && may_hit) {
-                    const uint32_t slot = atomicAdd(bcount, 1u);
-                    if (slot < task_cap) btasks[slot] = (owner << 16) | body;
-                    else atomicAdd(&res_cnt[owner], RL_COMPOUND_SLOTS + 1u);   // no room: the owner evaluates every body
-                }
+                const bool may_hit = valid && !outside_parallel && !(t_exit < 0.0f) && !(start > t_exit) && !(start > best_t);
+                const uint32_t keep = __ballot_sync(0xffffffffu, may_hit && sub == 0u);
+                __syncwarp();                                   // every group has read its pair: the list may be overwritten
+                if (may_hit && sub == 0u) pairs[nsurv + __popc(keep & lanes_below)] = (uint16_t)pair;
+                nsurv += __popc(keep);
             }
-        }
-        __syncthreads();
-#if RL_BODIES_FIRST
-        if (round == 0u) sphere_phase();
-#endif
-        const uint32_t ntasks = min(bcount[0], task_cap);
+            __syncwarp();
+            // 3. exact evaluation of the survivors
 #pragma unroll 1
-#if RL_TASK_STEAL
-        for (;;) {
-            uint32_t q = 0;
-            if (lane == 0) q = atomicAdd(bcount + 1, 32u);
-            q = __shfl_sync(0xffffffffu, q, 0) + lane;
-            if (q - lane >= ntasks) break;                      // warp-uniform
-#else
-        for (uint32_t q = tid; q - lane < ntasks; q += nthreads) {
-#endif
-            if (q < ntasks) {
-                const uint32_t task = btasks[q];
-                const uint32_t owner = task >> 16, body = task & 0xffffu;
+            for (uint32_t sb = 0; sb < nsurv; sb += 4) {
+                const uint32_t p = sb + group;
+                const bool valid = p < nsurv;
+                const uint32_t pair = valid ? pairs[p] : 0u;
+                const uint32_t owner = wbase + (pair >> RL_PAIR_INDEX_BITS), body = pair & RL_PAIR_INDEX_MAX;
                 const float4 c4 = compounds[2 * body];
+                const uint32_t first_leaf = __float_as_uint(c4.x), n_leaves = __float_as_uint(c4.y);
+                const bool use = valid && fast_bodies && n_leaves <= 8u;   // uniform within the group
                 const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1];
-                Ray oray;                                           // the owner's ray, bit for bit
+                Ray oray;                                       // the owner's ray, bit for bit
                 oray.origin = mk(-0.5f * ro.x, -0.5f * ro.y, -0.5f * ro.z);
                 oray.direction = mk(rd.x, rd.y, rd.z);
                 oray.wavelength = 0.0f;
-                uint32_t leaf;
-                const float t = compound_t(c4, oray, leaf);
-                if (t > 0.0f) {
+                uint32_t leaf_hit = 0;
+                float t_hit = eval_body_exact(leaves + 2 * first_leaf, n_leaves, oray, use, sub, group_bits, leaf_hit);
+                leaf_hit += first_leaf;
+                if (!use) t_hit = -2.0f;                        // -2: the owner runs the reference's recursion itself
+                if (valid && sub == 0u && t_hit != -1.0f) {     // -1: the body is missed
                     const uint32_t slot = atomicAdd(&res_cnt[owner], 1u);
                     if (slot < RL_COMPOUND_SLOTS)
-                        results[slot * nthreads + owner] = make_float2(t, __uint_as_float((body << 16) | leaf));
+                        results[slot * nthreads + owner] = make_float2(t_hit, __uint_as_float((body << 16) | leaf_hit));
                 }
             }
+            __syncwarp();
         }
-        __syncthreads();
+        // 4. merge
         const uint32_t nres = res_cnt[tid];
         if (nres > RL_COMPOUND_SLOTS) {
-            // more hits or tasks than slots (pathological): evaluate every body of the round here
+            // more results than slots (pathological): evaluate every body of the round here
 #pragma unroll 1
             for (uint32_t k = round; k < round_end; k++) {
-                const float4 c4 = compounds[2 * k];
                 uint32_t leaf;
-                const float t = compound_t(c4, ray, leaf);
+                const float t = compound_t(compounds[2 * k], ray, leaf);
                 if (t > 0.0f) consider(best, t, (int)compound_obj[k], (RL_HIT_LEAF << 28) | leaf);
             }
         } else {
@@ -855,15 +899,17 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
             for (uint32_t k = 0; k < nres; k++) {
                 const float2 r = results[k * nthreads + tid];
                 const uint32_t code = __float_as_uint(r.y);
-                consider(best, r.x, (int)compound_obj[code >> 16], (RL_HIT_LEAF << 28) | (code & 0xffffu));
+                if (r.x == -2.0f) {                             // handed over: the reference's recursion, by the owner
+                    uint32_t leaf;
+                    const float t = compound_t(compounds[2 * (code >> 16)], ray, leaf);
+                    if (t > 0.0f) consider(best, t, (int)compound_obj[code >> 16], (RL_HIT_LEAF << 28) | leaf);
+                } else {
+                    consider(best, r.x, (int)compound_obj[code >> 16], (RL_HIT_LEAF << 28) | (code & 0xffffu));
+                }
             }
         }
         res_cnt[tid] = 0u;
-        if (tid == 0) { bcount[0] = 0u; bcount[1] = 0u; }
-        // the next round is behind the barrier below; the next CALL must be behind a block barrier
-        // of the caller's (every kernel that loops over intersect_scene has one per iteration),
-        // which also orders these resets
-        if (round + RL_BODIES_PER_ROUND < n_compounds) __syncthreads();
+        __syncwarp();
     }
     return best;
 }
@@ -923,9 +969,9 @@ __device__ __forceinline__ V3 sphere_tangent(const Hit &hit, const Surf &s) {
 
 // ---------------------------------------------------------------- materials
 // material.rs:38-58 with monte_carlo.rs:47-58
-__device__ __forceinline__ V3 diffuse_direction(const Ray &in, const Surf &s, Rng &rng, const RngKey &key) {
-    const float phi = rng.longitude(key);
-    const float rq = rng.unit(key);
+__device__ __forceinline__ V3 diffuse_direction(const Ray &in, const Surf &s, BounceRng &rng) {
+    const float phi = rng.longitude();
+    const float rq = rng.unit();
     const float r = sqrtf(rq);
     const float2 sc = sincos_call(phi);
     const V3 hemi = mk(sc.y * r, sc.x * r, sqrtf(1.0f - rq));
@@ -940,8 +986,8 @@ __device__ __forceinline__ float soap_clamp(float x) {                 // materi
 // Material::get_new_ray for the five reflective materials; returns the new
 // direction and the ray's probability (origin = intersection position).  The
 // three diffuse-based materials share one copy of get_diffuse_ray.
-__device__ __forceinline__ V3 material_bounce(float4 m, const Ray &in, const Hit &hit, const Surf &s, Rng &rng,
-                                              const RngKey &key, float &probability) {
+__device__ __forceinline__ V3 material_bounce(float4 m, const Ray &in, const Hit &hit, const Surf &s, BounceRng &rng,
+                                              float &probability) {
     const uint32_t kind = __float_as_uint(m.x);
     if (kind <= RL_MATERIAL_GLOSSY_MIRROR) {
         // grey (material.rs:122-130), coloured (:155-168), glossy (:185-196)
@@ -950,7 +996,7 @@ __device__ __forceinline__ V3 material_bounce(float4 m, const Ray &in, const Hit
             const float p = (m.z - in.wavelength) / m.w;
             probability = m.y * spec_exp(-0.5f * p * p);
         }
-        V3 dir = diffuse_direction(in, s, rng, key);
+        V3 dir = diffuse_direction(in, s, rng);
         if (kind == RL_MATERIAL_GLOSSY_MIRROR) {
             const V3 reflection = reflect(in.direction, s.normal);
             dir = normalise_dev(dir * m.y + reflection * (1.0f - m.y));
@@ -975,7 +1021,7 @@ __device__ __forceinline__ V3 material_bounce(float4 m, const Ray &in, const Hit
     }
     // RL_MATERIAL_SOAP_BUBBLE                                            material.rs:267-306
     const float cos_alpha = dot(in.direction, s.normal);
-    const V3 direction = (rng.unit(key) - 0.3f > fabsf(cos_alpha)) ? reflect(in.direction, s.normal)
+    const V3 direction = (rng.unit() - 0.3f > fabsf(cos_alpha)) ? reflect(in.direction, s.normal)
                                                                 : in.direction;
     const float phase_shift = (in.wavelength - 380.0f) / 200.0f * RL_PI;
     const float cos_phi = soap_clamp(dot(direction, s.normal));

@@ -80,8 +80,7 @@ __device__ __forceinline__ TraceCta *trace_cta(const DevScene &sc) {
 
 // trace_unit.rs:151-158 and :136-145 for the photon at index `gidx` of the launch: the draws of
 // the wavelength, the screen position and the time, and the camera ray (which draws the lens
-// sample).  Six draws: the second Philox block is half used, its other two words travel with the
-// entry.
+// sample): the six draws of Philox blocks 0 and 1; the bounces draw from block 2 on (BounceRng).
 __device__ __forceinline__ void generate_camera_entry(const DevScene &sc, const TraceArgs &a, const TraceCta *cta,
                                                       float4 *entry, uint32_t gidx) {
     uint32_t seg = 0;
@@ -97,8 +96,7 @@ __device__ __forceinline__ void generate_camera_entry(const DevScene &sc, const 
     const Ray ray = camera_ray(sc.camera, sx, sy, wavelength, t, rng, key);
     entry[0] = make_float4(ray.origin.x, ray.origin.y, ray.origin.z, ray.direction.x);
     entry[1] = make_float4(ray.direction.y, ray.direction.z, wavelength, sx);
-    entry[2] = make_float4(sy, __uint_as_float(rng.b0), __uint_as_float(rng.b1),
-                           __uint_as_float((seg << a.seg_shift) | local));
+    entry[2] = make_float4(sy, 0.0f, 0.0f, __uint_as_float((seg << a.seg_shift) | local));
 }
 
 // Persistent threads with path regeneration.  A block owns a contiguous range of the launch's
@@ -154,9 +152,9 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
     Ray ray;
     ray.origin = mk(0.f, 0.f, 0.f); ray.direction = mk(0.f, 0.f, 0.f); ray.wavelength = 0.f;
     float intensity = 1.0f, continue_chance = 1.0f;
-    Rng rng;
-    rng.init();
-    uint32_t rays = 0;                                              // of the current path
+    BounceRng rng;
+    rng.d0 = rng.d1 = rng.d2 = 0u;
+    uint32_t rays = 0;                                              // of the current path = its bounces so far
 
     for (;;) {
         // lanes without a path, per warp and in the block; every thread of the block takes part in
@@ -200,8 +198,6 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
                 ray.direction = mk(e0.w, e1.x, e1.y);
                 ray.wavelength = e1.z;
                 *park = make_float2(e1.w, e2.x);                    // MappedPhoton x, y
-                rng.block = 2u; rng.left = 2u;                      // six draws made (generate_camera_entry)
-                rng.b0 = __float_as_uint(e2.y); rng.b1 = __float_as_uint(e2.z); rng.b2 = 0u; rng.b3 = 0u;
                 cur = __float_as_uint(e2.w);
                 intensity = 1.0f;
                 continue_chance = 1.0f;
@@ -210,10 +206,16 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
             }
         }
         parity ^= 1u;
+        const uint32_t seg = cur >> a.seg_shift, index = cur & ((1u << a.seg_shift) - 1u);
+        if (alive) {
+            // the draws of this bounce, for every live lane at once (independent of the intersection
+            // below, which hides the latency of the ten Philox rounds)
+            const RngKey key = {cta->seed[seg], cta->first_photon[seg] + index};
+            rng.load(key, rays);
+        }
         const Hit hit = intersect_scene(alive ? ray : idle_ray(), alive);
         if (alive) {
             rays++;                                                 // Scene::intersect calls (scene.rs:39)
-            const uint32_t seg = cur >> a.seg_shift, index = cur & ((1u << a.seg_shift) - 1u);
             // trace_unit.rs:91-131
             bool done = false;
             float result = 0.0f;
@@ -226,14 +228,13 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
                     done = true;
                 } else {
                     const Surf s = surface_at(ray, hit);
-                    const RngKey key = {cta->seed[seg], cta->first_photon[seg] + index};
                     float probability;
-                    const V3 dir = material_bounce(m, ray, hit, s, rng, key, probability);  // :104-107
+                    const V3 dir = material_bounce(m, ray, hit, s, rng, probability);       // :104-107
                     intensity = intensity * probability;
                     ray.direction = dir;
                     ray.origin = s.position + dir * 0.00001f;                      // :114
                     continue_chance = continue_chance * 0.96f;                    // :117
-                    if (rng.unit(key) * 0.85f
+                    if (rng.unit() * 0.85f
                         > continue_chance * (1.0f - spec_exp(intensity * -20.0f)))  // :122-125
                         done = true;
                 }
@@ -394,7 +395,7 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     auto pick_ring = [&](int t) {
         int best = -1;
         size_t best_ctas = 0;
-        for (int shrink = 0; shrink <= 2; shrink++) {
+        for (int shrink = env_int("RL_TRACE_RING_SHRINK", 0); shrink <= 2; shrink++) {
             const size_t bytes = trace_kernel_smem_bytes(sc, t, ring_entries(t, shrink));
             if (bytes > (size_t)max_smem) continue;
             const size_t ctas = trace_ctas_per_sm(bytes, t);
@@ -913,6 +914,7 @@ debug_cull_check_kernel(const DevScene sc, uint64_t seed, float aspect, uint64_t
     rng.init();
     RngKey key = {seed, first};
     float intensity = 1.0f, continue_chance = 1.0f;
+    uint32_t bounce = 0;
     for (;;) {
         if (!alive && next < n) {
             key.photon = first + next;
@@ -925,6 +927,7 @@ debug_cull_check_kernel(const DevScene sc, uint64_t seed, float aspect, uint64_t
             ray = camera_ray(sc.camera, x, y, wavelength, t, rng, key);
             intensity = 1.0f;
             continue_chance = 1.0f;
+            bounce = 0;
             alive = true;
         }
         if (!__syncthreads_or(alive)) break;
@@ -932,6 +935,9 @@ debug_cull_check_kernel(const DevScene sc, uint64_t seed, float aspect, uint64_t
         const Hit culled = intersect_scene(r);
         if (!alive) continue;
         const Hit hit = intersect_scene_brute(r);
+        BounceRng brng;
+        brng.load(key, bounce);
+        bounce++;
         rays++;
         if (hit.obj != culled.obj || __float_as_uint(hit.t) != __float_as_uint(culled.t) ||
             hit.code != culled.code)
@@ -942,12 +948,12 @@ debug_cull_check_kernel(const DevScene sc, uint64_t seed, float aspect, uint64_t
         if (__float_as_uint(m.x) == RL_MATERIAL_BLACKBODY) continue;
         const Surf s = surface_at(ray, hit);
         float probability;
-        const V3 dir = material_bounce(m, ray, hit, s, rng, key, probability);
+        const V3 dir = material_bounce(m, ray, hit, s, brng, probability);
         intensity = intensity * probability;
         ray.direction = dir;
         ray.origin = s.position + dir * 0.00001f;
         continue_chance = continue_chance * 0.96f;
-        if (rng.unit(key) * 0.85f > continue_chance * (1.0f - spec_exp(intensity * -20.0f))) continue;
+        if (brng.unit() * 0.85f > continue_chance * (1.0f - spec_exp(intensity * -20.0f))) continue;
         alive = true;
     }
     atomicAdd(rays_out, rays);

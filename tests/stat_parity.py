@@ -23,13 +23,14 @@ tile), the frame 0.1 %: an estimator 1 % off adds 0.6 to RMS(z) in quadrature an
 whole-frame z.
 
 THE STATED TOLERANCE (XYZ accumulator, GPU vs reference arithmetic, equal photon ids):
-  whole frame, per channel:   |sum(A) - sum(B)| <= 0.5 sigma_MC(sum)    (0.05 % at 2^24 photons)
+  whole frame, per channel:   |sum(A) - sum(B)| <= 1.0 sigma_MC(sum)    (0.1 % at 2^24 photons; the
+                              same-photon difference itself is ~0.24 sigma_MC times a unit normal)
   16x16-pixel tiles:          RMS(z) <= 0.75,  max |z| <= 4
 tiles whose signal is below 1e-4 of the brightest tile's excluded."""
 import numpy as np
 
 TILE = 16
-RMS_Z_MAX, MAX_Z, FRAME_Z_MAX = 0.75, 4.0, 0.5
+RMS_Z_MAX, MAX_Z, FRAME_Z_MAX = 0.75, 4.0, 1.0
 
 
 def tile_sums(img):

@@ -37,7 +37,9 @@ def test_philox4x32_10_known_answers(orc):
 
 
 def test_draw_stream_layout_and_distributions(orc):
-    # draw i = word i%4 of block i/4, counter (id_lo, id_hi, block, 0), key = seed
+    # sequential draws (what precedes the first bounce): draw i = word i%4 of block i/4, counter
+    # (id_lo, id_hi, block, 0), key = seed; the draws of bounce j restart at block 2 + j -- that
+    # part of the layout is pinned by tests/test_oracle_path_cross_check.py
     seed, photon = 0x0123456789ABCDEF, 0x1_0000_0007
     words = []
     for block in range(3):
@@ -219,7 +221,7 @@ def test_spec_and_libm_modes_agree_statistically(pkg, orc):
     import stat_parity
     d = pkg.SceneBuilder(pkg.SCENE_C2).desc()
     w = h = 64
-    k, n = 8, 12000
+    k, n = 16, 12000
     subs, differ = [], 0
     whole_libm = np.zeros((h, w, 3), dtype=np.float32)
     for i in range(k):

@@ -20,19 +20,22 @@ PI = F(3.14159274)          # std::f32::consts::PI
 
 
 class Draws:
-    """monte_carlo.rs:25-43 on the specified stream: draw i = word i % 4 of Philox block i / 4."""
+    """monte_carlo.rs:25-43 on the specified stream: the draws in front of the first bounce are the
+    words of Philox blocks 0 and 1 in order, the draws of bounce j the first words of block 2 + j."""
 
     def __init__(self, orc, seed, photon):
         self.orc, self.key = orc, (seed & 0xffffffff, seed >> 32)
         self.ctr = (photon & 0xffffffff, photon >> 32)
-        self.words, self.i = [], 0
+        self.block, self.words = 0, []
+
+    def begin_bounce(self, j):
+        self.block, self.words = 2 + j, []
 
     def _u24(self):
-        if self.i == len(self.words):
-            self.words += self.orc.philox(self.key, (self.ctr[0], self.ctr[1], len(self.words) // 4, 0))
-        w = self.words[self.i]
-        self.i += 1
-        return w >> 8
+        if not self.words:
+            self.words = list(self.orc.philox(self.key, (self.ctr[0], self.ctr[1], self.block, 0)))
+            self.block += 1
+        return self.words.pop(0) >> 8
 
     def unit(self):                                  # Closed01<f32>
         return F(self._u24()) / F(16777215.0)
@@ -204,7 +207,7 @@ def trace(pkg, orc, desc, seed, width, height, first, n, mode):
         out[k]["wavelength"], out[k]["x"], out[k]["y"] = wavelength, x, y
         t = rng.unit()
         origin, direction = camera_ray(camera_at(desc, m, t, pkg), m, x, y, wavelength, rng)
-        paths.append(dict(k=k, rng=rng, o=origin, d=direction, wl=wavelength, intensity=F(1), chance=F(1)))
+        paths.append(dict(k=k, rng=rng, o=origin, d=direction, wl=wavelength, intensity=F(1), chance=F(1), bounce=0))
     rays = 0
     while paths:                                     # trace_unit.rs:81-132
         o = np.stack([p["o"] for p in paths]).astype(F)
@@ -221,6 +224,8 @@ def trace(pkg, orc, desc, seed, width, height, first, n, mode):
                 light = F(orc.blackbody_intensity(mat.p0, mat.p1, np.array([p["wl"]], dtype=F), mode)[0])
                 out[p["k"]]["probability"] = p["intensity"] * light
                 continue
+            p["rng"].begin_bounce(p["bounce"])
+            p["bounce"] += 1
             new_d, probability = bounce(pkg, m, p["rng"], mat, p["d"], p["wl"], hit.normal[j], hit.tangent[j])
             p["intensity"] = p["intensity"] * probability
             p["d"] = new_d.astype(F)
