@@ -25,9 +25,6 @@ void kernel_launches_reset() { g_launches.store(0); }
 #ifndef RL_TRACE_THREADS
 #define RL_TRACE_THREADS 768
 #endif
-#ifndef RL_RING_STATE_SMEM
-#define RL_RING_STATE_SMEM 0     // 1: the camera-ray ring counters live in shared memory; 0: in registers of every thread (2963 vs 2916 Mrays/s)
-#endif
 #ifndef RL_TRACE_MIN_BLOCKS
 #define RL_TRACE_MIN_BLOCKS 1
 #endif
@@ -46,32 +43,30 @@ void kernel_launches_reset() { g_launches.store(0); }
 struct TraceArgs {
     uint32_t n_seg;
     uint32_t seg_shift;        // a path remembers its photon as (segment << seg_shift) | index within the segment
-    uint32_t ring_cap;         // camera-ray ring entries per CTA (a power of two)
+    uint32_t ring_cap;         // block ring: camera rays it holds (a power of two); warp rings hold RL_WARP_RING_ENTRIES
     int width, height;
     float aspect;
     float4 *accum;
     TraceSegment seg[RL_MAX_SEGMENTS];
 };
 
-// Per-CTA bookkeeping in shared memory, behind the intersection scratch; the camera-ray ring
-// (ring_cap entries of three float4) follows it.
+// Per-CTA bookkeeping in shared memory, behind the intersection scratch; the threads' parked
+// screen positions and the warps' camera-ray rings follow it.
 struct TraceCta {
     uint64_t seed[RL_MAX_SEGMENTS];
     uint64_t first_photon[RL_MAX_SEGMENTS];
     rl_mapped_photon *records[RL_MAX_SEGMENTS];
     uint32_t seg_start[RL_MAX_SEGMENTS + 1];   // first index of each segment in the launch's concatenated photon range
     uint32_t seg_rays[RL_MAX_SEGMENTS];        // Scene::intersect calls of the paths this CTA finished, per segment
-    uint32_t warp_dead[2][32];                 // lanes without a path, per warp (double-buffered by iteration parity)
-    // the ring: entries handed out / produced so far, next photon to generate, end of the block's
-    // range.  Double-buffered like warp_dead: every thread reads [parity] behind the loop's
-    // barrier, thread 0 writes [parity ^ 1] for the next iteration.
-    uint4 ring_state[2];
-    uint32_t pad[3];
+    uint32_t pool_next;                        // warp rings: next photon of the block's range that no warp has taken yet
+    uint32_t warp_dead[2][32];                 // block ring: lanes without a path, per warp (double-buffered by iteration parity)
+    uint32_t pad[2];
 };
 // behind TraceCta: the screen position of every thread's current photon (float2 per thread; only
-// read again when the path ends), then the camera-ray ring
+// read again when the path ends), then the camera-ray ring(s): one per block or one per warp
 #define RL_TRACE_PARK_BYTES_PER_THREAD 8
-static_assert(sizeof(TraceCta) % 16 == 0, "the ring behind TraceCta holds float4");
+#define RL_WARP_RING_ENTRIES 32u               // per warp, three float4 each
+static_assert(sizeof(TraceCta) % 16 == 0, "the rings behind TraceCta hold float4");
 
 __device__ __forceinline__ TraceCta *trace_cta(const DevScene &sc) {
     char *base = reinterpret_cast<char *>(rl_smem + RL_TABLES_VEC4 + sc.smem_vec4);
@@ -100,22 +95,37 @@ __device__ __forceinline__ void generate_camera_entry(const DevScene &sc, const 
 }
 
 // Persistent threads with path regeneration.  A block owns a contiguous range of the launch's
-// photons.  Camera rays are produced in bulk: whenever the block's ring of ready camera rays
-// cannot serve the lanes whose paths have just ended, EVERY thread of the block generates one
-// (the RNG draws, three sines and cosines, two normalisations and two quaternion rotations of
+// photons.  Camera rays are produced in bulk into a ring of ready rays: whenever the ring cannot
+// serve the lanes whose paths have just ended, ALL threads that share it generate one (the RNG
+// draws, three sines and cosines, two normalisations and two quaternion rotations of
 // trace_unit.rs:136-145 / camera.rs:47-108 run with full warps instead of for the two lanes in
 // seven that need a new path in a given iteration), and a lane takes its next photon from the ring
 // the moment the path it holds ends -- so a warp never idles on its longest path (1 ... ~150
-// bounces) and no lane idles while the block has photons left.  The result of a photon depends on
-// its id alone, so the deal changes nothing but the order of the accumulator atomics.  The
+// bounces) and no lane idles while the block has photons left.  The result of a photon depends
+// on its id alone, so the deal changes nothing but the order of the accumulator atomics.  The
 // primitive tables live in shared memory; each loop iteration is one Scene::intersect plus one
 // material interaction for every live lane.
+//
+// Nothing in an iteration crosses a warp (Scene::intersect does not either), and the kernel
+// exists in two forms:
+//   BLOCK_RING = false: one ring per warp, no block barrier between set-up and the final ray
+//     count; a warp with a long iteration holds nobody back.
+//   BLOCK_RING = true: one ring per block, refilled by all its threads together, and the block's
+//     warps meet at ONE barrier per iteration.  That barrier is there for the instruction cache:
+//     the loop's code (sphere scan, bodies, six materials, two f64 functions) is larger than the
+//     cache, and warps that drift apart fetch different parts of it -- free-running, the built-in
+//     scene is 22 % slower (4.5 instruction-fetch stall cycles per issued instruction instead of
+//     0.3).  Scenes without compound bodies execute a small enough part of the loop and are
+//     10-20 % faster free-running: launch_trace picks the form by that.
+template <bool BLOCK_RING>
 __global__ void __launch_bounds__(RL_TRACE_THREADS, RL_TRACE_MIN_BLOCKS)
 trace_kernel(const DevScene sc, const TraceArgs a) {
     setup_tables(sc);
     TraceCta *cta = trace_cta(sc);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     float2 *park = reinterpret_cast<float2 *>(cta + 1) + threadIdx.x;
-    float4 *ring = reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(cta + 1) + ((blockDim.x + 1u) & ~1u));
+    float4 *ring = reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(cta + 1) + ((blockDim.x + 1u) & ~1u))
+                   + (BLOCK_RING ? 0u : 3u * RL_WARP_RING_ENTRIES * warp);
     if (threadIdx.x < RL_MAX_SEGMENTS) {
         const uint32_t k = threadIdx.x;
         cta->seg_rays[k] = 0u;
@@ -129,24 +139,16 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
         uint32_t at = 0;
         for (uint32_t k = 0; k < a.n_seg; k++) { cta->seg_start[k] = at; at += (uint32_t)a.seg[k].n_photons; }
         cta->seg_start[a.n_seg] = at;
+        cta->pool_next = (uint32_t)((uint64_t)at * blockIdx.x / gridDim.x);
     }
     __syncthreads();
+    const uint32_t pool_begin = (uint32_t)((uint64_t)cta->seg_start[a.n_seg] * blockIdx.x / gridDim.x);
+    const uint32_t pool_end = (uint32_t)((uint64_t)cta->seg_start[a.n_seg] * (blockIdx.x + 1ull) / gridDim.x);
 
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t parity = 0;
-#if RL_RING_STATE_SMEM
-    if (threadIdx.x == 0) {
-        const uint32_t total = cta->seg_start[a.n_seg];
-        cta->ring_state[0] = make_uint4(0u, 0u, (uint32_t)((uint64_t)total * blockIdx.x / gridDim.x),
-                                        (uint32_t)((uint64_t)total * (blockIdx.x + 1ull) / gridDim.x));
-    }
-    // (the loop's first barrier publishes it)
-#else
-    // the same, kept by every thread in registers
-    uint4 ring_regs = make_uint4(0u, 0u, (uint32_t)((uint64_t)cta->seg_start[a.n_seg] * blockIdx.x / gridDim.x),
-                                 (uint32_t)((uint64_t)cta->seg_start[a.n_seg] * (blockIdx.x + 1ull) / gridDim.x));
-#endif
-
+    // the ring the thread takes its camera rays from, as every thread that shares it sees it:
+    // entries produced / handed out so far; block ring: next photon to generate
+    uint32_t tail = 0, head = 0, gen_next = pool_begin, parity = 0;
+    bool pool_empty = false;
     bool alive = false;
     uint32_t cur = 0;                                               // (segment << seg_shift) | photon index in it
     Ray ray;
@@ -157,55 +159,67 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
     uint32_t rays = 0;                                              // of the current path = its bounces so far
 
     for (;;) {
-        // lanes without a path, per warp and in the block; every thread of the block takes part in
-        // the intersection (block barriers and warp votes inside), and this barrier also
-        // separates two calls of it
         const uint32_t want = __ballot_sync(0xffffffffu, !alive);
-        if (lane == 0) cta->warp_dead[parity][warp] = (uint32_t)__popc(want);
-        const uint32_t dead = (uint32_t)__syncthreads_count(!alive);
-        const uint32_t T = blockDim.x, cap_mask = a.ring_cap - 1u;
-#if RL_RING_STATE_SMEM
-        const uint4 rs = cta->ring_state[parity];                   // {head, tail, gen_next, gen_end}: block-uniform
-#else
-        const uint4 rs = ring_regs;
-#endif
-        uint32_t avail = rs.y - rs.x, tail = rs.y, n_new = 0u;
-        if (avail < dead && rs.z < rs.w) {
-            n_new = a.ring_cap - avail;
-            if (n_new > T) n_new = T;
-            if (n_new > rs.w - rs.z) n_new = rs.w - rs.z;
-            if (threadIdx.x < n_new)
-                generate_camera_entry(sc, a, cta, ring + 3u * ((tail + threadIdx.x) & cap_mask), rs.z + threadIdx.x);
-            __syncthreads();
-            tail += n_new; avail += n_new;
-        }
-        if (dead == T && avail == 0u) break;                        // no path alive, no photon left
-#if RL_RING_STATE_SMEM
-        if (threadIdx.x == 0)
-            cta->ring_state[parity ^ 1u] = make_uint4(rs.x + (dead < avail ? dead : avail), tail, rs.z + n_new, rs.w);
-#else
-        ring_regs = make_uint4(rs.x + (dead < avail ? dead : avail), tail, rs.z + n_new, rs.w);
-#endif
-        if (avail != 0u && want != 0u) {
-            // the lanes without a path take the oldest ready camera rays, in thread order: a
-            // warp's first entry is the number of such lanes in the warps before it
-            const uint32_t before = __reduce_add_sync(0xffffffffu, lane < warp ? cta->warp_dead[parity][lane] : 0u);
-            const uint32_t idx = rs.x + before + __popc(want & ((1u << lane) - 1u));
-            if (!alive && idx < tail) {
-                const float4 *e = ring + 3u * (idx & cap_mask);
-                const float4 e0 = e[0], e1 = e[1], e2 = e[2];
-                ray.origin = mk(e0.x, e0.y, e0.z);
-                ray.direction = mk(e0.w, e1.x, e1.y);
-                ray.wavelength = e1.z;
-                *park = make_float2(e1.w, e2.x);                    // MappedPhoton x, y
-                cur = __float_as_uint(e2.w);
-                intensity = 1.0f;
-                continue_chance = 1.0f;
-                rays = 0;
-                alive = true;
+        uint32_t slot = 0xffffffffu;                                // ring entry this lane takes
+        if (BLOCK_RING) {
+            // lanes without a path, per warp and in the block
+            if (lane == 0) cta->warp_dead[parity][warp] = (uint32_t)__popc(want);
+            const uint32_t dead = (uint32_t)__syncthreads_count(!alive);
+            const uint32_t T = blockDim.x, cap_mask = a.ring_cap - 1u;
+            uint32_t avail = tail - head;
+            if (avail < dead && gen_next < pool_end) {
+                uint32_t n_new = a.ring_cap - avail;
+                if (n_new > T) n_new = T;
+                if (n_new > pool_end - gen_next) n_new = pool_end - gen_next;
+                if (threadIdx.x < n_new)
+                    generate_camera_entry(sc, a, cta, ring + 3u * ((tail + threadIdx.x) & cap_mask), gen_next + threadIdx.x);
+                __syncthreads();
+                tail += n_new; gen_next += n_new; avail += n_new;
             }
+            if (dead == T && avail == 0u) break;                    // no path alive, no photon left
+            if (avail != 0u && want != 0u) {
+                // the lanes without a path take the oldest ready camera rays, in thread order: a
+                // warp's first entry is the number of such lanes in the warps before it
+                const uint32_t before = __reduce_add_sync(0xffffffffu, lane < warp ? cta->warp_dead[parity][lane] : 0u);
+                const uint32_t idx = head + before + __popc(want & ((1u << lane) - 1u));
+                if (!alive && idx < tail) slot = idx & cap_mask;
+            }
+            head += dead < avail ? dead : avail;
+            parity ^= 1u;
+        } else {
+            const uint32_t dead = (uint32_t)__popc(want);
+            uint32_t avail = tail - head;
+            if (avail < dead && !pool_empty) {
+                // refill: as many camera rays as the ring has room for, from the block's photon range
+                uint32_t n_new = RL_WARP_RING_ENTRIES - avail, base = 0;
+                if (lane == 0) base = atomicAdd(&cta->pool_next, n_new);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= pool_end) { n_new = 0; pool_empty = true; }
+                else if (n_new >= pool_end - base) { n_new = pool_end - base; pool_empty = true; }
+                if (lane < n_new)
+                    generate_camera_entry(sc, a, cta, ring + 3u * ((tail + lane) & (RL_WARP_RING_ENTRIES - 1u)), base + lane);
+                __syncwarp();
+                tail += n_new; avail += n_new;
+            }
+            if (dead == 32u && avail == 0u) break;                  // no path alive, no photon left for this warp
+            const uint32_t rank = (uint32_t)__popc(want & ((1u << lane) - 1u));
+            if (!alive && rank < avail) slot = (head + rank) & (RL_WARP_RING_ENTRIES - 1u);
+            head += dead < avail ? dead : avail;
         }
-        parity ^= 1u;
+        if (slot != 0xffffffffu) {
+            const float4 *e = ring + 3u * slot;
+            const float4 e0 = e[0], e1 = e[1], e2 = e[2];
+            ray.origin = mk(e0.x, e0.y, e0.z);
+            ray.direction = mk(e0.w, e1.x, e1.y);
+            ray.wavelength = e1.z;
+            *park = make_float2(e1.w, e2.x);                        // MappedPhoton x, y
+            cur = __float_as_uint(e2.w);
+            intensity = 1.0f;
+            continue_chance = 1.0f;
+            rays = 0;
+            alive = true;
+        }
+        if (!BLOCK_RING) __syncwarp();                              // the entries are read before a refill overwrites them
         const uint32_t seg = cur >> a.seg_shift, index = cur & ((1u << a.seg_shift) - 1u);
         if (alive) {
             // the draws of this bounce, for every live lane at once (independent of the intersection
@@ -262,28 +276,31 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
     }
 }
 
-// camera-ray ring entries for CTAs of `threads` threads: the power of two at or above the CTA
-// size (a refill is never cut short), or a half / a quarter of it (at least 128) when shared
-// memory is short -- lanes that find the ring empty wait one iteration for the next refill
-static uint32_t ring_entries(int threads, int shrink) {
+// block ring entries for CTAs of `threads` threads: the power of two at or above the CTA size (a
+// refill is never cut short), or a half / a quarter of it (at least 128) when shared memory is
+// short -- lanes that find the ring empty wait one iteration for the next refill
+static uint32_t block_ring_entries(int threads, int shrink) {
     uint32_t cap = 128;
     while ((int)cap < threads) cap <<= 1;
     for (int k = 0; k < shrink && cap > 128; k++) cap >>= 1;
     return cap;
 }
-// CTAs of `threads` threads that fit an SM with that ring (228 KB of shared memory, 1 KB reserved
-// per CTA; 2048 threads; 64 K registers at 80 per thread)
+// CTAs of `threads` threads that fit an SM (228 KB of shared memory, 1 KB reserved per CTA; 2048
+// threads; 64 K registers at 80 per thread)
 static size_t trace_ctas_per_sm(size_t smem, int threads) {
     const size_t by_smem = (228u * 1024u) / (smem + 1024u);
     const size_t by_threads = 2048u / (size_t)threads, by_regs = 65536u / (80u * (size_t)threads);
     const size_t cap = by_threads < by_regs ? by_threads : by_regs;
     return by_smem < cap ? by_smem : cap;
 }
+// ring_cap > 0: one ring of that many entries per block; 0: one ring per warp
 static size_t trace_kernel_smem_bytes(const DevScene &sc, int threads, uint32_t ring_cap) {
+    const size_t entries = ring_cap ? (size_t)ring_cap : (size_t)(threads / 32) * RL_WARP_RING_ENTRIES;
     return tracing_smem_bytes(sc, threads) + sizeof(TraceCta) + (size_t)RL_TRACE_PARK_BYTES_PER_THREAD * ((threads + 1) & ~1)
-           + (size_t)ring_cap * 3 * sizeof(float4);
+           + entries * 3 * sizeof(float4);
 }
 size_t trace_smem_bytes(const DevScene &sc, int threads) { return tracing_smem_bytes(sc, threads); }
+
 
 // Small launches in flight: one mark per stream, an event re-recorded behind that stream's latest
 // small launch.  launch_trace (under its lock) counts the OTHER streams whose mark has not
@@ -378,25 +395,28 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     // units (each on its own stream) take turns setting them and launching
     static std::mutex launch_lock;
     std::lock_guard<std::mutex> guard(launch_lock);
-    // the largest CTA (up to RL_TRACE_THREADS) whose tables + scratch fit the shared memory of an SM:
-    // big CTAs fill the per-CTA task list of the body evaluation best
     static KernelCache cache[16];
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
     KernelCache scratch_entry;
-    KernelCache &cached = dev >= 0 && dev < 16 ? cache[dev] : scratch_entry;
-    err = prepare_kernel(trace_kernel, cached, dev);
+    // which form of the kernel: see trace_kernel.  RL_TRACE_LOCKSTEP overrides (experiments).
+    const bool block_ring = env_int("RL_TRACE_LOCKSTEP", sc.n_compounds != 0u ? 1 : 0) != 0;
+    static KernelCache cache_free[16];
+    KernelCache &cached = block_ring ? (dev >= 0 && dev < 16 ? cache[dev] : scratch_entry)
+                                     : (dev >= 0 && dev < 16 ? cache_free[dev] : scratch_entry);
+    err = block_ring ? prepare_kernel(trace_kernel<true>, cached, dev) : prepare_kernel(trace_kernel<false>, cached, dev);
     if (err != cudaSuccess) return err;
     const int max_smem = cached.max_smem;
     int threads = env_int("RL_TRACE_THREADS_MAX", RL_TRACE_THREADS);
     if (threads > RL_TRACE_THREADS || threads < 128 || threads % 128) threads = RL_TRACE_THREADS;
-    // the largest CTA that fits, with the roomiest ring that does not cost a resident CTA
-    auto pick_ring = [&](int t) {
+    // the largest CTA that fits; block ring: the roomiest one that does not cost a resident CTA
+    auto pick_ring = [&](int t) -> int {
+        if (!block_ring) return trace_kernel_smem_bytes(sc, t, 0) <= (size_t)max_smem ? 0 : -1;
         int best = -1;
         size_t best_ctas = 0;
-        for (int shrink = env_int("RL_TRACE_RING_SHRINK", 0); shrink <= 2; shrink++) {
-            const size_t bytes = trace_kernel_smem_bytes(sc, t, ring_entries(t, shrink));
+        for (int shrink = 0; shrink <= 2; shrink++) {
+            const size_t bytes = trace_kernel_smem_bytes(sc, t, block_ring_entries(t, shrink));
             if (bytes > (size_t)max_smem) continue;
             const size_t ctas = trace_ctas_per_sm(bytes, t);
             if (ctas > best_ctas) { best_ctas = ctas; best = shrink; }
@@ -428,16 +448,18 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
         shrink = pick_ring(threads);
         if (shrink < 0) return cudaErrorInvalidValue;
     }
-    const uint32_t ring_cap = ring_entries(threads, shrink);
+    const uint32_t ring_cap = block_ring ? block_ring_entries(threads, shrink) : 0u;
     const size_t smem = trace_kernel_smem_bytes(sc, threads, ring_cap);
     if (cached.threads != threads || cached.smem != smem) {
         int occ = 0;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_kernel, threads, smem);
+        err = block_ring ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_kernel<true>, threads, smem)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_kernel<false>, threads, smem);
         if (err != cudaSuccess) return err;
         cached.threads = threads; cached.smem = smem; cached.per_sm = occ < 1 ? 1 : occ;
     }
     const int per_sm = cached.per_sm;
-    set_carveout(trace_kernel, cached, per_sm, smem);
+    if (block_ring) set_carveout(trace_kernel<true>, cached, per_sm, smem);
+    else set_carveout(trace_kernel<false>, cached, per_sm, smem);
     uint64_t full = (uint64_t)sm_count * per_sm;
     if (small) {
         // The launch's share of the GPU's block slots, by the concurrency seen: with k other
@@ -480,7 +502,8 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
         }
         const uint64_t want = (n_launch + threads - 1) / threads;
         const unsigned grid = (unsigned)(want < full ? want : full);
-        trace_kernel<<<grid, threads, smem, st>>>(sc, a);
+        if (block_ring) trace_kernel<true><<<grid, threads, smem, st>>>(sc, a);
+        else trace_kernel<false><<<grid, threads, smem, st>>>(sc, a);
         g_launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
