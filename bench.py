@@ -613,11 +613,13 @@ def main():
             entry_["note"] = ("fused trace+splat, weak scaling (every rank its own photon ids), CUDA events; "
                               "a sample of the config's photon count, the rate does not depend on it")
             other_configs.append(entry_)
-        if world == 8:
-            # configs[4] in full: 4096^2, 4096 spp = 2^36 photons over the 8 GPUs, one exchange of the
-            # XYZ frame, Kahan gather and tonemap on rank 0
+        c5_spp = int(os.environ.get("RL_BENCH_C5_SPP", "4096" if world == 8 else "0"))
+        if c5_spp > 0 and world > 1:
+            # configs[4] in full (at 8 GPUs): 4096^2, 4096 spp = 2^36 photons over the GPUs, one exchange
+            # of the XYZ frame, Kahan gather and tonemap on rank 0.  (RL_BENCH_C5_SPP runs the same
+            # code at another world size / sample count: how this block is tested on two GPUs.)
             w5 = h5 = 4096
-            n5 = (w5 * h5 * 4096) // world
+            n5 = (w5 * h5 * c5_spp) // world
             tu5 = pkg.TraceUnit(700 + rank, w5, h5, seed=SEED, batch=n5)
             pl5 = pkg.PlotUnit(700 + rank, w5, h5)
             g5 = pkg.GatherUnit(w5, h5)
@@ -644,7 +646,8 @@ def main():
             dist.all_reduce(rr, op=dist.ReduceOp.SUM)
             c5 = {"config": "c5", "workload": CONFIGS["c5"]["workload"], "mrays_per_s": int(rr[0]) / float(ms[0]) / 1e3,
                   "seconds": float(ms[0]) / 1e3, "photons": n5 * world, "rays_per_photon": int(rr[0]) / (n5 * world),
-                  "n_gpus": world, "note": "one full pass: 2^33 photons per GPU, one frame exchange, gather + tonemap on rank 0"}
+                  "n_gpus": world, "spp": c5_spp,
+                  "note": f"one full pass: {n5} photons per GPU, one frame exchange, gather + tonemap on rank 0"}
             ex5.close()
             del tu5, pl5, g5, tm5
 

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define RL_ABI_VERSION 2
+#define RL_ABI_VERSION 3
 
 /* trace_unit.rs:67 -- photons per TraceUnit batch (1024 under cfg(test), :70) */
 #define RL_BATCH_PHOTONS (1024u * 512u)
@@ -119,7 +119,7 @@ typedef struct rl_camera {
 } rl_camera;
 
 /*
- * scene.rs:34 holds `fn(f32) -> Camera`, which cannot cross an FFI.  The two
+ * scene.rs:34 holds `fn(f32) -> Camera`, which cannot cross an FFI.  The three
  * camera models the engine evaluates per photon on the device:
  *   STATIC : `fixed` for every t.
  *   ORBIT  : the closed form of make_camera (app.rs:327-357):
@@ -130,8 +130,14 @@ typedef struct rl_camera {
  *              orientation = rot(0,0,-1, phi + PI) * rot(1,0,0, -alpha)
  *              focal_distance = distance * focal_factor
  *            field_of_view / depth_of_field / chromatic_abberation from `fixed`.
+ *   KEYFRAMES : any other `fn(f32) -> Camera`, tabulated by the host: the
+ *            camera of time t (a draw in [0, 1], trace_unit.rs:141) is
+ *              keyframes[min(floor(t * n_keyframes), n_keyframes - 1)],
+ *            every field taken from the keyframe.  Exact for a camera function
+ *            that is piecewise constant on that grid, a discretisation of
+ *            anything else (the host picks n_keyframes; 11 floats per frame).
  */
-typedef enum rl_camera_kind { RL_CAMERA_STATIC = 1, RL_CAMERA_ORBIT = 2 } rl_camera_kind;
+typedef enum rl_camera_kind { RL_CAMERA_STATIC = 1, RL_CAMERA_ORBIT = 2, RL_CAMERA_KEYFRAMES = 3 } rl_camera_kind;
 
 typedef struct rl_camera_model {
     uint32_t kind;
@@ -140,6 +146,8 @@ typedef struct rl_camera_model {
     float alpha_base, alpha_rate;
     float distance_base, distance_rate;
     float focal_factor;
+    const rl_camera *keyframes;  /* KEYFRAMES only; copied by rl_scene_create */
+    uint32_t n_keyframes;
 } rl_camera_model;
 
 /* scene.rs:23-36 flattened: what a `describe()` pass over Scene emits */
@@ -335,6 +343,15 @@ int rl_tonemap_unit_tonemap(rl_tonemap_unit *unit, const float *xyz, uint8_t *rg
 int rl_tonemap_unit_tonemap_gather(rl_tonemap_unit *unit, rl_gather_unit *gather, uint8_t *rgb);
 /* The exposure (`max_intensity`, tonemap_unit.rs:55-69) of the last call. */
 int rl_tonemap_unit_last_exposure(rl_tonemap_unit *unit, float *out);
+/* How find_exposure (tonemap_unit.rs:55-69) sums the pixels.
+ * RL_EXPOSURE_F64_REDUCTION (default): parallel, in f64 -- the exposure agrees with the reference's
+ *   to ~1e-4 relative, and a near-constant image gets a finite exposure.
+ * RL_EXPOSURE_REFERENCE_FOLD: the reference's two sequential f32 folds in pixel order, by one
+ *   thread (a few ms per megapixel; the reference tone-maps once per 30 s): the exposure is
+ *   bit-equal to the reference's arithmetic, including the NaN it yields when the f32 sums make
+ *   the variance round negative (near-constant images go black, as they do in the reference). */
+typedef enum rl_exposure_mode { RL_EXPOSURE_F64_REDUCTION = 0, RL_EXPOSURE_REFERENCE_FOLD = 1 } rl_exposure_mode;
+int rl_tonemap_unit_set_exposure_mode(rl_tonemap_unit *unit, int mode);
 
 /* ------------------------------------------------------------- debugging */
 /*

@@ -549,6 +549,19 @@ struct Camera {                                                                 
 template <class M>
 inline Camera camera_at_time(const rl_camera_model &cm, float t) {
     Camera cam;
+    if (cm.kind == RL_CAMERA_KEYFRAMES) {
+        // a tabulated `fn(f32) -> Camera` (scene.rs:34): frame floor(t n), the last one for t == 1
+        uint32_t k = (uint32_t)std::floor(t * (float)cm.n_keyframes);
+        if (k > cm.n_keyframes - 1u) k = cm.n_keyframes - 1u;
+        const rl_camera &f = cm.keyframes[k];
+        cam.position = v3(f.position);
+        cam.field_of_view = f.field_of_view;
+        cam.focal_distance = f.focal_distance;
+        cam.depth_of_field = f.depth_of_field;
+        cam.chromatic_abberation = f.chromatic_abberation;
+        cam.orientation = {f.orientation.x, f.orientation.y, f.orientation.z, f.orientation.w};
+        return cam;
+    }
     cam.field_of_view = cm.fixed.field_of_view;
     cam.depth_of_field = cm.fixed.depth_of_field;
     cam.chromatic_abberation = cm.fixed.chromatic_abberation;
@@ -788,7 +801,10 @@ int make_view(const rl_scene_desc *desc, SceneView &sc) {
     sc.objects = desc->objects;
     sc.n_objects = desc->n_objects;
     sc.camera = desc->camera;
-    if (sc.camera.kind != RL_CAMERA_STATIC && sc.camera.kind != RL_CAMERA_ORBIT)
+    if (sc.camera.kind != RL_CAMERA_STATIC && sc.camera.kind != RL_CAMERA_ORBIT
+        && sc.camera.kind != RL_CAMERA_KEYFRAMES)
+        return RL_ERR_INVALID;
+    if (sc.camera.kind == RL_CAMERA_KEYFRAMES && (!sc.camera.keyframes || sc.camera.n_keyframes == 0))
         return RL_ERR_INVALID;
     for (uint32_t i = 0; i < sc.n_objects; i++) {
         const rl_object &o = sc.objects[i];

@@ -63,7 +63,8 @@ class CameraModel(C.Structure):
                 ("phi_base", C.c_float), ("phi_rate", C.c_float),
                 ("alpha_base", C.c_float), ("alpha_rate", C.c_float),
                 ("distance_base", C.c_float), ("distance_rate", C.c_float),
-                ("focal_factor", C.c_float)]
+                ("focal_factor", C.c_float),
+                ("keyframes", C.POINTER(Camera)), ("n_keyframes", C.c_uint32)]
 
 
 class SceneDesc(C.Structure):
@@ -81,7 +82,7 @@ HIT = np.dtype([("object", "<i4"), ("distance", "<f4"), ("position", "<f4", 3),
 SURFACE_PLANE, SURFACE_HALFSPACE, SURFACE_CIRCLE, SURFACE_SPHERE, SURFACE_PARABOLOID, SURFACE_COMPOUND = range(1, 7)
 (MATERIAL_BLACKBODY, MATERIAL_DIFFUSE_GREY, MATERIAL_DIFFUSE_COLOURED, MATERIAL_GLOSSY_MIRROR,
  MATERIAL_SF10_GLASS, MATERIAL_SOAP_BUBBLE) = range(1, 7)
-CAMERA_STATIC, CAMERA_ORBIT = 1, 2
+CAMERA_STATIC, CAMERA_ORBIT, CAMERA_KEYFRAMES = 1, 2, 3
 SCENE_C1, SCENE_C2, SCENE_C3, SCENE_C4 = 1, 2, 3, 4
 SCENE_C6 = 6        # compounds over spheres and half-spaces
 
@@ -153,6 +154,7 @@ SYMBOLS = {
     "rl_tonemap_unit_set_stream": (_I, [_P, _P]),
     "rl_tonemap_unit_tonemap": (_I, [_P, _P, _P]),
     "rl_tonemap_unit_tonemap_gather": (_I, [_P, _P, _P]),
+    "rl_tonemap_unit_set_exposure_mode": (_I, [_P, _I]),
     "rl_tonemap_unit_last_exposure": (_I, [_P, _PF]),
     "rl_debug_intersect": (_I, [_P, _P, _U64, _P]),
     "rl_debug_math": (_I, [_I, _P, _P, _U64, _P]),
@@ -328,6 +330,20 @@ class SceneBuilder:
         _check_host(host_lib().rl_scene_builder_camera(self._h, C.byref(cm)))
 
     def camera_model(self, cm):
+        _check_host(host_lib().rl_scene_builder_camera(self._h, C.byref(cm)))
+
+    def keyframe_camera(self, cameras):
+        """A tabulated `fn(f32) -> Camera` (scene.rs:34): camera(t) = cameras[min(floor(t n), n - 1)].
+        `cameras`: Camera structures, or (position, orientation, fov, focal, dof, ca) tuples."""
+        frames = (Camera * len(cameras))()
+        for k, c in enumerate(cameras):
+            frames[k] = c if isinstance(c, Camera) else Camera(vec3(*c[0]), c[2], c[3], c[4], c[5],
+                                                             Quat(*[float(v) for v in c[1]]))
+        cm = CameraModel()
+        cm.kind = CAMERA_KEYFRAMES
+        cm.fixed = frames[0]
+        cm.keyframes = frames
+        cm.n_keyframes = len(cameras)
         _check_host(host_lib().rl_scene_builder_camera(self._h, C.byref(cm)))
 
     def desc(self):
@@ -587,6 +603,10 @@ class TonemapUnit:
             assert t.size == self.width * self.height * 3
             _check(lib().rl_tonemap_unit_tonemap(self._h, _ptr(t), _ptr(self.rgb_buffer)))
         return self.rgb_buffer
+
+    def set_exposure_mode(self, reference_fold):
+        """find_exposure by the reference's sequential f32 folds (True) or the f64 reduction (False)."""
+        _check(lib().rl_tonemap_unit_set_exposure_mode(self._h, 1 if reference_fold else 0))
 
     @property
     def last_exposure(self):

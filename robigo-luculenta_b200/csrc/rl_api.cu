@@ -169,6 +169,7 @@ struct rl_scene {
     DevScene ds;
     void *d_blob = nullptr;
     void *d_materials = nullptr;
+    void *d_keyframes = nullptr;
     size_t smem = 0;
     // TraceUnit::render takes its photon ids from the scene's batch counter: one scene is one
     // App (app.rs:63), two renders in one process do not share ids
@@ -308,6 +309,7 @@ struct rl_tonemap_unit {
     double *d_moments = nullptr;
     float *d_exposure = nullptr;
     float last_exposure = 0.0f;
+    bool reference_fold = false;   // find_exposure by the reference's sequential f32 folds
 };
 
 // ------------------------------------------------------------ scene flatten
@@ -650,8 +652,12 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     if (!desc || !out) return fail(RL_ERR_INVALID, "rl_scene_create: null argument");
     if ((!desc->surfaces && desc->n_surfaces) || (!desc->objects && desc->n_objects))
         return fail(RL_ERR_INVALID, "rl_scene_create: null table");
-    if (desc->camera.kind != RL_CAMERA_STATIC && desc->camera.kind != RL_CAMERA_ORBIT)
+    if (desc->camera.kind != RL_CAMERA_STATIC && desc->camera.kind != RL_CAMERA_ORBIT
+        && desc->camera.kind != RL_CAMERA_KEYFRAMES)
         return fail(RL_ERR_INVALID, "rl_scene_create: unknown camera kind");
+    if (desc->camera.kind == RL_CAMERA_KEYFRAMES && (!desc->camera.keyframes || desc->camera.n_keyframes == 0
+                                                      || desc->camera.n_keyframes > (1u << 20)))
+        return fail(RL_ERR_INVALID, "rl_scene_create: a keyframe camera needs 1 .. 2^20 keyframes");
 
     Flat fl;
     std::vector<float4> materials;
@@ -809,7 +815,12 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
         ds.off_body_always = append(blob, body_always);
         ds.body_rmax = (float)(body_rmax * 1.0001);
     }
-    ds.off_sphere_k = append(blob, fl.sphere_k);
+    // the pre-test records of the spheres go to shared memory with the rest -- unless there are so
+    // many of them (> 6144: 96 KB) that the CTAs would shrink or the scene would not fit at all:
+    // then they stay in global memory (read through L1 by the cooperative member test) and the
+    // scene is bounded by the 65 535 spheres of the 16-bit candidate queues only
+    const bool sphere_k_global = fl.sphere_k.size() > 6144 && !env_int("RL_SPHERE_K_SHARED", 0);
+    if (!sphere_k_global) ds.off_sphere_k = append(blob, fl.sphere_k);
     ds.off_clusters = append(blob, clusters);           ds.n_clusters = (uint32_t)clusters.size();
     ds.off_cluster_range = append(blob, cluster_range);
     ds.sphere_cmax2 = (float)(fl.cmax2 * 1.0001);
@@ -821,6 +832,8 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     ds.off_compound_obj = append(blob, fl.compound_obj);
     if (blob.empty()) blob.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
     ds.smem_vec4 = (uint32_t)blob.size();               // everything above goes to shared memory
+    ds.sphere_k_global = sphere_k_global ? 1u : 0u;
+    if (sphere_k_global) ds.off_sphere_k = append(blob, fl.sphere_k);
     ds.off_spheres = append(blob, fl.spheres);          // exact records: global memory only
     ds.off_sphere_obj = append(blob, fl.sphere_obj);
     if (blob.empty()) blob.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
@@ -853,8 +866,28 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     c.distance_base = cm.distance_base; c.distance_rate = cm.distance_rate;
     c.focal_factor = cm.focal_factor;
 
+    // the tabulated camera function: three float4 per frame, 1 / tan(fov / 2) evaluated per frame
+    std::vector<float4> keyframes;
+    if (cm.kind == RL_CAMERA_KEYFRAMES) {
+        for (uint32_t k = 0; k < cm.n_keyframes; k++) {
+            const rl_camera &f = cm.keyframes[k];
+            float fs, fc;
+            spec_sincos(f.field_of_view * 0.5f, fs, fc);
+            keyframes.push_back(make_float4(f.position.x, f.position.y, f.position.z, f.focal_distance));
+            keyframes.push_back(make_float4(f.orientation.x, f.orientation.y, f.orientation.z, f.orientation.w));
+            keyframes.push_back(make_float4(f.depth_of_field, f.chromatic_abberation, 1.0f / (fs / fc), 0.f));
+        }
+        c.n_keyframes = cm.n_keyframes;
+    }
+
     if (materials.empty()) materials.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
     cudaError_t e = cudaMalloc(&sc->d_blob, blob.size() * sizeof(float4));
+    if (e == cudaSuccess && !keyframes.empty()) {
+        e = cudaMalloc(&sc->d_keyframes, keyframes.size() * sizeof(float4));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(sc->d_keyframes, keyframes.data(), keyframes.size() * sizeof(float4), cudaMemcpyHostToDevice);
+        g_h2d_bytes += keyframes.size() * sizeof(float4);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&sc->d_materials, materials.size() * sizeof(float4));
     if (e == cudaSuccess)
         e = cudaMemcpy(sc->d_blob, blob.data(), blob.size() * sizeof(float4), cudaMemcpyHostToDevice);
@@ -863,10 +896,11 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
         e = cudaMemcpy(sc->d_materials, materials.data(), materials.size() * sizeof(float4),
                        cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
-        cudaFree(sc->d_blob); cudaFree(sc->d_materials);
+        cudaFree(sc->d_blob); cudaFree(sc->d_materials); cudaFree(sc->d_keyframes);
         delete sc;
         return fail(RL_ERR_CUDA, std::string("rl_scene_create: ") + cudaGetErrorString(e));
     }
+    ds.camera.keyframes = (const float4 *)sc->d_keyframes;
     ds.blob = (const float4 *)sc->d_blob;
     ds.materials = (const float4 *)sc->d_materials;
     *out = sc;
@@ -879,6 +913,7 @@ int rl_scene_destroy(rl_scene *scene) {
     dispatcher_stop(scene);
     cudaFree(scene->d_blob);
     cudaFree(scene->d_materials);
+    cudaFree(scene->d_keyframes);
     delete scene;
     return RL_OK;
 }
@@ -1506,6 +1541,13 @@ int rl_tonemap_unit_create(uint32_t width, uint32_t height, rl_tonemap_unit **ou
     return RL_OK;
 }
 
+int rl_tonemap_unit_set_exposure_mode(rl_tonemap_unit *u, int mode) {
+    if (!u || (mode != RL_EXPOSURE_F64_REDUCTION && mode != RL_EXPOSURE_REFERENCE_FOLD))
+        return fail(RL_ERR_INVALID, "rl_tonemap_unit_set_exposure_mode: bad argument");
+    u->reference_fold = mode == RL_EXPOSURE_REFERENCE_FOLD;
+    return RL_OK;
+}
+
 int rl_tonemap_unit_destroy(rl_tonemap_unit *u) {
     if (!u) return RL_OK;
     DeviceGuard guard(u->dev.index);
@@ -1524,7 +1566,7 @@ int rl_tonemap_unit_set_stream(rl_tonemap_unit *u, void *s) {
 
 static int tonemap_device(rl_tonemap_unit *u, const float *d_xyz, uint8_t *rgb) {
     RL_CUDA(launch_tonemap(d_xyz, u->width, u->height, u->d_moments, u->d_exposure, u->d_rgb,
-                           u->dev.sm_count, u->ss.stream));
+                           u->dev.sm_count, u->reference_fold, u->ss.stream));
     RL_CUDA(copy_async(&u->last_exposure, u->d_exposure, sizeof(float), cudaMemcpyDeviceToHost,
                             u->ss.stream));
     if (rgb)

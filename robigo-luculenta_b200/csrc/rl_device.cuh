@@ -45,6 +45,7 @@ struct PrimTables {
     // they stay in global memory (L1/L2-resident), which halves the shared memory of big scenes
     const float4 *spheres;
     const uint32_t *sphere_obj;
+    const float4 *sphere_k_global;   // the pre-test records when they are too many for shared memory, else null
     uint32_t sphere_k, clusters, cluster_range, planes, paraboloids, leaves, compounds, ops;
     uint32_t body_bounds, body_always;
     uint32_t plane_obj, paraboloid_obj, compound_obj;
@@ -82,6 +83,7 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         t.spheres = sc.blob + sc.off_spheres;
         t.sphere_obj = reinterpret_cast<const uint32_t *>(sc.blob + sc.off_sphere_obj);
         t.sphere_k = base + sc.off_sphere_k;
+        t.sphere_k_global = sc.sphere_k_global ? sc.blob + sc.off_sphere_k : nullptr;
         t.clusters = base + sc.off_clusters;
         t.cluster_range = base + sc.off_cluster_range;
         t.planes = base + sc.off_planes;
@@ -262,10 +264,25 @@ __device__ __forceinline__ Ray camera_ray(const DevCamera &cm, float x, float y,
     V3 position;
     Quat orientation;
     float focal_distance;
+    float depth_of_field = cm.depth_of_field, chromatic_abberation = cm.chromatic_abberation;
+    // camera.rs:60: 1 / tan(fov / 2) is a constant of the camera, evaluated once on the host with the
+    // same specified functions (rl_api.cu, dev_camera)
+    float screen_distance = cm.screen_distance;
     if (cm.kind == RL_CAMERA_STATIC) {
         position = mk(cm.px, cm.py, cm.pz);
         orientation = mkq(cm.qx, cm.qy, cm.qz, cm.qw);
         focal_distance = cm.focal_distance;
+    } else if (cm.kind == RL_CAMERA_KEYFRAMES) {
+        // the tabulated camera function: frame floor(t n), the last one for t == 1
+        const uint32_t n = cm.n_keyframes;
+        uint32_t k = (uint32_t)floorf(t * (float)n);
+        if (k > n - 1u) k = n - 1u;
+        const float4 f0 = __ldg(cm.keyframes + 3u * k), f1 = __ldg(cm.keyframes + 3u * k + 1u),
+                     f2 = __ldg(cm.keyframes + 3u * k + 2u);
+        position = mk(f0.x, f0.y, f0.z);
+        focal_distance = f0.w;
+        orientation = mkq(f1.x, f1.y, f1.z, f1.w);
+        depth_of_field = f2.x; chromatic_abberation = f2.y; screen_distance = f2.z;
     } else {
         const float phi = RL_PI * (cm.phi_base + cm.phi_rate * t);
         const float alpha = RL_PI * (cm.alpha_base + cm.alpha_rate * t);
@@ -277,12 +294,9 @@ __device__ __forceinline__ Ray camera_ray(const DevCamera &cm, float x, float y,
         focal_distance = distance * cm.focal_factor;
     }
     const float dof_angle = rng.longitude(key);
-    const float dof_radius = rng.unit(key) / cm.depth_of_field;
+    const float dof_radius = rng.unit(key) / depth_of_field;
     const float d = (wavelength - 580.0f) / 200.0f;
-    const float chromatic_zoom = 1.0f + d * cm.chromatic_abberation;
-    // camera.rs:60: 1 / tan(fov / 2) is a constant of the scene, evaluated once on the host with the
-    // same specified functions (rl_api.cu, dev_camera)
-    const float screen_distance = cm.screen_distance;
+    const float chromatic_zoom = 1.0f + d * chromatic_abberation;
     const float xs = x * chromatic_zoom;
     const float ys = y * chromatic_zoom;
     const V3 direction = normalise_dev(mk(xs, screen_distance, -ys));
@@ -718,6 +732,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
     auto sphere_phase = [&]() {
         const float4 *spheres = tb.spheres;
         const float4 *sphere_k = sm_vec(tb.sphere_k);
+        const float4 *sphere_k_global = tb.sphere_k_global;         // block-uniform
         const float4 *clusters = sm_vec(tb.clusters);
         const uint32_t *cluster_range = sm_u32(tb.cluster_range);
         const uint32_t *sphere_obj = tb.sphere_obj;
@@ -745,7 +760,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
                         const float2 rt = *reinterpret_cast<const float2 *>(&ray_tab[3 * owner + 2]);
 #pragma unroll 1
                         for (uint32_t m = (r & 0xffffu) + (lane & 7u); m < end; m += 8) {
-                            const float4 s = sphere_k[m];               // {cx, cy, cz, |c|^2 - r^2}
+                            const float4 s = sphere_k_global ? __ldg(sphere_k_global + m) : sphere_k[m];   // {cx, cy, cz, |c|^2 - r^2}
                             const float b = fmaf(rd.x, s.x, fmaf(rd.y, s.y, fmaf(rd.z, s.z, rd.w)));
                             const float c = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w))) + ro.w;
                             const float disc = fmaf(b, b, -c);

@@ -812,6 +812,39 @@ tonemap_moments_kernel(const float *__restrict__ xyz, uint64_t n_pixels, double 
     }
 }
 
+// tonemap_unit.rs:55-69 to the letter: two sequential f32 folds over the pixels in row-major order
+// (Rust's Iterator::sum), by ONE thread -- the block only stages the Y values in shared memory.
+// 1 M pixels take a few milliseconds; the reference tone-maps once per 30 s
+// (task_scheduler.rs:43-46).  Reproduces the reference's rounding and with it the accident that
+// near-constant images get a NaN exposure (the variance rounds negative).
+#define RL_FOLD_CHUNK 4096
+__global__ void __launch_bounds__(256)
+tonemap_fold_kernel(const float *__restrict__ xyz, uint64_t n_pixels, uint32_t width, uint32_t height, float *exposure) {
+    __shared__ float ys[RL_FOLD_CHUNK];
+    float sum = 0.0f, sqr = 0.0f;
+    for (uint64_t first = 0; first < n_pixels; first += RL_FOLD_CHUNK) {
+        const uint32_t count = (uint32_t)(n_pixels - first < RL_FOLD_CHUNK ? n_pixels - first : RL_FOLD_CHUNK);
+        for (uint32_t k = threadIdx.x; k < count; k += blockDim.x) ys[k] = xyz[3 * (first + k) + 1];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll 8
+            for (uint32_t k = 0; k < count; k++) {
+                const float y = ys[k];
+                sum += y;                                // :61
+                sqr += y * y;                            // :64
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float n = (float)(width * height);         // :56
+        const float mean = sum / n;
+        const float sqr_mean = sqr / n;
+        const float variance = sqr_mean - mean * mean;   // :65
+        *exposure = mean + sqrtf(variance);              // :68
+    }
+}
+
 __global__ void tonemap_exposure_kernel(const double *moments, uint32_t width, uint32_t height,
                                         float *exposure) {
     const float n = (float)(width * height);               // tonemap_unit.rs:56
@@ -858,18 +891,24 @@ tonemap_map_kernel(const float *__restrict__ xyz, uint64_t n_pixels, const float
 }
 
 cudaError_t launch_tonemap(const float *xyz, uint32_t width, uint32_t height, double *moments,
-                           float *exposure_out, uint8_t *rgb, int sm_count, cudaStream_t st) {
+                           float *exposure_out, uint8_t *rgb, int sm_count, bool reference_fold, cudaStream_t st) {
     const uint64_t n_pixels = (uint64_t)width * height;
     if (n_pixels == 0) return cudaSuccess;
-    cudaError_t err = cudaMemsetAsync(moments, 0, 2 * sizeof(double), st);
-    if (err != cudaSuccess) return err;
     uint64_t want = (n_pixels + 255) / 256;
     uint64_t full = (uint64_t)sm_count * 8;
     unsigned grid = (unsigned)(want < full ? want : full);
-    tonemap_moments_kernel<<<grid, 256, 0, st>>>(xyz, n_pixels, moments);
-    tonemap_exposure_kernel<<<1, 1, 0, st>>>(moments, width, height, exposure_out);
+    if (reference_fold) {
+        tonemap_fold_kernel<<<1, 256, 0, st>>>(xyz, n_pixels, width, height, exposure_out);
+        g_launches += 1;
+    } else {
+        cudaError_t err = cudaMemsetAsync(moments, 0, 2 * sizeof(double), st);
+        if (err != cudaSuccess) return err;
+        tonemap_moments_kernel<<<grid, 256, 0, st>>>(xyz, n_pixels, moments);
+        tonemap_exposure_kernel<<<1, 1, 0, st>>>(moments, width, height, exposure_out);
+        g_launches += 2;
+    }
     tonemap_map_kernel<<<grid, 256, 0, st>>>(xyz, n_pixels, exposure_out, rgb);
-    g_launches += 3;
+    g_launches += 1;
     return cudaGetLastError();
 }
 

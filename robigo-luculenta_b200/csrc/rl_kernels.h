@@ -44,8 +44,10 @@ cudaError_t launch_gather(float *acc, float *comp, const float4 *const *srcs, ui
                           const float *packed_src, float4 *clear_or_null, uint64_t n_pixels,
                           int sm_count, cudaStream_t st);
 // K4: TonemapUnit::tonemap.  moments = 2 doubles of scratch; exposure_out = 1 float.
+// reference_fold: find_exposure as the reference's two sequential f32 folds (one thread) instead
+// of the parallel f64 reduction.
 cudaError_t launch_tonemap(const float *xyz, uint32_t width, uint32_t height, double *moments,
-                           float *exposure_out, uint8_t *rgb, int sm_count, cudaStream_t st);
+                           float *exposure_out, uint8_t *rgb, int sm_count, bool reference_fold, cudaStream_t st);
 
 // probes
 cudaError_t launch_debug_intersect(const DevScene &sc, const rl_ray *rays, uint64_t n, rl_hit *out,

@@ -20,6 +20,10 @@ struct DevCamera {
     float screen_distance;    // 1 / tan(field_of_view / 2) (camera.rs:60), specified arithmetic
     float qx, qy, qz, qw;
     float phi_base, phi_rate, alpha_base, alpha_rate, distance_base, distance_rate, focal_factor;
+    // KEYFRAMES: three float4 per frame {position, focal_distance} {orientation} {depth_of_field,
+    // chromatic_abberation, screen_distance, 0}, in global memory
+    const float4 *keyframes;
+    uint32_t n_keyframes;
 };
 
 struct DevScene {
@@ -44,6 +48,7 @@ struct DevScene {
     float leaf_off_max;       // largest |offset| over the half-spaces of compound surfaces (slab-test inflation)
     float body_rmax;          // largest bounding radius of a compound
     uint32_t sphere_leaves;   // 1: some compound has a sphere leaf (geometry.rs:263-267)
+    uint32_t sphere_k_global; // 1: the spheres' pre-test records (off_sphere_k) are not in the shared-memory part
     DevCamera camera;
 };
 

@@ -17,6 +17,7 @@ using rl::mk;
 struct rl_scene_builder {
     std::vector<rl_surface> surfaces;
     std::vector<rl_object> objects;
+    std::vector<rl_camera> keyframes;
     rl_camera_model camera;
 };
 
@@ -186,6 +187,7 @@ rl_camera_model orbit_camera() {  // app.rs:327-357
     cm.alpha_base = 0.3f; cm.alpha_rate = -0.01f;
     cm.distance_base = 50.0f; cm.distance_rate = -0.5f;
     cm.focal_factor = 0.9f;
+    cm.keyframes = nullptr; cm.n_keyframes = 0;
     return cm;
 }
 
@@ -200,6 +202,7 @@ rl_camera_model static_camera(V3 position, rl::Quat q, float fov, float focal, f
     cm.fixed.orientation = rl_quat{q.x, q.y, q.z, q.w};
     cm.phi_base = cm.phi_rate = cm.alpha_base = cm.alpha_rate = 0.f;
     cm.distance_base = cm.distance_rate = cm.focal_factor = 0.f;
+    cm.keyframes = nullptr; cm.n_keyframes = 0;
     return cm;
 }
 
@@ -451,6 +454,13 @@ int rl_scene_builder_object(rl_scene_builder *b, uint32_t surface, rl_material m
 int rl_scene_builder_camera(rl_scene_builder *b, const rl_camera_model *camera) {
     if (!b || !camera) return RL_ERR_INVALID;
     b->camera = *camera;
+    b->keyframes.clear();
+    if (camera->kind == RL_CAMERA_KEYFRAMES) {                 // the builder keeps its own copy of the table
+        if (!camera->keyframes || camera->n_keyframes == 0) return RL_ERR_INVALID;
+        b->keyframes.assign(camera->keyframes, camera->keyframes + camera->n_keyframes);
+    }
+    b->camera.keyframes = b->keyframes.empty() ? nullptr : b->keyframes.data();
+    b->camera.n_keyframes = (uint32_t)b->keyframes.size();
     return RL_OK;
 }
 int rl_scene_builder_desc(rl_scene_builder *b, rl_scene_desc *out) {

@@ -39,7 +39,7 @@ def test_python_mirror_binds_every_declared_symbol(pkg):
     assert sorted(pkg.HOST_SYMBOLS) == declared_symbols("rl_host.h")
     pkg.lib()
     pkg.host_lib()
-    assert pkg.lib().rl_abi_version() == 2
+    assert pkg.lib().rl_abi_version() == 3
 
 
 def test_pod_layouts_match_reference_records(pkg):

@@ -500,6 +500,35 @@ def test_tonemap_matches_oracle(gpu, orc):
     assert rgb_dev.max() > 100                      # not a black frame
 
 
+def test_tonemap_reference_fold_is_bit_equal(gpu, orc):
+    # RL_EXPOSURE_REFERENCE_FOLD: find_exposure as the reference's two sequential f32 folds
+    # (tonemap_unit.rs:55-69): the exposure, and with it the whole image, bit-equal to the oracle
+    w, h, n = 320, 200, 400000
+    b = gpu.SceneBuilder(2)
+    sc = gpu.Scene(b)
+    tu = gpu.TraceUnit(0, w, h, seed=SEED, batch=n)
+    p = gpu.PlotUnit(0, w, h)
+    tu.render_fused(sc, p, 0, n)
+    g = gpu.GatherUnit(w, h)
+    g.accumulate(p, clear=True)
+    xyz = g.tristimulus_buffer
+    t = gpu.TonemapUnit(w, h)
+    t.set_exposure_mode(True)
+    rgb = t.tonemap(g).copy()
+    assert np.float32(t.last_exposure).view(np.uint32) == np.float32(orc.find_exposure(xyz)).view(np.uint32)
+    assert np.array_equal(rgb, orc.tonemap(xyz, orc.MATH_SPEC))        # exposure found by the oracle's own fold
+    # ... including the reference's accident: a near-constant image has a NaN exposure and goes black
+    flat = np.full((1024, 1024, 3), 0.1, dtype=np.float32)
+    assert np.isnan(orc.find_exposure(flat))
+    t2 = gpu.TonemapUnit(1024, 1024)
+    t2.set_exposure_mode(True)
+    black = t2.tonemap(flat)
+    assert np.isnan(t2.last_exposure) and not black.any()
+    assert np.array_equal(black, orc.tonemap(flat, orc.MATH_SPEC))
+    t2.set_exposure_mode(False)                                         # the default reduces in f64: finite
+    assert np.isfinite(t2.tonemap(flat).astype(np.float32)).all() and np.isfinite(t2.last_exposure)
+
+
 def test_tonemap_constant_image(gpu, orc):
     xyz = np.full((16, 16, 3), 0.5, dtype=np.float32)
     t = gpu.TonemapUnit(16, 16)
@@ -692,3 +721,33 @@ def test_image_matches_reference_arithmetic(gpu, orc):
     differ = np.count_nonzero(~np.isclose(got["probability"], want["probability"], rtol=1e-4, atol=1e-7)) / m
     print(f"photons whose probability differs from the LIBM oracle's by more than 1e-4: {differ:.4f}")
     assert differ < 0.03
+
+
+def test_keyframe_camera_bit_equal(gpu, orc):
+    # the third camera model (rl_b200.h: RL_CAMERA_KEYFRAMES): rays and whole paths against the oracle
+    from test_oracle_kat import keyframe_scene
+    b = keyframe_scene(gpu)
+    sc = gpu.Scene(b)
+    n = 50000
+    got_r, got_xy = sc.camera_rays(SEED, 320, 200, 123, n)
+    want_r, want_xy = orc.camera_rays(b.desc(), SEED, 320, 200, 123, n)
+    assert_bit_equal(got_r["origin"], want_r["origin"], "keyframe camera origin")
+    assert_bit_equal(got_r["direction"], want_r["direction"], "keyframe camera direction")
+    tu = gpu.TraceUnit(0, 320, 200, seed=SEED, batch=n)
+    assert_records_equal(tu.render_range(sc, 123, n), orc.trace(b.desc(), SEED, 320, 200, 123, n), "keyframe scene")
+
+
+def test_scene_beyond_shared_memory(gpu, orc):
+    # 20 000 spheres: their pre-test records (320 KB) do not fit an SM's shared memory and stay in
+    # global memory; same records, same ray count, culls still result-preserving
+    b = gpu.SceneBuilder(4, 20000)
+    sc = gpu.Scene(b)
+    n = 3000
+    tu = gpu.TraceUnit(0, 256, 256, seed=SEED, batch=n)
+    got = tu.render_range(sc, 0, n)
+    ct = orc.Counters()
+    want = orc.trace(b.desc(), SEED, 256, 256, 0, n, orc.MATH_SPEC, False, ct)
+    assert_records_equal(got, want, "20000 spheres")
+    assert tu.ray_count() == ct.rays
+    rays, bad = sc.cull_check(SEED, 256, 256, 0, 1 << 15)
+    assert bad == 0 and rays >= 1 << 15

@@ -357,3 +357,32 @@ def test_compound_of_spheres(pkg, orc):
     assert hit["object"][5] == 1 and abs(hit["distance"][5] - 10.5) < 1e-5 and np.allclose(hit["normal"][5], (0, 0, -1))
     assert np.allclose(hit["tangent"][5], 0.0)          # only spheres set a tangent (geometry.rs:250-251)
     assert hit["object"][6] == -1                       # below the cut: the sphere's faces there are outside the half-space
+
+
+def keyframe_scene(pkg):
+    """C1's sphere and emissive plane under a tabulated camera function: three frames that differ in
+    position, orientation, field of view, depth of field and chromatic aberration."""
+    b = pkg.SceneBuilder()
+    b.object(b.sphere((0, 0, 0), 1.0), pkg.SceneBuilder.material(pkg.MATERIAL_DIFFUSE_GREY, 0.8))
+    b.object(b.plane((0, 0, -1), (0, 0, 4)), pkg.SceneBuilder.blackbody(6504.0, 1.0))
+    s = float(np.sin(0.2)), float(np.cos(0.2))
+    b.keyframe_camera([((0, -5, 0), (0, 0, 0, 1), 0.35 * np.pi, 5.0, 1.0e9, 0.0),
+                       ((1, -6, 0.5), (0, 0, s[0], s[1]), 0.30 * np.pi, 6.0, 3.0, 0.01),
+                       ((-2, -4, 1), (s[0], 0, 0, s[1]), 0.40 * np.pi, 4.5, 2.0, 0.02)])
+    return b
+
+
+def test_keyframe_camera_picks_floor_of_t_times_n(pkg, orc):
+    # scene.rs:34 `fn(f32) -> Camera`, tabulated: frame min(floor(t n), n - 1); t is the fourth draw
+    b = keyframe_scene(pkg)
+    n = 3000
+    rays, xy = orc.camera_rays(b.desc(), 5, 64, 64, 0, n)
+    t = xy["probability"]                               # the probe returns t in this field
+    frame = np.minimum(np.floor(t * np.float32(3)).astype(int), 2)
+    assert set(frame) == {0, 1, 2}
+    pos = np.array([(0, -5, 0), (1, -6, 0.5), (-2, -4, 1)], dtype=np.float32)
+    pinhole = frame == 0                                # depth_of_field 1e9: the lens is a point
+    assert np.allclose(rays["origin"][pinhole], pos[0], atol=1e-6)
+    for k in (1, 2):                                    # lens radius <= 1 / depth_of_field
+        d = np.linalg.norm(rays["origin"][frame == k] - pos[k], axis=1)
+        assert d.max() <= 1.0 / (3.0, 2.0)[k - 1] + 1e-5 and d.max() > 0.05
