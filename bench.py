@@ -545,6 +545,8 @@ def main():
                 "steps": args.steps, "batches_per_step_per_gpu": max(1, n // batch), "worker_threads_per_gpu": workers,
                 "host_cpus_rank0": f"{len(cpus)} cores" + (f" of NUMA node {numa_node}" if numa_node >= 0 else ""),
                 "seconds": float(t[0]),
+                "d2h_gb_per_s": (int(r[2]) + frame_bytes) / float(t[0]) / 1e9,
+                "h2d_gb_per_s": (int(r[1]) + frame_bytes * world) / float(t[0]) / 1e9,
                 "value_with_unit_creation": int(r[0]) / float(t[1]) / 1e6,
                 "timing": "steady state: wall time from the first scheduler task to buffer.raw on disk, max over "
                           "ranks; TaskScheduler::new (unit creation, page-locking of the units' host buffers, once "
@@ -568,7 +570,9 @@ def main():
                            "(host/rl_replay.cpp; app.rs:95-164, task_scheduler.rs:91-182): 524 288-photon "
                            "TraceUnit::render calls, each a launch that shares the SMs with the other units' launches, every batch of records copied "
                            "into the unit's host Vec, PlotUnit::plot / GatherUnit::accumulate consuming the units' "
-                           "device copies, buffer.raw saved after every gather, tonemap at the end"
+                           "device copies, buffer.raw saved after every gather, tonemap at the end; 16 B per photon "
+                           "cross PCIe to the host, which is what bounds this mode on several GPUs of one host "
+                           "(profiles/r2_pcie_probe_8gpu.jsonl: 92 GB/s device-to-host in all with 8 GPUs copying)"
                            + ("; ranks' frames summed onto rank 0" if world > 1 else ""))
 
     # ---- the other BASELINE.json configs, as measured lines -------------------------------------
