@@ -117,7 +117,7 @@ __device__ __forceinline__ void generate_camera_entry(const DevScene &sc, const 
 //     scene is 22 % slower (4.5 instruction-fetch stall cycles per issued instruction instead of
 //     0.3).  Scenes without compound bodies execute a small enough part of the loop and are
 //     10-20 % faster free-running: launch_trace picks the form by that.
-template <bool BLOCK_RING>
+template <bool BLOCK_RING, bool GLOBAL_K>
 __global__ void __launch_bounds__(RL_TRACE_THREADS, RL_TRACE_MIN_BLOCKS)
 trace_kernel(const DevScene sc, const TraceArgs a) {
     setup_tables(sc);
@@ -227,7 +227,7 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
             const RngKey key = {cta->seed[seg], cta->first_photon[seg] + index};
             rng.load(key, rays);
         }
-        const Hit hit = intersect_scene(alive ? ray : idle_ray(), alive);
+        const Hit hit = intersect_scene<GLOBAL_K>(alive ? ray : idle_ray(), alive);
         if (alive) {
             rays++;                                                 // Scene::intersect calls (scene.rs:39)
             // trace_unit.rs:91-131
@@ -395,17 +395,20 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     // units (each on its own stream) take turns setting them and launching
     static std::mutex launch_lock;
     std::lock_guard<std::mutex> guard(launch_lock);
-    static KernelCache cache[16];
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
     KernelCache scratch_entry;
-    // which form of the kernel: see trace_kernel.  RL_TRACE_LOCKSTEP overrides (experiments).
+    // which instance of the kernel: see trace_kernel and intersect_scene.  RL_TRACE_LOCKSTEP
+    // overrides the ring form (experiments).
     const bool block_ring = env_int("RL_TRACE_LOCKSTEP", sc.n_compounds != 0u ? 1 : 0) != 0;
-    static KernelCache cache_free[16];
-    KernelCache &cached = block_ring ? (dev >= 0 && dev < 16 ? cache[dev] : scratch_entry)
-                                     : (dev >= 0 && dev < 16 ? cache_free[dev] : scratch_entry);
-    err = block_ring ? prepare_kernel(trace_kernel<true>, cached, dev) : prepare_kernel(trace_kernel<false>, cached, dev);
+    const bool global_k = sc.sphere_k_global != 0u;
+    typedef void (*TraceKernel)(const DevScene, const TraceArgs);
+    const TraceKernel kernel = block_ring ? (global_k ? trace_kernel<true, true> : trace_kernel<true, false>)
+                                          : (global_k ? trace_kernel<false, true> : trace_kernel<false, false>);
+    static KernelCache caches[4][16];
+    KernelCache &cached = dev >= 0 && dev < 16 ? caches[(block_ring ? 2 : 0) + (global_k ? 1 : 0)][dev] : scratch_entry;
+    err = prepare_kernel(kernel, cached, dev);
     if (err != cudaSuccess) return err;
     const int max_smem = cached.max_smem;
     int threads = env_int("RL_TRACE_THREADS_MAX", RL_TRACE_THREADS);
@@ -452,14 +455,12 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     const size_t smem = trace_kernel_smem_bytes(sc, threads, ring_cap);
     if (cached.threads != threads || cached.smem != smem) {
         int occ = 0;
-        err = block_ring ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_kernel<true>, threads, smem)
-                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_kernel<false>, threads, smem);
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
         if (err != cudaSuccess) return err;
         cached.threads = threads; cached.smem = smem; cached.per_sm = occ < 1 ? 1 : occ;
     }
     const int per_sm = cached.per_sm;
-    if (block_ring) set_carveout(trace_kernel<true>, cached, per_sm, smem);
-    else set_carveout(trace_kernel<false>, cached, per_sm, smem);
+    set_carveout(kernel, cached, per_sm, smem);
     uint64_t full = (uint64_t)sm_count * per_sm;
     if (small) {
         // The launch's share of the GPU's block slots, by the concurrency seen: with k other
@@ -502,8 +503,7 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
         }
         const uint64_t want = (n_launch + threads - 1) / threads;
         const unsigned grid = (unsigned)(want < full ? want : full);
-        if (block_ring) trace_kernel<true><<<grid, threads, smem, st>>>(sc, a);
-        else trace_kernel<false><<<grid, threads, smem, st>>>(sc, a);
+        kernel<<<grid, threads, smem, st>>>(sc, a);
         g_launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -926,7 +926,7 @@ __global__ void debug_intersect_kernel(const DevScene sc, const rl_ray *rays, ui
             r.direction = mk(rays[i].direction.x, rays[i].direction.y, rays[i].direction.z);
             r.wavelength = rays[i].wavelength;
         }
-        const Hit h = intersect_scene(r);
+        const Hit h = intersect_scene_any(r);
         // intersect_scene leaves its block-wide scratch (task counter, result slots) to be reset
         // behind a barrier that the next call must not overtake
         __syncthreads();
@@ -994,7 +994,7 @@ debug_cull_check_kernel(const DevScene sc, uint64_t seed, float aspect, uint64_t
         }
         if (!__syncthreads_or(alive)) break;
         const Ray r = alive ? ray : idle_ray();
-        const Hit culled = intersect_scene(r);
+        const Hit culled = intersect_scene_any(r);
         if (!alive) continue;
         const Hit hit = intersect_scene_brute(r);
         BounceRng brng;
