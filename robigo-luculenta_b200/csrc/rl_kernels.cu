@@ -31,7 +31,7 @@ void kernel_launches_reset() { g_launches.store(0); }
 // launches with fewer than RL_TRACE_SMALL_PATHS photons per thread of a full grid use CTAs of
 // RL_TRACE_SMALL_CTA threads (0 paths: never); both can be overridden from the environment
 #ifndef RL_TRACE_SMALL_CTA
-#define RL_TRACE_SMALL_CTA 256
+#define RL_TRACE_SMALL_CTA 384
 #endif
 #ifndef RL_TRACE_SMALL_PATHS
 #define RL_TRACE_SMALL_PATHS 64
@@ -432,16 +432,14 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
         threads -= 128;
         shrink = pick_ring(threads);
     }
-    // Small batches (the reference's 524 288 photons are 4.6 per thread of a full grid) spend most
-    // of their time in the tail, where a block waits for its last paths.  They are launched as
-    // small CTAs, several per SM, so that the blocks of a launch retire one by one and the blocks
-    // of the next unit's launch (another stream) move in beside the ones still in their tail.
-    // Each such launch also takes only its share of the SM's block slots: with k other units'
-    // small launches in flight it asks for ceil(per_sm / (k + 1)) blocks per SM, so k + 1 launches
-    // run side by side with three times the paths per thread (fewer table copies and tails per
-    // photon) instead of one after the other with every block spending most of its life in its
-    // tail.  Measured on the reference's batch, built-in scene, 8 units (tools/strict_rates.py):
-    // 768 x 1: 2200 Mrays/s, 256 x 3 full grid: 2310, 256 x 1-of-3: 2600 (large batches: 2750).
+    // Small batches (the reference's 524 288 photons are 4.6 per thread of a full grid) would spend
+    // most of their time in the tail, where a block waits for its last paths.  They are launched
+    // as half-size CTAs, two per SM, and as few of them as the concurrency allows (below), so that
+    // a block lives for tens of photons per thread and the block beside it on the SM -- another
+    // unit's batch, from another stream -- covers its tail.  Scheduler replay, 6144 reference
+    // batches, built-in scene (tools/replay_knobs.sh, profiles/r2_replay_knobs.txt), Mrays/s:
+    // CTAs of 128: 2554, 256: 2954, 384: 3152, 512: 2703, 768 (no small launches): 2734; one
+    // 2^28-photon launch: 3450.
     const int small_cta = env_int("RL_TRACE_SMALL_CTA", RL_TRACE_SMALL_CTA);
     const uint64_t small_paths = (uint64_t)env_int("RL_TRACE_SMALL_PATHS", RL_TRACE_SMALL_PATHS);
     const bool small = small_cta >= 128 && small_cta < threads && small_cta % 32 == 0
