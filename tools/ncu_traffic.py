@@ -39,7 +39,8 @@ def main():
         unit = r[mu].lower()
         scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0,
                  "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}.get(unit, 1)
-        launches.setdefault((int(r[idc]), r[kn].split("(")[0]), {})[r[mn]] = v * scale
+        name = r[kn].split("(")[0].split("<")[0].replace("void ", "").strip()      # "void trace_kernel<1, 0>(...)"
+        launches.setdefault((int(r[idc]), name), {})[r[mn]] = v * scale
     by_kernel = {}
     for (i, name), m in sorted(launches.items()):
         by_kernel.setdefault(name, []).append(m)
