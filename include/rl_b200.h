@@ -199,11 +199,15 @@ int rl_trace_unit_set_stream(rl_trace_unit *unit, void *cuda_stream);
 /* TraceUnit::render (trace_unit.rs:151-168).  Photon ids of the batch are
  * taken from the scene's batch counter (one scene = one App, app.rs:63), so the
  * union of photons over any schedule of B render() calls on a scene is ids
- * [0, B * batch).  Batches of the reference's size do not get a kernel launch
- * of their own: they are queued to the scene's trace dispatcher, which traces
- * everything the scheduler's worker threads have queued (task_scheduler.rs:
- * 95-96,127-182) with one launch whenever a launch slot is free (DESIGN.md 4,
- * "group launches").  If `out` is non-NULL
+ * [0, B * batch).  A batch of the reference's size (4.6 photons per thread of
+ * a full grid) is launched as a few dozen small blocks that take only the
+ * launch's share of each SM's block slots, by the number of other units'
+ * batches in flight (task_scheduler.rs:95-96,127-182 keeps 3C units going):
+ * the batches of the worker threads run side by side on every SM and cover
+ * each other's tails ("small launches").  With RL_TRACE_GROUPS=1
+ * in the environment the batches are instead queued to a per-scene dispatcher
+ * thread that traces whatever is queued with one multi-segment launch
+ * (measured slower, kept for experiments).  If `out` is non-NULL
  * it receives batch_size records (the shim's `mapped_photons` Vec) and the
  * call blocks; with NULL the records stay on the device for plot_device. */
 int rl_trace_unit_render(rl_trace_unit *unit, const rl_scene *scene, rl_mapped_photon *out);
@@ -312,16 +316,24 @@ int rl_gather_unit_accumulate_device(rl_gather_unit *unit, const void *const *xy
 /* GatherUnit::save (gather_unit.rs:68-78): accumulator then compensation,
  * 12 raw bytes per pixel each, no header -> 24*w*h bytes.
  * The host calls this after every gather (app.rs:151).  The call snapshots
- * the device buffers into page-locked host memory and returns; a writer
- * thread of the unit puts the snapshot into `path.tmp` and renames it over
- * `path`, so the file always holds one complete snapshot (the reference
- * truncates and rewrites in place).  A newer snapshot replaces one that has
- * not been written yet.  The first save to a path is written before the call
- * returns, so an unwritable path fails here ("failed to open file",
- * gather_unit.rs:69); a later write failure is returned by the next save or
- * flush.  rl_gather_unit_flush waits for the file to be current;
- * rl_gather_unit_load and rl_gather_unit_destroy flush first. */
+ * the two buffers on the device, in the unit's stream order, and returns; a
+ * writer thread of the unit copies the newest snapshot to page-locked host
+ * memory, puts it into `path.tmp` and renames it over `path`, so the file
+ * always holds one complete snapshot (the reference truncates and rewrites
+ * in place).  A newer snapshot replaces one that has not been written yet,
+ * and the writer starts at most one file per save interval (default 0.1 s,
+ * rl_gather_unit_set_save_interval; 0 = as fast as the files can be
+ * written): a GPU gathers a hundred times a second where the reference's
+ * CPU host gathers every few seconds, and checkpoints that close together
+ * are only host traffic.  The file is never further behind the latest save
+ * than that interval plus one write.  The first save to a path is written
+ * before the call returns, so an unwritable path fails here ("failed to
+ * open file", gather_unit.rs:69); a later write failure is returned by the
+ * next save or flush.  rl_gather_unit_flush waits for the file to be
+ * current (without waiting for the interval); rl_gather_unit_load and
+ * rl_gather_unit_destroy flush first. */
 int rl_gather_unit_save(rl_gather_unit *unit, const char *path);
+int rl_gather_unit_set_save_interval(rl_gather_unit *unit, double seconds);
 int rl_gather_unit_flush(rl_gather_unit *unit);
 /* GatherUnit::read (gather_unit.rs:81-92); a short file is not an error
  * (read.rs:20-32), a missing file is RL_ERR_IO here. */

@@ -145,6 +145,7 @@ SYMBOLS = {
     "rl_gather_unit_accumulate_plot": (_I, [_P, _P, _I]),
     "rl_gather_unit_accumulate_device": (_I, [_P, C.POINTER(_P), _U32]),
     "rl_gather_unit_save": (_I, [_P, C.c_char_p]),
+    "rl_gather_unit_set_save_interval": (_I, [_P, C.c_double]),
     "rl_gather_unit_flush": (_I, [_P]),
     "rl_gather_unit_load": (_I, [_P, C.c_char_p]),
     "rl_gather_unit_download": (_I, [_P, _P, _P]),
@@ -553,6 +554,10 @@ class GatherUnit:
         _check(lib().rl_gather_unit_save(self._h, os.fsencode(path)))
         if wait:
             self.flush()
+
+    def set_save_interval(self, seconds):
+        """At most one background buffer.raw write is started per interval (default 0.1 s)."""
+        _check(lib().rl_gather_unit_set_save_interval(self._h, float(seconds)))
 
     def flush(self):
         _check(lib().rl_gather_unit_flush(self._h))

@@ -211,25 +211,36 @@ struct rl_plot_unit {
 
 // buffer.raw writer of a gather unit (gather_unit.rs:68-78 rewrites the whole file on every
 // gather, app.rs:151; at 1024^2 that is 25 MB of file I/O per gather and was the critical path
-// of the whole pipeline).  save() only snapshots the two device buffers into page-locked host
-// memory (one DMA transfer); a background thread writes the snapshot to `path.tmp` and renames
-// it over `path`, so the file on disk is always one complete snapshot.  A save that arrives
-// while an older snapshot still waits to be written replaces it (every save rewrites the whole
-// file, only the newest state matters).  The first save to a path is written synchronously so
-// that an unwritable path fails in the caller ("failed to open file", gather_unit.rs:69); a
-// later background failure is returned by the next save / flush.
+// of the whole pipeline -- and with the GPU gathering a hundred times a second it would be
+// 2.5 GB/s of device-to-host traffic per GPU for checkpoints nobody can tell apart).
+// save() snapshots the two device buffers into a device-side copy (25 MB at HBM speed, in the
+// unit's stream order) and returns; the unit's writer thread brings the newest snapshot to
+// page-locked host memory on its own stream, writes it to `path.tmp` and renames it over
+// `path`, so the file on disk is always one complete snapshot.  A save that arrives while an
+// older snapshot still waits replaces it (every save rewrites the whole file, only the newest
+// state matters), and the writer starts at most one file per `min_interval` (0.1 s unless
+// rl_gather_unit_set_save_interval says otherwise; flush / load / destroy do not wait for it):
+// the file is never more than that interval plus one write behind the latest save.
+// The first save to a path is written synchronously so that an unwritable path fails in the
+// caller ("failed to open file", gather_unit.rs:69); a later background failure is returned by
+// the next save / flush.
 struct SaveWriter {
     std::mutex m;
     std::condition_variable cv;
     std::thread thread;
     bool started = false, stop = false;
-    float *buf[2] = {nullptr, nullptr};
-    cudaEvent_t copied[2] = {nullptr, nullptr};   // the snapshot in buf[i] has arrived (recorded behind its copies)
+    int hurry = 0;                                  // flush() callers waiting: no pacing
+    float *host = nullptr;                          // page-locked; the writer's (and the synchronous first save's)
+    float *dsnap[2] = {nullptr, nullptr};           // device-side snapshots
+    cudaEvent_t taken[2] = {nullptr, nullptr};      // dsnap[i] is complete (recorded on the unit's stream)
+    cudaStream_t copy_stream = nullptr;             // the writer's device-to-host copies
     int device = 0;
     size_t floats = 0;
-    int pending = -1, writing = -1;
-    std::string pending_path, error;
+    int latest = -1, reading = -1;                  // newest snapshot not yet taken by the writer / the one it is copying out
+    std::string latest_path, error;
     std::vector<std::string> proven;
+    double min_interval = 0.1;                      // seconds between the starts of two background writes
+    std::chrono::steady_clock::time_point last_start{};
 
     static bool write_file(const std::string &path, const float *data, size_t floats, std::string &err) {
         const std::string tmp = path + ".tmp";
@@ -244,25 +255,55 @@ struct SaveWriter {
         }
         return true;
     }
+    cudaError_t allocate(int dev, size_t n_floats) {
+        device = dev;
+        floats = n_floats;
+        cudaError_t e = cudaMallocHost(&host, floats * sizeof(float));
+        for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+            e = cudaMalloc(&dsnap[i], floats * sizeof(float));
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&taken[i], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) release();
+        return e;
+    }
+    void release() {
+        if (host) cudaFreeHost(host);
+        host = nullptr;
+        for (float *&b : dsnap) { if (b) cudaFree(b); b = nullptr; }
+        for (cudaEvent_t &e : taken) { if (e) cudaEventDestroy(e); e = nullptr; }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        copy_stream = nullptr;
+    }
     void run() {
         cudaSetDevice(device);
         std::unique_lock<std::mutex> lock(m);
         for (;;) {
-            cv.wait(lock, [&] { return pending >= 0 || stop; });
-            if (pending < 0) return;
-            const int idx = pending;
-            const std::string path = pending_path;
-            pending = -1;
-            writing = idx;
+            cv.wait(lock, [&] { return latest >= 0 || stop; });
+            if (latest < 0) return;
+            if (min_interval > 0.0)                 // pacing; a newer save may replace `latest` meanwhile
+                cv.wait_until(lock, last_start + std::chrono::duration_cast<std::chrono::steady_clock::duration>(
+                                                     std::chrono::duration<double>(min_interval)),
+                              [&] { return hurry > 0 || stop; });
+            const int idx = latest;
+            const std::string path = latest_path;
+            latest = -1;
+            reading = idx;
+            last_start = std::chrono::steady_clock::now();
             lock.unlock();
             std::string err;
-            // the snapshot was only queued by save(): wait here, not in the caller, for the copies
-            const cudaError_t ce = cudaEventSynchronize(copied[idx]);
+            // the snapshot was only queued by save(): wait here, not in the caller, for it
+            cudaError_t ce = cudaStreamWaitEvent(copy_stream, taken[idx], 0);
+            if (ce == cudaSuccess) {
+                g_d2h_bytes += floats * sizeof(float);
+                ce = cudaMemcpyAsync(host, dsnap[idx], floats * sizeof(float), cudaMemcpyDeviceToHost, copy_stream);
+            }
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(copy_stream);
             bool ok = ce == cudaSuccess;
             if (!ok) err = std::string("buffer.raw snapshot: ") + cudaGetErrorString(ce);
-            else ok = write_file(path, buf[idx], floats, err);
+            else ok = write_file(path, host, floats, err);
             lock.lock();
-            writing = -1;
+            reading = -1;
             if (!ok && error.empty()) error = err;
             cv.notify_all();
         }
@@ -270,7 +311,10 @@ struct SaveWriter {
     // waits until nothing is queued or being written; returns the first background failure
     std::string flush() {
         std::unique_lock<std::mutex> lock(m);
-        cv.wait(lock, [&] { return pending < 0 && writing < 0; });
+        hurry++;
+        cv.notify_all();
+        cv.wait(lock, [&] { return latest < 0 && reading < 0; });
+        hurry--;
         std::string e;
         e.swap(error);
         return e;
@@ -285,8 +329,7 @@ struct SaveWriter {
             thread.join();
             started = false;
         }
-        for (float *&b : buf) { if (b) cudaFreeHost(b); b = nullptr; }
-        for (cudaEvent_t &e : copied) { if (e) cudaEventDestroy(e); e = nullptr; }
+        release();
     }
 };
 
@@ -449,8 +492,10 @@ void sphere_leaf_bound(const std::vector<float4> &leaves, size_t first, size_t n
 // range and bounding sphere {centre m, radius R >= max |c_i - m| + r_i}.
 struct Cluster { uint32_t first, count; double m[3], R; };
 
+// `full_leaves`: split at multiples of `leaf`, so that every cluster but the last has exactly
+// `leaf` members (the three-level scan walks clusters of eight).
 void split_spheres(const std::vector<float4> &sph, std::vector<uint32_t> &idx, size_t lo, size_t hi,
-                   size_t leaf, std::vector<Cluster> &out) {
+                   size_t leaf, std::vector<Cluster> &out, bool full_leaves = false) {
     if (hi - lo <= leaf) {
         Cluster c;
         c.first = (uint32_t)lo; c.count = (uint32_t)(hi - lo);
@@ -479,12 +524,16 @@ void split_spheres(const std::vector<float4> &sph, std::vector<uint32_t> &idx, s
     }
     int axis = 0;
     for (int a = 1; a < 3; a++) if (mx[a] - mn[a] > mx[axis] - mn[axis]) axis = a;
-    const size_t mid = lo + (hi - lo) / 2;
+    size_t mid = lo + (hi - lo) / 2;
+    if (full_leaves) {
+        mid = lo + ((hi - lo) / 2 + leaf - 1) / leaf * leaf;
+        if (mid >= hi) mid = hi - leaf;
+    }
     auto key = [&](uint32_t i) { const float4 s = sph[i]; return axis == 0 ? s.x : (axis == 1 ? s.y : s.z); };
     std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi,
                      [&](uint32_t a, uint32_t b) { return key(a) < key(b) || (key(a) == key(b) && a < b); });
-    split_spheres(sph, idx, lo, mid, leaf, out);
-    split_spheres(sph, idx, mid, hi, leaf, out);
+    split_spheres(sph, idx, lo, mid, leaf, out, full_leaves);
+    split_spheres(sph, idx, mid, hi, leaf, out, full_leaves);
 }
 
 int max_stack(const std::vector<uint32_t> &ops, size_t first, size_t n) {
@@ -730,7 +779,9 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     }
     std::vector<float4> clusters;
     std::vector<uint32_t> cluster_range;
-    double cluster_rmax = 0.0;
+    std::vector<float4> supers;
+    double cluster_rmax = 0.0, super_rmax = 0.0;
+    bool deep = false;
     {
         const size_t n = fl.spheres.size();
         std::vector<uint32_t> idx(n);
@@ -740,9 +791,13 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
         // per cluster, more for large scenes (balances the uniform cluster scan against it)
         size_t leaf = (size_t)(0.45 * sqrt((double)n) + 0.5);
         leaf = leaf < 8 ? 8 : (leaf > 32 ? 32 : leaf);
+        // a thousand spheres or more: three levels (groups of eight clusters of eight spheres), so
+        // that neither the uniform scan of the top level nor the member tests grow with sqrt(n)
+        deep = env_int("RL_DEEP_CLUSTERS", n >= 1024 ? 1 : 0) != 0;
+        if (deep) leaf = 8;
         if (env_int("RL_CLUSTER_LEAF", 0) > 0) leaf = (size_t)env_int("RL_CLUSTER_LEAF", 0);   // experiments
         if (leaf < (n + 999) / 1000) leaf = (n + 999) / 1000;   // pair records index clusters with 11 bits
-        if (n) split_spheres(fl.spheres, idx, 0, n, leaf, cl);
+        if (n) split_spheres(fl.spheres, idx, 0, n, leaf, cl, deep);
         std::vector<float4> spheres(n), sphere_k(n);
         std::vector<uint32_t> sphere_obj(n);
         for (size_t k = 0; k < n; k++) {
@@ -774,6 +829,33 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
             clusters.push_back(make_float4(0.f, 0.f, 0.f, 1.0e30f));
             cluster_range.push_back(0u);
         }
+        // the level above: clusters come out of the median split in tree order, so eight
+        // consecutive ones are neighbours; their bound is taken over the member spheres themselves
+        deep = deep && cl.size() > 8;
+        for (size_t g = 0; deep && g < cl.size(); g += 8) {
+            const size_t g_end = g + 8 < cl.size() ? g + 8 : cl.size();
+            const uint32_t first = cl[g].first, last = cl[g_end - 1].first + cl[g_end - 1].count;
+            double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+            for (uint32_t k = first; k < last; k++) {
+                const float4 sp = fl.spheres[k];
+                const double p[3] = {sp.x, sp.y, sp.z};
+                for (int a = 0; a < 3; a++) { mn[a] = fmin(mn[a], p[a]); mx[a] = fmax(mx[a], p[a]); }
+            }
+            const float4 rec = make_float4((float)(0.5 * (mn[0] + mx[0])), (float)(0.5 * (mn[1] + mx[1])),
+                                           (float)(0.5 * (mn[2] + mx[2])), 0.f);
+            double R = 0.0;
+            for (uint32_t k = first; k < last; k++) {
+                const float4 sp = fl.spheres[k];
+                const double dx = sp.x - rec.x, dy = sp.y - rec.y, dz = sp.z - rec.z;
+                R = fmax(R, sqrt(dx * dx + dy * dy + dz * dz) + sqrt((double)sp.w));
+            }
+            R = R * (1.0 + 1e-6) + 1e-6;
+            const double mr2 = (double)rec.x * rec.x + (double)rec.y * rec.y + (double)rec.z * rec.z;
+            supers.push_back(make_float4(rec.x, rec.y, rec.z, (float)(mr2 - R * R)));
+            if (R > super_rmax) super_rmax = R;
+            if (mr2 + R * R > fl.cmax2) fl.cmax2 = mr2 + R * R;
+        }
+        while (supers.size() % 8 != 0) supers.push_back(make_float4(0.f, 0.f, 0.f, 1.0e30f));
     }
     ds.n_spheres = (uint32_t)fl.spheres.size();
     ds.off_planes = append(blob, fl.planes);            ds.n_planes = (uint32_t)fl.planes.size() / 2;
@@ -823,6 +905,8 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
     if (!sphere_k_global) ds.off_sphere_k = append(blob, fl.sphere_k);
     ds.off_clusters = append(blob, clusters);           ds.n_clusters = (uint32_t)clusters.size();
     ds.off_cluster_range = append(blob, cluster_range);
+    ds.off_supers = append(blob, supers);               ds.n_supers = (uint32_t)supers.size();
+    ds.super_rmax = (float)(super_rmax * 1.0001);
     ds.sphere_cmax2 = (float)(fl.cmax2 * 1.0001);
     ds.cluster_rmax = (float)(cluster_rmax * 1.0001);
     ds.leaf_off_max = (float)(fl.leaf_off_max * 1.0001);
@@ -1391,60 +1475,27 @@ int rl_gather_unit_save(rl_gather_unit *u, const char *path) {
     DeviceGuard guard(u->dev.index);
     SaveWriter &wr = u->writer;
     const size_t n = (size_t)u->width * u->height * 3;
-    if (!wr.buf[0]) {
-        wr.floats = 2 * n;
-        RL_CUDA(cudaMallocHost(&wr.buf[0], 2 * n * sizeof(float)));
-        cudaError_t e = cudaMallocHost(&wr.buf[1], 2 * n * sizeof(float));
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&wr.copied[0], cudaEventDisableTiming | cudaEventBlockingSync);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&wr.copied[1], cudaEventDisableTiming | cudaEventBlockingSync);
-        if (e != cudaSuccess) {
-            cudaFreeHost(wr.buf[0]); wr.buf[0] = nullptr;
-            if (wr.buf[1]) cudaFreeHost(wr.buf[1]);
-            wr.buf[1] = nullptr;
-            return fail(RL_ERR_CUDA, cudaGetErrorString(e));
-        }
-        wr.device = u->dev.index;
+    if (!wr.host) {
+        const cudaError_t e = wr.allocate(u->dev.index, 2 * n);
+        if (e != cudaSuccess) return fail(RL_ERR_CUDA, cudaGetErrorString(e));
     }
     bool proven = false;
     for (const std::string &p : wr.proven) proven |= p == path;
-    int idx = 0;
+    bool no_thread = false;
     if (proven) {
-        {
-            // a snapshot queued for another file is not this one's to replace: let it land first
-            std::unique_lock<std::mutex> lock(wr.m);
-            wr.cv.wait(lock, [&] { return wr.pending < 0 || wr.pending_path == path; });
+        std::unique_lock<std::mutex> lock(wr.m);
+        // a snapshot queued for another file is not this one's to replace: let it land first
+        if (wr.latest >= 0 && wr.latest_path != path) {
+            wr.hurry++;
+            wr.cv.notify_all();
+            wr.cv.wait(lock, [&] { return wr.latest < 0; });
+            wr.hurry--;
         }
-        std::lock_guard<std::mutex> lock(wr.m);
         if (!wr.error.empty()) {
             std::string e;
             e.swap(wr.error);
             return fail(RL_ERR_IO, e);
         }
-        if (wr.pending >= 0) { idx = wr.pending; wr.pending = -1; }   // replace the snapshot not yet written
-        else idx = wr.writing == 0 ? 1 : 0;
-    } else {
-        const std::string e = wr.flush();
-        if (!e.empty()) return fail(RL_ERR_IO, e);
-    }
-    // only this thread fills buffers (a unit is never shared), the writer only reads `writing`
-    float *host = wr.buf[idx];
-    RL_CUDA(copy_async(host, u->d_acc, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
-    RL_CUDA(copy_async(host + n, u->d_comp, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
-    // The snapshot is taken in stream order; nobody waits for it here.  The gather task holds the
-    // gather unit and every finished plot unit while it runs (task_scheduler.rs:209-219): a host
-    // wait at this point is as long as the GPU's queue is deep, and the scheduler has no plot
-    // unit to hand out meanwhile.  The writer thread waits for the event instead.
-    RL_CUDA(cudaEventRecord(wr.copied[idx], u->ss.stream));
-    if (!proven) RL_CUDA(cudaStreamSynchronize(u->ss.stream));
-    if (!proven) {
-        std::string err;
-        if (!SaveWriter::write_file(path, host, 2 * n, err)) return fail(RL_ERR_IO, err);
-        wr.proven.push_back(path);
-        return RL_OK;
-    }
-    bool no_thread = false;
-    {
-        std::lock_guard<std::mutex> lock(wr.m);
         if (!wr.started) {
             try {
                 wr.thread = std::thread([&wr] { wr.run(); });
@@ -1454,18 +1505,42 @@ int rl_gather_unit_save(rl_gather_unit *u, const char *path) {
             }
         }
         if (!no_thread) {
-            wr.pending = idx;
-            wr.pending_path = path;
+            // The snapshot is taken in stream order, on the device; nobody waits for it here.  The
+            // gather task holds the gather unit and every finished plot unit while it runs
+            // (task_scheduler.rs:209-219): a host wait at this point is as long as the GPU's queue
+            // is deep, and the scheduler has no plot unit to hand out meanwhile.  The lock is held
+            // while the copies are queued so that the writer cannot pick this buffer half-queued;
+            // the buffer it is copying out (`reading`) is never the one written here.
+            const int idx = wr.latest >= 0 ? wr.latest : (wr.reading == 0 ? 1 : 0);
+            RL_CUDA(cudaMemcpyAsync(wr.dsnap[idx], u->d_acc, n * sizeof(float), cudaMemcpyDeviceToDevice, u->ss.stream));
+            RL_CUDA(cudaMemcpyAsync(wr.dsnap[idx] + n, u->d_comp, n * sizeof(float), cudaMemcpyDeviceToDevice, u->ss.stream));
+            RL_CUDA(cudaEventRecord(wr.taken[idx], u->ss.stream));
+            wr.latest = idx;
+            wr.latest_path = path;
+            lock.unlock();
+            wr.cv.notify_all();
+            return RL_OK;
         }
     }
-    if (no_thread) {
-        // no writer thread to be had: write in the caller, as the first save does
-        RL_CUDA(cudaStreamSynchronize(u->ss.stream));
-        std::string err;
-        if (!SaveWriter::write_file(path, host, 2 * n, err)) return fail(RL_ERR_IO, err);
-        return RL_OK;
+    // first save to this path, or no writer thread to be had: written here, in the caller
+    {
+        const std::string e = wr.flush();
+        if (!e.empty()) return fail(RL_ERR_IO, e);
     }
-    wr.cv.notify_all();
+    RL_CUDA(copy_async(wr.host, u->d_acc, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(copy_async(wr.host + n, u->d_comp, n * sizeof(float), cudaMemcpyDeviceToHost, u->ss.stream));
+    RL_CUDA(cudaStreamSynchronize(u->ss.stream));
+    std::string err;
+    if (!SaveWriter::write_file(path, wr.host, 2 * n, err)) return fail(RL_ERR_IO, err);
+    if (!proven) wr.proven.push_back(path);
+    return RL_OK;
+}
+
+int rl_gather_unit_set_save_interval(rl_gather_unit *u, double seconds) {
+    if (!u || !(seconds >= 0.0)) return fail(RL_ERR_INVALID, "rl_gather_unit_set_save_interval: invalid argument");
+    std::lock_guard<std::mutex> lock(u->writer.m);
+    u->writer.min_interval = seconds;
+    u->writer.cv.notify_all();
     return RL_OK;
 }
 

@@ -9,6 +9,7 @@
 //   sphere_k     n_spheres     x float4   {cx, cy, cz, |c|^2 - r^2}, record of the sphere pre-test
 //   clusters     n_clusters    x float4   {mx, my, mz, |m|^2 - R^2}, bounding sphere of a group of spheres
 //   cluster_range n_clusters   x uint32   first member | count << 16 (members are contiguous)
+//   supers       n_supers      x float4   bounding sphere of clusters [8k, 8k + 8) (scenes of >= 1024 spheres)
 //   planes       n_planes      x 2 float4 {n.xyz, kind} {offset.xyz, r^2}
 //   paraboloids  n_paraboloids x 3 float4 {offset,0} {normal,0} {focal_point,0}
 //   leaves       n_leaves      x 2 float4 {n.xyz, 0} {offset.xyz, 0}   half-spaces of compounds
@@ -46,19 +47,29 @@ struct PrimTables {
     const float4 *spheres;
     const uint32_t *sphere_obj;
     const float4 *sphere_k_global;   // the pre-test records when they are too many for shared memory, else null
-    uint32_t sphere_k, clusters, cluster_range, planes, paraboloids, leaves, compounds, ops;
+    uint32_t sphere_k, clusters, cluster_range, supers, planes, paraboloids, leaves, compounds, ops;
     uint32_t body_bounds, body_always;
     uint32_t plane_obj, paraboloid_obj, compound_obj;
     uint32_t scratch;         // per-block scratch behind the blob (see Scratch)
-    uint32_t n_spheres, n_clusters, n_planes, n_paraboloids, n_compounds;
+    uint32_t n_spheres, n_clusters, n_supers, n_planes, n_paraboloids, n_compounds;
     uint32_t sphere_leaves;   // some compound has a sphere leaf
-    float sphere_cmax2, cluster_rmax, leaf_off_max, body_rmax;
+    float sphere_cmax2, cluster_rmax, super_rmax, leaf_off_max, body_rmax;
 };
 
 #define RL_TABLES_VEC4 ((sizeof(PrimTables) + 15) / 16)
 #define RL_CAND_SLOTS 8        // queued sphere candidates per lane
 #define RL_COMPOUND_SLOTS 4    // body results per lane, and body tasks per thread of the block list
 #define RL_PAIR_CAP 768        // (lane, cluster) or (lane, body) pairs per warp and round
+// three-level scan: the (lane, cluster) pairs in flight sit at the end of the pair list; a step of the
+// group level runs while at most RL_PAIR2_FILL are waiting and adds at most 32 x 8
+#define RL_PAIR2_FILL 64
+#define RL_PAIR2_CAP (RL_PAIR2_FILL + 256)
+// lanes that share one (lane, cluster) pair in the member tests: 1 = every lane takes a pair of the
+// warp's list and walks the cluster's members itself (the list is what balances the lanes; the
+// per-pair set-up is then paid once per 32 pairs), 8 = eight lanes split the members of a pair
+#ifndef RL_PAIR_LANES
+#define RL_PAIR_LANES 1
+#endif
 #define RL_BODIES_PER_ROUND 64  // bodies whose bounds one scan covers (one bit each of a lane's candidate mask)
 // scratch bytes per thread: ray table 48; sphere queue 2 per slot; two counters 8; pair list
 // 2 * RL_PAIR_CAP / 32; body results 8 per slot.  All of it is private to a warp (its threads'
@@ -86,6 +97,7 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         t.sphere_k_global = sc.sphere_k_global ? sc.blob + sc.off_sphere_k : nullptr;
         t.clusters = base + sc.off_clusters;
         t.cluster_range = base + sc.off_cluster_range;
+        t.supers = base + sc.off_supers;
         t.planes = base + sc.off_planes;
         t.paraboloids = base + sc.off_paraboloids;
         t.leaves = base + sc.off_leaves;
@@ -99,12 +111,14 @@ __device__ __forceinline__ void setup_tables(const DevScene &sc) {
         t.scratch = base + sc.smem_vec4;
         t.n_spheres = sc.n_spheres;
         t.n_clusters = sc.n_clusters;
+        t.n_supers = sc.n_supers;
         t.n_planes = sc.n_planes;
         t.n_paraboloids = sc.n_paraboloids;
         t.n_compounds = sc.n_compounds;
         t.sphere_leaves = sc.sphere_leaves;
         t.sphere_cmax2 = sc.sphere_cmax2;
         t.cluster_rmax = sc.cluster_rmax;
+        t.super_rmax = sc.super_rmax;
         t.leaf_off_max = sc.leaf_off_max;
         t.body_rmax = sc.body_rmax;
         *reinterpret_cast<PrimTables *>(rl_smem) = t;
@@ -546,14 +560,15 @@ __device__ __forceinline__ uint64_t scan_bounds(const float4 *tab, uint32_t coun
 // Lists the warp's candidates as (lane, base + bit) records in `pairs` (RL_PAIR_CAP entries) and
 // clears the listed bits of `todo`; returns the number of records (warp-uniform).  When the
 // warp's candidates do not fit, only a window of 24 bit positions is listed (at most 24 x 32
-// records) and the caller comes back for the rest.
-__device__ __forceinline__ uint32_t emit_pairs(uint64_t &todo, uint32_t base, uint16_t *pairs, uint32_t lane) {
+// records; cap / 32 positions for a smaller cap) and the caller comes back for the rest.
+__device__ __forceinline__ uint32_t emit_pairs(uint64_t &todo, uint32_t base, uint16_t *pairs, uint32_t lane,
+                                               uint32_t cap = RL_PAIR_CAP) {
     uint64_t take = todo;
     uint32_t cnt = (uint32_t)__popcll(take);
     uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
-    if (total > RL_PAIR_CAP) {                                      // warp-uniform
+    if (total > cap) {                                              // warp-uniform
         const uint32_t low = __reduce_min_sync(0xffffffffu, take ? (uint32_t)__ffsll((long long)take) - 1u : 64u);
-        take &= 0xffffffull << low;
+        take &= ((1ull << (cap >> 5)) - 1ull) << low;
         cnt = (uint32_t)__popcll(take);
         total = __reduce_add_sync(0xffffffffu, cnt);
     }
@@ -687,7 +702,15 @@ __device__ __forceinline__ float eval_body_exact(const float4 *leaves, uint32_t 
 // spheres) instead of shared memory.  A template parameter, not a run-time test: the read sits in
 // the innermost loop of the member test, where a uniform select costs 2.7 % of the kernel's time
 // on the built-in scene.
-template <bool GLOBAL_K>
+//
+// DEEP: scenes of a thousand spheres or more carry a third level, bounds over groups of eight
+// clusters (of eight spheres each).  The uniform scan then runs over the groups; a lane's
+// candidate groups are listed as (lane, group) pairs and eight lanes test the eight cluster bounds
+// of one pair with the owner's constants, exactly as they test the members of a cluster one level
+// down; the surviving (lane, cluster) pairs collect in a short list that is drained four pairs at
+// a time into the member tests.  4096 random spheres: 64 + ~80 + ~150 pre-tests per ray instead of
+// 256 + ~300 with two levels.
+template <bool GLOBAL_K, bool DEEP>
 __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true) {
     const PrimTables &tb = tables();
     Hit best;
@@ -723,8 +746,13 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
     const bool warp_live = __any_sync(0xffffffffu, live);       // warp-uniform
 
     if (warp_live) intersect_flat_surfaces(tb, ray, best);
-    ray_tab[3 * tid + 2] = make_float4(thr, bthr, best.t,       // .z: nearest hit so far, bodies beyond it are skipped
-                                       fmaf(RL_SLAB_INFLATE_REL, sqrtf(oo) + tb.leaf_off_max, RL_SLAB_INFLATE));
+    const float slab_inflate = fmaf(RL_SLAB_INFLATE_REL, sqrtf(oo) + tb.leaf_off_max, RL_SLAB_INFLATE);
+    if (DEEP)                                                   // .zw: the owner's thresholds of the cluster-bound test
+        ray_tab[3 * tid + 2] = make_float4(thr, bthr, -(2.0f * tb.cluster_rmax * sqrtf(slack) + 2.0f * slack),
+                                           bthr - sqrtf(dd) * tb.cluster_rmax);
+    else
+        ray_tab[3 * tid + 2] = make_float4(thr, bthr, best.t,   // .z: nearest hit so far, bodies beyond it are skipped
+                                           slab_inflate);
 
     // Two-level sphere scan.  Level 1, uniform over the warp: the same pre-test against the bounding
     // sphere {m, R} of each cluster of spheres, with thresholds widened so that a cluster is
@@ -745,6 +773,117 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
         const uint32_t n_clusters = tb.n_clusters;
         const float thr_c = -(2.0f * tb.cluster_rmax * sqrtf(slack) + 2.0f * slack);
         const float bthr_c = bthr - sqrtf(dd) * tb.cluster_rmax;
+        if constexpr (DEEP) {
+            const float4 *supers = sm_vec(tb.supers);
+            const uint32_t n_supers = tb.n_supers;
+            const float thr_s = -(2.0f * tb.super_rmax * sqrtf(slack) + 2.0f * slack);
+            const float bthr_s = bthr - sqrtf(dd) * tb.super_rmax;
+            uint16_t *pairs2 = pairs + (RL_PAIR_CAP - RL_PAIR2_CAP);
+#pragma unroll 1
+            for (uint32_t base = 0; warp_live && base < n_supers; base += 64) {
+                uint64_t todo = scan_bounds(supers + base, min(64u, n_supers - base), d, ndo, m2ox, m2oy, m2oz, oo,
+                                            thr_s, bthr_s);
+                while (__any_sync(0xffffffffu, todo != 0ull)) {
+                    const uint32_t npairs = emit_pairs(todo, base, pairs, lane, RL_PAIR_CAP - RL_PAIR2_CAP);
+                    uint32_t pb = 0, n2 = 0;                        // warp-uniform
+#pragma unroll 1
+                    for (;;) {
+                        if (pb < npairs && n2 <= RL_PAIR2_FILL) {
+                            // group level: every lane takes one (lane, group) pair of the list and tests
+                            // the group's eight cluster bounds with the owner's constants
+                            const uint32_t p = pb + lane;
+                            uint32_t m8 = 0u, tag = 0u;
+                            if (p < npairs) {
+                                const uint32_t pair = pairs[p];
+                                const uint32_t owner = wbase + (pair >> RL_PAIR_INDEX_BITS);
+                                const float4 *cl = clusters + ((pair & RL_PAIR_INDEX_MAX) << 3);
+                                tag = (pair & ~RL_PAIR_INDEX_MAX) | ((pair & RL_PAIR_INDEX_MAX) << 3);
+                                const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1];
+                                const float2 th = *reinterpret_cast<const float2 *>(&ray_tab[3 * owner + 2].z);
+                                // groups start at multiples of eight records = 128 bytes: lane l begins
+                                // with record l mod 8, so that the 32 reads of a step spread over all banks
+#pragma unroll
+                                for (uint32_t j = 0; j < 8; j++) {
+                                    const uint32_t jj = (j + lane) & 7u;
+                                    const float4 s = cl[jj];         // padding records are never kept
+                                    const float b = fmaf(rd.x, s.x, fmaf(rd.y, s.y, fmaf(rd.z, s.z, rd.w)));
+                                    const float cc = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w))) + ro.w;
+                                    const float disc = fmaf(b, b, -cc);
+                                    if (disc >= th.x && b >= th.y) m8 |= 1u << jj;
+                                }
+                            }
+                            const uint32_t cnt = (uint32_t)__popc(m8);
+                            uint32_t incl = cnt;
+#pragma unroll
+                            for (uint32_t sh = 1; sh < 32; sh <<= 1) {
+                                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, sh);
+                                if (lane >= sh) incl += v;
+                            }
+                            uint16_t *dst = pairs2 + n2 + (incl - cnt);
+#pragma unroll 1
+                            while (m8) {
+                                const uint32_t bit = (uint32_t)__ffs((int)m8) - 1u;
+                                m8 &= m8 - 1u;
+                                *dst++ = (uint16_t)(tag | bit);
+                            }
+                            n2 += __shfl_sync(0xffffffffu, incl, 31);
+                            pb += 32u;
+                            __syncwarp();
+                        } else if (n2 != 0u) {
+                            // member level: every lane takes one of the last 32 (lane, cluster) pairs
+                            const uint32_t take = n2 < 32u ? n2 : 32u;
+                            if (lane < take) {
+                                const uint32_t pair = pairs2[n2 - 1u - lane];
+                                const uint32_t owner = wbase + (pair >> RL_PAIR_INDEX_BITS);
+                                const uint32_t r = cluster_range[pair & RL_PAIR_INDEX_MAX];
+                                const uint32_t first = r & 0xffffu, count = r >> 16;
+                                const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1];
+                                const float2 rt = *reinterpret_cast<const float2 *>(&ray_tab[3 * owner + 2]);
+                                // clusters of eight start at multiples of 128 bytes: the lanes walk them
+                                // from different members on (see the group level)
+                                const uint32_t start = (lane & 7u) < count ? (lane & 7u) : 0u;
+#pragma unroll 1
+                                for (uint32_t j = 0; j < count; j++) {
+                                    uint32_t jj = j + start;
+                                    if (jj >= count) jj -= count;
+                                    const uint32_t m = first + jj;
+                                    const float4 s = GLOBAL_K ? __ldg(sphere_k_global + m) : sphere_k[m];
+                                    const float b = fmaf(rd.x, s.x, fmaf(rd.y, s.y, fmaf(rd.z, s.z, rd.w)));
+                                    const float c = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w))) + ro.w;
+                                    const float disc = fmaf(b, b, -c);
+                                    if (disc >= rt.x && b >= rt.y) {
+                                        const uint32_t slot = atomicAdd(&sq_cnt[owner], 1u);
+                                        if (slot < RL_CAND_SLOTS) sq_base[slot * nthreads + owner] = (uint16_t)m;
+                                    }
+                                }
+                            }
+                            n2 -= take;
+                            __syncwarp();
+                        } else {
+                            break;
+                        }
+                    }
+                    // exact Sphere::intersect for the candidates queued for this lane (as below)
+                    const uint32_t cnt = sq_cnt[tid];
+                    if (cnt > RL_CAND_SLOTS) {
+#pragma unroll 1
+                        for (uint32_t k = 0; k < tb.n_spheres; k++) {
+                            const float t = sphere_t(__ldg(spheres + k), ray);
+                            if (t > 0.0f) consider(best, t, (int)__ldg(sphere_obj + k), (RL_HIT_SPHERE << 28) | k);
+                        }
+                    } else {
+#pragma unroll 1
+                        for (uint32_t k = 0; k < cnt; k++) {
+                            const uint32_t idx = sq_base[k * nthreads + tid];
+                            const float t = sphere_t(__ldg(spheres + idx), ray);
+                            if (t > 0.0f) consider(best, t, (int)__ldg(sphere_obj + idx), (RL_HIT_SPHERE << 28) | idx);
+                        }
+                    }
+                    sq_cnt[tid] = 0u;
+                    __syncwarp();
+                }
+            }
+        } else {
 #pragma unroll 1
         for (uint32_t base = 0; warp_live && base < n_clusters; base += 64) {
             uint64_t todo = scan_bounds(clusters + base, min(64u, n_clusters - base), d, ndo, m2ox, m2oy, m2oz, oo,
@@ -755,8 +894,8 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
                 // member each with the owner's constants, so the work of lanes with many candidate
                 // clusters is spread over the warp; survivors go to the owner's sphere queue.
 #pragma unroll 1
-                for (uint32_t pb = 0; pb < npairs; pb += 4) {
-                    const uint32_t p = pb + (lane >> 3);
+                for (uint32_t pb = 0; pb < npairs; pb += 32 / RL_PAIR_LANES) {
+                    const uint32_t p = pb + lane / RL_PAIR_LANES;
                     if (p < npairs) {
                         const uint32_t pair = pairs[p];
                         const uint32_t owner = wbase + (pair >> RL_PAIR_INDEX_BITS);
@@ -765,7 +904,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
                         const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1];
                         const float2 rt = *reinterpret_cast<const float2 *>(&ray_tab[3 * owner + 2]);
 #pragma unroll 1
-                        for (uint32_t m = (r & 0xffffu) + (lane & 7u); m < end; m += 8) {
+                        for (uint32_t m = (r & 0xffffu) + lane % RL_PAIR_LANES; m < end; m += RL_PAIR_LANES) {
                             const float4 s = GLOBAL_K ? __ldg(sphere_k_global + m) : sphere_k[m];   // {cx, cy, cz, |c|^2 - r^2}
                             const float b = fmaf(rd.x, s.x, fmaf(rd.y, s.y, fmaf(rd.z, s.z, rd.w)));
                             const float c = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w))) + ro.w;
@@ -799,12 +938,14 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
                 __syncwarp();
             }
         }
+        }
     };
 
     const uint32_t n_compounds = tb.n_compounds;
     sphere_phase();
     if (n_compounds == 0u) return best;                         // block-uniform
-    ray_tab[3 * tid + 2].z = best.t;                            // sphere and flat hits bound the bodies worth evaluating
+    if (DEEP) *reinterpret_cast<float2 *>(&ray_tab[3 * tid + 2].z) = make_float2(best.t, slab_inflate);
+    else ray_tab[3 * tid + 2].z = best.t;                       // sphere and flat hits bound the bodies worth evaluating
     res_cnt[tid] = 0u;
 
     // Compound bodies, entirely within the warp (no block barrier: the warps of a block run
@@ -937,7 +1078,9 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
 
 // for the probes: whichever instance the scene needs
 __device__ __forceinline__ Hit intersect_scene_any(const Ray &ray, bool live = true) {
-    return tables().sphere_k_global ? intersect_scene<true>(ray, live) : intersect_scene<false>(ray, live);
+    if (tables().n_supers != 0u)
+        return tables().sphere_k_global ? intersect_scene<true, true>(ray, live) : intersect_scene<false, true>(ray, live);
+    return tables().sphere_k_global ? intersect_scene<true, false>(ray, live) : intersect_scene<false, false>(ray, live);
 }
 
 struct Surf { V3 position, normal, tangent; };

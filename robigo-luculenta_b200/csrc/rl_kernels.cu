@@ -117,7 +117,7 @@ __device__ __forceinline__ void generate_camera_entry(const DevScene &sc, const 
 //     scene is 22 % slower (4.5 instruction-fetch stall cycles per issued instruction instead of
 //     0.3).  Scenes without compound bodies execute a small enough part of the loop and are
 //     10-20 % faster free-running: launch_trace picks the form by that.
-template <bool BLOCK_RING, bool GLOBAL_K>
+template <bool BLOCK_RING, bool GLOBAL_K, bool DEEP>
 __global__ void __launch_bounds__(RL_TRACE_THREADS, RL_TRACE_MIN_BLOCKS)
 trace_kernel(const DevScene sc, const TraceArgs a) {
     setup_tables(sc);
@@ -227,7 +227,7 @@ trace_kernel(const DevScene sc, const TraceArgs a) {
             const RngKey key = {cta->seed[seg], cta->first_photon[seg] + index};
             rng.load(key, rays);
         }
-        const Hit hit = intersect_scene<GLOBAL_K>(alive ? ray : idle_ray(), alive);
+        const Hit hit = intersect_scene<GLOBAL_K, DEEP>(alive ? ray : idle_ray(), alive);
         if (alive) {
             rays++;                                                 // Scene::intersect calls (scene.rs:39)
             // trace_unit.rs:91-131
@@ -404,10 +404,15 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     const bool block_ring = env_int("RL_TRACE_LOCKSTEP", sc.n_compounds != 0u ? 1 : 0) != 0;
     const bool global_k = sc.sphere_k_global != 0u;
     typedef void (*TraceKernel)(const DevScene, const TraceArgs);
-    const TraceKernel kernel = block_ring ? (global_k ? trace_kernel<true, true> : trace_kernel<true, false>)
-                                          : (global_k ? trace_kernel<false, true> : trace_kernel<false, false>);
-    static KernelCache caches[4][16];
-    KernelCache &cached = dev >= 0 && dev < 16 ? caches[(block_ring ? 2 : 0) + (global_k ? 1 : 0)][dev] : scratch_entry;
+    const bool deep = sc.n_supers != 0u;
+    static const TraceKernel instances[8] = {
+        trace_kernel<false, false, false>, trace_kernel<false, true, false>, trace_kernel<true, false, false>,
+        trace_kernel<true, true, false>,   trace_kernel<false, false, true>, trace_kernel<false, true, true>,
+        trace_kernel<true, false, true>,   trace_kernel<true, true, true>};
+    const int which = (deep ? 4 : 0) + (block_ring ? 2 : 0) + (global_k ? 1 : 0);
+    const TraceKernel kernel = instances[which];
+    static KernelCache caches[8][16];
+    KernelCache &cached = dev >= 0 && dev < 16 ? caches[which][dev] : scratch_entry;
     err = prepare_kernel(kernel, cached, dev);
     if (err != cudaSuccess) return err;
     const int max_smem = cached.max_smem;

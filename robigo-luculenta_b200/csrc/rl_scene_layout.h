@@ -39,12 +39,16 @@ struct DevScene {
     uint32_t off_ops, n_ops;
     uint32_t off_sphere_obj, off_plane_obj, off_paraboloid_obj, off_compound_obj, off_sphere_k;
     uint32_t off_clusters, n_clusters, off_cluster_range;   // clusters padded to a multiple of 8 records
+    // scenes with a thousand spheres or more: a level of bounds above the clusters -- super k bounds
+    // the members of clusters [8k, 8k + 8) (padded to a multiple of 8 records; 0: no such level)
+    uint32_t off_supers, n_supers;
     uint32_t off_body_bounds, off_body_always;              // bounding spheres of the compounds in the pre-test's form
                                                             // (padded to 8), and per 64 bodies the mask of unbounded ones
     const float4 *materials;  // per object
     uint32_t n_objects;
     float sphere_cmax2;       // max (|centre|^2 + r^2) over spheres and clusters (error bound of the pre-test)
     float cluster_rmax;       // largest cluster bounding radius
+    float super_rmax;         // largest bounding radius of a group of eight clusters
     float leaf_off_max;       // largest |offset| over the half-spaces of compound surfaces (slab-test inflation)
     float body_rmax;          // largest bounding radius of a compound
     uint32_t sphere_leaves;   // 1: some compound has a sphere leaf (geometry.rs:263-267)

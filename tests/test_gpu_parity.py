@@ -8,6 +8,7 @@ bit-equal; tonemap is bit-equal given the same exposure and within 1 LSB
 end to end.
 """
 import os
+import time
 
 import numpy as np
 import pytest
@@ -95,7 +96,8 @@ def compare_hits(got, want, what):
         assert_bit_equal(got[f], want[f], f"{what}.{f}")
 
 
-@pytest.mark.parametrize("which,param,extent", [(1, 0, 8.0), (2, 0, 60.0), (3, 0, 15.0), (4, 512, 30.0), (6, 0, 12.0)])
+@pytest.mark.parametrize("which,param,extent", [(1, 0, 8.0), (2, 0, 60.0), (3, 0, 15.0), (4, 512, 30.0), (4, 4096, 30.0), (4, 1500, 30.0),
+                                                (6, 0, 12.0)])
 def test_scene_intersect_bit_equal(gpu, orc, which, param, extent):
     b = gpu.SceneBuilder(which, param)
     sc = gpu.Scene(b)
@@ -471,6 +473,39 @@ def test_buffer_raw_background_writer(gpu, tmp_path):
     raw = np.fromfile(path, dtype="<f4")
     assert np.array_equal(raw[: 3 * w * h], acc.reshape(-1)) and np.array_equal(raw[3 * w * h:], comp.reshape(-1))
     assert not os.path.exists(path + ".tmp")
+
+
+def test_buffer_raw_save_interval(gpu, tmp_path):
+    # the writer starts at most one file per save interval: a burst of gathers (a GPU gathers a
+    # hundred times a second, app.rs:143-152) costs device-side snapshots, not host traffic, and
+    # flush still leaves the newest state on disk
+    w, h = 256, 256
+    snapshot = 24 * w * h
+    rng = np.random.default_rng(12)
+    path = str(tmp_path / "buffer.raw")
+    g = gpu.GatherUnit(w, h)
+    frame = rng.uniform(0, 5, (h, w, 3)).astype(np.float32)
+    g.save(path)                                     # proves the path (synchronous)
+    g.set_save_interval(5.0)
+    g.accumulate(frame)
+    g.save(path, wait=False)                         # the first background write starts at once
+    time.sleep(0.5)
+    gpu.reset_transfer_counters()
+    for _ in range(25):
+        g.accumulate(frame)
+        g.save(path, wait=False)
+    h2d, d2h = gpu.transfer_counters()
+    assert h2d == 25 * 12 * w * h and d2h == 0       # inside the interval: nothing came down
+    acc, comp = g.download(with_compensation=True)
+    t0 = time.time()
+    g.flush()                                        # does not wait for the interval
+    assert time.time() - t0 < 2.0
+    raw = np.fromfile(path, dtype="<f4")
+    assert np.array_equal(raw[: 3 * w * h], acc.reshape(-1)) and np.array_equal(raw[3 * w * h:], comp.reshape(-1))
+    _, d2h = gpu.transfer_counters()
+    assert d2h == snapshot + 2 * 12 * w * h          # one snapshot + the download above
+    with pytest.raises(gpu.RlError):
+        g.set_save_interval(-1.0)
 
 
 # ----------------------------------------------------------------- tonemap

@@ -13,6 +13,7 @@ for w in $WHAT; do
     dsweep) bash tools/dispatch_sweep.sh ${TAG} ;;
     ssweep) bash tools/share_sweep.sh ${TAG} ;;
     ab) bash tools/kernel_ab.sh ${TAG} ;;
+    deep) bash tools/deep_ab.sh ${TAG} ;;
     traffic) timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_traffic.csv python tools/profile_trace.py > gpurun_out/${TAG}_traffic.log 2>&1; tail -1 gpurun_out/${TAG}_traffic.log ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_launches.log 2>&1; tail -1 gpurun_out/${TAG}_launches.log | cut -c1-200 ;;
     leaf) for L in 12 16 20 24 29 40; do echo "RL_CLUSTER_LEAF=$L"; RL_CLUSTER_LEAF=$L RL_RATES_ONLY=C4 timeout 200 python tools/config_rates.py 2>&1 | tail -1; done | tee gpurun_out/${TAG}_leaf.txt ;;

@@ -19,6 +19,6 @@ if [ -f variants/env.txt ]; then
   while read -r setting; do
     [ -z "$setting" ] && continue
     echo "== in-place library, $setting" | tee -a gpurun_out/${TAG}_ab.txt
-    env $setting RL_RATES_ONLY=${RL_RATES_ONLY:-C2} timeout 300 python tools/config_rates.py 2>&1 | tail -1 | tee -a gpurun_out/${TAG}_ab.txt
+    env RL_RATES_ONLY=${RL_RATES_ONLY:-C2} $setting timeout 300 python tools/config_rates.py 2>&1 | tail -1 | tee -a gpurun_out/${TAG}_ab.txt
   done < variants/env.txt
 fi
