@@ -70,6 +70,9 @@ struct PrimTables {
 #ifndef RL_PAIR_LANES
 #define RL_PAIR_LANES 1
 #endif
+#ifndef RL_SLAB_LANES
+#define RL_SLAB_LANES 1        // the same choice for the slab test of the (lane, body) pairs
+#endif
 #define RL_BODIES_PER_ROUND 64  // bodies whose bounds one scan covers (one bit each of a lane's candidate mask)
 // scratch bytes per thread: ray table 48; sphere queue 2 per slot; two counters 8; pair list
 // 2 * RL_PAIR_CAP / 32; body results 8 per slot.  All of it is private to a warp (its threads'
@@ -538,8 +541,12 @@ __device__ __forceinline__ Hit intersect_scene_brute(const Ray &ray) {
 // 64; tables are padded with records no ray selects): bit k of the result is set iff the sphere
 // pre-test keeps record k for this lane's ray -- 8 fused operations, two compares and one
 // predicated OR per record, the candidates of a lane stay in two registers.
+// B'^2 - C' >= thr is evaluated as B'^2 - (C' - |o|^2) >= thr + |o|^2: the |o|^2 term is the same for
+// every record of a ray, so it is added to the threshold once instead of to every C' (one rounding
+// of a term of the same magnitude either way: the error bound of the pre-test is unchanged).
 __device__ __forceinline__ uint64_t scan_bounds(const float4 *tab, uint32_t count, V3 d, float ndo, float m2ox,
                                                 float m2oy, float m2oz, float oo, float thr, float bthr) {
+    const float thr_oo = thr + oo;
     uint64_t mask = 0ull;
 #pragma unroll 1
     for (uint32_t g = 0; g < count; g += 8) {
@@ -548,9 +555,9 @@ __device__ __forceinline__ uint64_t scan_bounds(const float4 *tab, uint32_t coun
         for (uint32_t j = 0; j < 8; j++) {
             const float4 s = tab[g + j];
             const float b = fmaf(d.x, s.x, fmaf(d.y, s.y, fmaf(d.z, s.z, ndo)));
-            const float c = fmaf(m2ox, s.x, fmaf(m2oy, s.y, fmaf(m2oz, s.z, s.w))) + oo;
+            const float c = fmaf(m2ox, s.x, fmaf(m2oy, s.y, fmaf(m2oz, s.z, s.w)));   // C' - |o|^2
             const float disc = fmaf(b, b, -c);
-            if (disc >= thr && b >= bthr) m8 |= 1u << j;
+            if (disc >= thr_oo && b >= bthr) m8 |= 1u << j;
         }
         mask |= (uint64_t)m8 << g;
     }
@@ -748,10 +755,10 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
     if (warp_live) intersect_flat_surfaces(tb, ray, best);
     const float slab_inflate = fmaf(RL_SLAB_INFLATE_REL, sqrtf(oo) + tb.leaf_off_max, RL_SLAB_INFLATE);
     if (DEEP)                                                   // .zw: the owner's thresholds of the cluster-bound test
-        ray_tab[3 * tid + 2] = make_float4(thr, bthr, -(2.0f * tb.cluster_rmax * sqrtf(slack) + 2.0f * slack),
+        ray_tab[3 * tid + 2] = make_float4(thr + oo, bthr, -(2.0f * tb.cluster_rmax * sqrtf(slack) + 2.0f * slack) + oo,
                                            bthr - sqrtf(dd) * tb.cluster_rmax);
     else
-        ray_tab[3 * tid + 2] = make_float4(thr, bthr, best.t,   // .z: nearest hit so far, bodies beyond it are skipped
+        ray_tab[3 * tid + 2] = make_float4(thr + oo, bthr, best.t,   // .x: threshold + |o|^2 (see scan_bounds); .z: nearest hit so far, bodies beyond it are skipped
                                            slab_inflate);
 
     // Two-level sphere scan.  Level 1, uniform over the warp: the same pre-test against the bounding
@@ -807,7 +814,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
                                     const uint32_t jj = (j + lane) & 7u;
                                     const float4 s = cl[jj];         // padding records are never kept
                                     const float b = fmaf(rd.x, s.x, fmaf(rd.y, s.y, fmaf(rd.z, s.z, rd.w)));
-                                    const float cc = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w))) + ro.w;
+                                    const float cc = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w)));
                                     const float disc = fmaf(b, b, -cc);
                                     if (disc >= th.x && b >= th.y) m8 |= 1u << jj;
                                 }
@@ -849,7 +856,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
                                     const uint32_t m = first + jj;
                                     const float4 s = GLOBAL_K ? __ldg(sphere_k_global + m) : sphere_k[m];
                                     const float b = fmaf(rd.x, s.x, fmaf(rd.y, s.y, fmaf(rd.z, s.z, rd.w)));
-                                    const float c = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w))) + ro.w;
+                                    const float c = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w)));
                                     const float disc = fmaf(b, b, -c);
                                     if (disc >= rt.x && b >= rt.y) {
                                         const uint32_t slot = atomicAdd(&sq_cnt[owner], 1u);
@@ -890,9 +897,9 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
                                         thr_c, bthr_c);
             while (__any_sync(0xffffffffu, todo != 0ull)) {
                 const uint32_t npairs = emit_pairs(todo, base, pairs, lane);
-                // Level 2, warp-cooperative: eight lanes take one (lane, cluster) pair and test one
-                // member each with the owner's constants, so the work of lanes with many candidate
-                // clusters is spread over the warp; survivors go to the owner's sphere queue.
+                // Level 2: every lane takes one (lane, cluster) pair of the list and tests the
+                // cluster's members with the owner's constants, so the work of lanes with many
+                // candidate clusters is spread over the warp; survivors go to the owner's sphere queue.
 #pragma unroll 1
                 for (uint32_t pb = 0; pb < npairs; pb += 32 / RL_PAIR_LANES) {
                     const uint32_t p = pb + lane / RL_PAIR_LANES;
@@ -907,7 +914,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
                         for (uint32_t m = (r & 0xffffu) + lane % RL_PAIR_LANES; m < end; m += RL_PAIR_LANES) {
                             const float4 s = GLOBAL_K ? __ldg(sphere_k_global + m) : sphere_k[m];   // {cx, cy, cz, |c|^2 - r^2}
                             const float b = fmaf(rd.x, s.x, fmaf(rd.y, s.y, fmaf(rd.z, s.z, rd.w)));
-                            const float c = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w))) + ro.w;
+                            const float c = fmaf(ro.x, s.x, fmaf(ro.y, s.y, fmaf(ro.z, s.z, s.w)));
                             const float disc = fmaf(b, b, -c);
                             if (disc >= rt.x && b >= rt.y) {
                                 const uint32_t slot = atomicAdd(&sq_cnt[owner], 1u);
@@ -955,8 +962,8 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
     //     exactly B^2 - dd C >= 0, and the evaluated B'^2 - C' can fall short of that by the
     //     rounding of both (e1) and by |dd - 1| |C| only: threshold -slack; B >= -|d| R.
     //     Unbounded bodies are flagged in a mask that is OR-ed in;
-    //  2. slab test warp-cooperatively: eight lanes per (lane, body) pair, one leaf each, shuffle
-    //     reduction of the interval; the surviving pairs are compacted in place;
+    //  2. slab test, one lane per (lane, body) pair of the warp's list (the list is what balances
+    //     the lanes); the surviving pairs are compacted in place;
     //  3. exact evaluation, again eight lanes per pair and one leaf per lane (eval_bodies_exact):
     //     the reference's recursion is decided from the leaves' own hits and containment tests,
     //     all independent of each other, or handed to the owner lane when it cannot be;
@@ -980,6 +987,47 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
             const uint32_t npairs = emit_pairs(todo, round, pairs, lane);
             uint32_t nsurv = 0;                                 // warp-uniform: pairs that pass the slab test, compacted in place
 #pragma unroll 1
+#if RL_SLAB_LANES == 1
+            // every lane takes one (lane, body) pair of the list and walks the body's half-spaces
+            // itself, from a start staggered by lane (bodies of eight leaves start at multiples of
+            // 256 bytes: the 32 reads of a step would otherwise meet in the same banks); max and min
+            // are exact, so the interval does not depend on the order
+            for (uint32_t pb = 0; pb < npairs; pb += 32) {
+                const uint32_t p = pb + lane;
+                const bool valid = p < npairs;
+                const uint32_t pair = valid ? pairs[p] : 0u;
+                const uint32_t owner = wbase + (pair >> RL_PAIR_INDEX_BITS), body = pair & RL_PAIR_INDEX_MAX;
+                const float4 c4 = compounds[2 * body];
+                const uint32_t first_leaf = __float_as_uint(c4.x);
+                const uint32_t n_leaves = valid ? __float_as_uint(c4.y) : 0u;
+                const float4 ro = ray_tab[3 * owner], rd = ray_tab[3 * owner + 1];
+                const float2 bi = *reinterpret_cast<const float2 *>(&ray_tab[3 * owner + 2].z);
+                const float best_t = bi.x, inflate = bi.y;
+                const float ox = -0.5f * ro.x, oy = -0.5f * ro.y, oz = -0.5f * ro.z;   // ro = -2 o, exactly
+                float t_enter = 0.0f, t_exit = 3.0e38f;
+                bool outside_parallel = false;
+                const uint32_t first_j = sub < n_leaves ? sub : 0u;
+#pragma unroll 1
+                for (uint32_t j = 0; j < n_leaves; j++) {
+                    uint32_t jj = j + first_j;
+                    if (jj >= n_leaves) jj -= n_leaves;
+                    const uint32_t k = first_leaf + jj;
+                    const float4 n4 = leaves[2 * k], o4 = leaves[2 * k + 1];
+                    const float dn = fmaf(n4.z, rd.z, fmaf(n4.y, rd.y, n4.x * rd.x));
+                    const float s0 = fmaf(n4.z, oz - o4.z, fmaf(n4.y, oy - o4.y, n4.x * (ox - o4.x))) - inflate * n4.w;
+                    const float tk = __fdividef(-s0, dn);
+                    if (dn < 0.0f) t_enter = fmaxf(t_enter, tk);
+                    else if (dn > 0.0f) t_exit = fminf(t_exit, tk);
+                    else if (s0 > 0.0f) outside_parallel = true;
+                }
+                const float start = t_enter * 0.9999f - 1.0e-3f;
+                const bool may_hit = valid && !outside_parallel && !(t_exit < 0.0f) && !(start > t_exit) && !(start > best_t);
+                const uint32_t keep = __ballot_sync(0xffffffffu, may_hit);
+                __syncwarp();                                   // every lane has read its pair: the list may be overwritten
+                if (may_hit) pairs[nsurv + __popc(keep & lanes_below)] = (uint16_t)pair;
+                nsurv += __popc(keep);
+            }
+#else
             for (uint32_t pb = 0; pb < npairs; pb += 4) {
                 const uint32_t p = pb + group;
                 const bool valid = p < npairs;                  // uniform within a group of eight
@@ -1018,6 +1066,7 @@ __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true)
                 if (may_hit && sub == 0u) pairs[nsurv + __popc(keep & lanes_below)] = (uint16_t)pair;
                 nsurv += __popc(keep);
             }
+#endif
             __syncwarp();
             // 3. exact evaluation of the survivors
 #pragma unroll 1

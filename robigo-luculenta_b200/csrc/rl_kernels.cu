@@ -289,7 +289,8 @@ static uint32_t block_ring_entries(int threads, int shrink) {
 // threads; 64 K registers at 80 per thread)
 static size_t trace_ctas_per_sm(size_t smem, int threads) {
     const size_t by_smem = (228u * 1024u) / (smem + 1024u);
-    const size_t by_threads = 2048u / (size_t)threads, by_regs = 65536u / (80u * (size_t)threads);
+    const size_t regs = RL_TRACE_THREADS > 768 ? 64u : 80u;      // what __launch_bounds__ leaves the compiler
+    const size_t by_threads = 2048u / (size_t)threads, by_regs = 65536u / (regs * (size_t)threads);
     const size_t cap = by_threads < by_regs ? by_threads : by_regs;
     return by_smem < cap ? by_smem : cap;
 }
