@@ -787,8 +787,9 @@ int rl_scene_create(const rl_scene_desc *desc, rl_scene **out) {
         std::vector<uint32_t> idx(n);
         for (size_t k = 0; k < n; k++) idx[k] = (uint32_t)k;
         std::vector<Cluster> cl;
-        // eight lanes share one cluster in the cooperative member test: at least eight members
-        // per cluster, more for large scenes (balances the uniform cluster scan against it)
+        // clusters of about eight members, more for larger scenes (balances the uniform scan of
+        // the cluster bounds against the member tests; measured flat between 5 and 16 on the
+        // built-in scene, profiles/r2_cluster_leaf_sweep.txt)
         size_t leaf = (size_t)(0.45 * sqrt((double)n) + 0.5);
         leaf = leaf < 8 ? 8 : (leaf > 32 ? 32 : leaf);
         // a thousand spheres or more: three levels (groups of eight clusters of eight spheres), so

@@ -650,8 +650,8 @@ __device__ __forceinline__ float eval_body_exact(const float4 *leaves, uint32_t 
 }
 
 // Conservative slab test of a convex body against the ray, with every
-// half-space moved outwards by RL_SLAB_INFLATE (evaluated eight lanes per body
-// inside intersect_scene).  A hit the reference returns lies on one leaf plane
+// half-space moved outwards by RL_SLAB_INFLATE (evaluated one lane per (lane,
+// body) pair inside intersect_scene).  A hit the reference returns lies on one leaf plane
 // and passes the f32 containment test of every other leaf (each sits in a
 // sibling subtree on the way to the root, geometry.rs:386-388), so it is inside
 // the inflated body up to rounding (~1e-5 at the scene's coordinate
@@ -685,16 +685,17 @@ __device__ __forceinline__ float eval_body_exact(const float4 *leaves, uint32_t 
 // The spheres are grouped into clusters with bounding spheres (host side):
 // level 1 runs the pre-test against the cluster bounds in a uniform loop, each
 // lane queueing its candidate clusters privately; the queues are compacted into
-// one (lane, cluster) list per warp; level 2 tests the members eight lanes per
-// pair with the owner's constants from a shared ray table, so that lanes with
-// many candidates do not hold the warp back; level 3 is the exact sphere_t, each
-// lane for the few candidates queued for it.
+// one (lane, cluster) list per warp; at level 2 every lane takes ONE pair of
+// that list and tests the cluster's members with the owner's constants from a
+// shared ray table, so that lanes with many candidates do not hold the warp
+// back and the per-pair set-up is paid once per 32 pairs; level 3 is the exact
+// sphere_t, each lane for the few candidates queued for it.
 //
 // Compounds.  A bounded convex body can only be hit where the ray passes its
 // bounding sphere (inflated on the host well beyond rounding); survivors go
-// through the slab test above (eight lanes per body), and what remains is
-// evaluated exactly, again by eight lanes per body (eval_body_exact).  Unbounded
-// bodies always pass the bounding test.
+// through the slab test above (one lane per listed pair), and what remains is
+// evaluated exactly by eight lanes per body, one leaf each (eval_body_exact).
+// Unbounded bodies always pass the bounding test.
 //
 // Nothing in here crosses a warp: every warp of the block runs through Scene::intersect on its
 // own (with the body evaluation shared by the whole block through a task list and two block
@@ -712,11 +713,11 @@ __device__ __forceinline__ float eval_body_exact(const float4 *leaves, uint32_t 
 //
 // DEEP: scenes of a thousand spheres or more carry a third level, bounds over groups of eight
 // clusters (of eight spheres each).  The uniform scan then runs over the groups; a lane's
-// candidate groups are listed as (lane, group) pairs and eight lanes test the eight cluster bounds
-// of one pair with the owner's constants, exactly as they test the members of a cluster one level
-// down; the surviving (lane, cluster) pairs collect in a short list that is drained four pairs at
-// a time into the member tests.  4096 random spheres: 64 + ~80 + ~150 pre-tests per ray instead of
-// 256 + ~300 with two levels.
+// candidate groups are listed as (lane, group) pairs and every lane tests the eight cluster bounds
+// of one pair with the owner's constants, exactly as the members of a cluster are tested one level
+// down; the surviving (lane, cluster) pairs collect in a short list that is drained 32 pairs at a
+// time into the member tests.  4096 random spheres: 64 + ~80 + ~150 pre-tests per ray instead of
+// 256 + ~300 with two levels (1842 -> 2500 Mrays/s together with the one-lane-per-pair walks).
 template <bool GLOBAL_K, bool DEEP>
 __device__ __forceinline__ Hit intersect_scene(const Ray &ray, bool live = true) {
     const PrimTables &tb = tables();
