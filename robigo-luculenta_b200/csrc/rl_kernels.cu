@@ -458,6 +458,14 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
     const uint32_t ring_cap = block_ring ? block_ring_entries(threads, shrink) : 0u;
     const size_t smem = trace_kernel_smem_bytes(sc, threads, ring_cap);
     if (cached.threads != threads || cached.smem != smem) {
+        // the occupancy the runtime reports counts with the carve-out in force, i.e. the one the
+        // PREVIOUS launch shape asked for (after one big launch -- a single CTA per SM, 67 % -- the
+        // small launches were told that only one of their CTAs fits, and ran at two thirds of their
+        // rate): ask with the largest carve-out, set_carveout below lowers it to what is needed
+        if (cached.pct != 100) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cached.pct = 100;
+        }
         int occ = 0;
         err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
         if (err != cudaSuccess) return err;
