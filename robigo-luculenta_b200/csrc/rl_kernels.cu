@@ -424,7 +424,8 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
         if (!block_ring) return trace_kernel_smem_bytes(sc, t, 0) <= (size_t)max_smem ? 0 : -1;
         int best = -1;
         size_t best_ctas = 0;
-        for (int shrink = 0; shrink <= 2; shrink++) {
+        const int forced = env_int("RL_TRACE_RING_SHRINK", -1);      // experiments: a half (1) or a quarter (2) of the ring
+        for (int shrink = forced >= 0 && forced <= 2 ? forced : 0; shrink <= 2; shrink++) {
             const size_t bytes = trace_kernel_smem_bytes(sc, t, block_ring_entries(t, shrink));
             if (bytes > (size_t)max_smem) continue;
             const size_t ctas = trace_ctas_per_sm(bytes, t);
@@ -454,6 +455,9 @@ cudaError_t launch_trace(const DevScene &sc, const TraceLaunch &p, int sm_count,
         threads = small_cta;
         shrink = pick_ring(threads);
         if (shrink < 0) return cudaErrorInvalidValue;
+        // two CTAs per SM leave 16 KB of the 228 for L1 (spills, material and exact sphere records):
+        // half a ring each gives some of it back (+1.2 % on the replay, profiles/r2_ring_knobs.txt)
+        if (block_ring && shrink == 0 && env_int("RL_TRACE_RING_SHRINK", -1) < 0) shrink = 1;
     }
     const uint32_t ring_cap = block_ring ? block_ring_entries(threads, shrink) : 0u;
     const size_t smem = trace_kernel_smem_bytes(sc, threads, ring_cap);
@@ -664,10 +668,27 @@ cudaError_t launch_splat(const rl_mapped_photon *records, uint64_t n, float4 *ac
     int per_sm = 0;
     {
         std::lock_guard<std::mutex> guard(attr_lock);
-        cudaError_t err = cudaFuncSetAttribute(splat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err == cudaSuccess)
-            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, splat_kernel, RL_SPLAT_THREADS, smem);
+        // what the attribute calls last set, per device (thousands of plot() calls per second)
+        static size_t cached_smem[16] = {};
+        static int cached_per_sm[16] = {};
+        int dev = 0;
+        cudaError_t err = cudaGetDevice(&dev);
         if (err != cudaSuccess) return err;
+        if (dev < 0 || dev >= 16 || cached_smem[dev] != smem) {
+            err = cudaFuncSetAttribute(splat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            // the splat runs beside trace blocks that hold the SM at its largest shared-memory
+            // configuration: ask for the same one, so that placing a splat block never waits
+            // for the SM to change its split
+            const int carve = env_int("RL_SPLAT_CARVEOUT", 100);
+            if (err == cudaSuccess && carve >= 0)
+                err = cudaFuncSetAttribute(splat_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            if (err == cudaSuccess)
+                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, splat_kernel, RL_SPLAT_THREADS, smem);
+            if (err != cudaSuccess) return err;
+            if (dev >= 0 && dev < 16) { cached_smem[dev] = smem; cached_per_sm[dev] = per_sm; }
+        } else {
+            per_sm = cached_per_sm[dev];
+        }
         if (per_sm < 1) per_sm = 1;
         // one block per SM: eight consumer warps keep up with the stream, and fewer reductions in
         // flight at once measured slightly faster than two or three blocks (tools/splat_probe.py)

@@ -8,6 +8,7 @@ cp $LIB /tmp/librl_b200.keep
 mkdir -p gpurun_out
 : > gpurun_out/${TAG}_ab.txt
 for v in variants/*.so; do
+  [ -f "$v" ] || continue
   cp $v $LIB; touch $LIB
   echo "== $v" | tee -a gpurun_out/${TAG}_ab.txt
   timeout 300 python tools/config_rates.py 2>&1 | tail -1 | tee -a gpurun_out/${TAG}_ab.txt
