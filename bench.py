@@ -19,7 +19,8 @@ does is check that exchange against a sequential gather and a single-GPU render
 pushed through the reference host's own call pattern with host buffers (strict mode:
 host/rl_replay.cpp replays app.rs / task_scheduler.rs against the C ABI: 524 288-photon
 TraceUnit::render calls from C worker threads, every MappedPhoton batch copied to the host,
-buffer.raw written after every gather, the idle task sleeping the reference's 100 ms).
+GatherUnit::save called after every gather (device-side snapshot; the file is rewritten at
+most every 0.1 s and once more at the end), the idle task sleeping the reference's 100 ms).
 """
 from __future__ import annotations
 
@@ -570,7 +571,7 @@ def main():
                            "(host/rl_replay.cpp; app.rs:95-164, task_scheduler.rs:91-182): 524 288-photon "
                            "TraceUnit::render calls, each a launch that shares the SMs with the other units' launches, every batch of records copied "
                            "into the unit's host Vec, PlotUnit::plot / GatherUnit::accumulate consuming the units' "
-                           "device copies, buffer.raw saved after every gather, tonemap at the end; 16 B per photon "
+                           "device copies, GatherUnit::save after every gather (device-side snapshot, file rewritten at most every 0.1 s and at the end), tonemap at the end; 16 B per photon "
                            "cross PCIe to the host, which is what bounds this mode on several GPUs of one host "
                            "(profiles/r2_pcie_probe_8gpu.jsonl: 92 GB/s device-to-host in all with 8 GPUs copying)"
                            + ("; ranks' frames summed onto rank 0" if world > 1 else ""))
